@@ -1,0 +1,164 @@
+/* pistachio_b200 -- C ABI of the B200-native transfer-matrix (TMM) hot path.
+ *
+ * This is the drop-in boundary for the path BASELINE.json's north_star names.  The
+ * reference (garrekstemo/pistachio, src/pistachio/transfer_matrix.py, "tm.py" below)
+ * is pure Python and has no FFI; each entry point states the reference method(s) it
+ * replaces.  INTEGRATION.md shows the ctypes stubs a maintainer of the reference
+ * would add inside those methods.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative PST_E_* code; the message of
+ *    the last failure on the calling thread is pst_last_error().  No C++ exceptions
+ *    and no torch types cross this boundary: plain pointers and sizes only.
+ *  - pointers marked [dev] are CUDA device pointers on the handle's device, [host]
+ *    are ordinary host pointers.  The library never frees or retains caller buffers
+ *    (small [host] metadata is copied during the call).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Work
+ *    is enqueued asynchronously; the caller synchronises.  A handle owns device
+ *    scratch memory and must be used from one stream at a time.
+ *  - complex numbers are interleaved (re, im) doubles, numpy complex128 layout.
+ *  - polarisation codes: PST_POL_S / PST_POL_P, the reference's "s-wave"/"p-wave".
+ *  - angles are radians; wavelengths and thicknesses share one (arbitrary) unit.
+ *  - result layout of grid evaluations: [sweep][pol][wavelength][theta], theta fastest.
+ */
+#ifndef PISTACHIO_B200_H
+#define PISTACHIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PST_ABI_VERSION 1
+
+#define PST_OK 0
+#define PST_E_INVALID (-1)  /* bad argument */
+#define PST_E_CUDA (-2)     /* CUDA runtime error (message has the cudaError string) */
+#define PST_E_NOMEM (-3)    /* host or device allocation failed */
+#define PST_E_NODEVICE (-4) /* no usable sm_100 device */
+
+#define PST_POL_S 1u /* "s-wave" */
+#define PST_POL_P 2u /* "p-wave" */
+
+/* flags of pst_grid_args */
+#define PST_FLAG_FORCE_POINT_KERNEL (1u << 0) /* always one thread per point (K1) */
+#define PST_FLAG_FORCE_DEEP_KERNEL (1u << 1)  /* always the layer-parallel scan kernel (K2) */
+#define PST_FLAG_NUMERIC_DET (1u << 2)        /* T = Re(det(M) |t|^2) with det from the computed matrix, as
+                                                 tm.py:486 does, instead of the closed form a_last/a_first */
+#define PST_FLAG_NO_SMEM_STAGING (1u << 3)    /* read the optical table from global memory (debug/ablation) */
+
+typedef struct pst_handle_s* pst_handle_t;
+
+/* ---- lifetime ------------------------------------------------------------------------------------- */
+int pst_abi_version(void);
+const char* pst_last_error(void);
+/* Bind a handle to CUDA device `device`.  Fails with PST_E_NODEVICE when no GPU is visible:
+ * there is no CPU fallback anywhere in this library. */
+int pst_create(int device, pst_handle_t* out);
+int pst_destroy(pst_handle_t h);
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t pst_launch_count(pst_handle_t h);
+
+/* ---- K0: dispersion-table lookup ------------------------------------------------------------------
+ * Replaces Layer.make_datapoints (tm.py:117-170): resample n_tab (lambda, n, k) tables onto the grid
+ * wl[n_wl].  Table t occupies rows tab_off[t] .. tab_off[t+1]-1 of tab_wl/tab_n/tab_k and must be sorted
+ * by wavelength (the host wrapper applies interp1d's stable sort).  A one-row table is broadcast
+ * (tm.py:158-162); otherwise linear inter/extrapolation with scipy's two-term formula
+ *   y = ((x-x_lo)/(x_hi-x_lo))*y_hi + ((x_hi-x)/(x_hi-x_lo))*y_lo,  i_hi = clip(lower_bound(x), 1, rows-1),
+ * evaluated without FMA contraction so the result is bit-identical to the reference's.
+ * out_n, out_k: [n_tab][n_wl]. */
+int pst_resample_tables(pst_handle_t h, int n_tab, const int* tab_off /*[host] n_tab+1*/,
+                        const double* tab_wl /*[dev]*/, const double* tab_n /*[dev]*/, const double* tab_k /*[dev]*/,
+                        const double* wl /*[dev]*/, int n_wl, double* out_n /*[dev]*/, double* out_k /*[dev]*/,
+                        void* stream);
+
+/* ---- K1/K2/K3: fused matrix build + ordered chain + R/T/A over a (sweep, pol, lambda, theta) grid -----
+ * Replaces, for every grid point at once, the reference call sequence
+ *   Structure.calculate_layer_matrices(theta, pol)      tm.py:516-534  (-> Layer.calculate_transfer_matrix 236-277)
+ *   Structure.calculate_all_transfer_matrices(...)      tm.py:536-572  (M = D_0^-1 (M_1..M_{N-2}) D_{N-1})
+ *   Structure.calculate_all_t_r(M)                      tm.py:490-514  (t = 1/M00, r = M10/M00, R, T)
+ * and the fan-out over angles Structure.angle_resolved_spectra (tm.py:597-628).
+ * The reference model is kept: the same theta in every layer (no Snell refraction, tm.py:209,212,270). */
+typedef struct pst_grid_args {
+  size_t struct_size; /* = sizeof(pst_grid_args) */
+  int n_wl;           /* wavelengths */
+  int n_theta;        /* incidence angles */
+  int n_mat;          /* distinct (n,k) columns */
+  int n_layers;       /* layers including the incidence (0) and exit (n_layers-1) media; >= 2 */
+  int n_sweep;        /* thickness-sweep length; 1 when sweep_layer < 0 */
+  int sweep_layer;    /* index of the interior layer whose thickness takes sweep_d[...]; -1 = none */
+  unsigned pol_mask;  /* PST_POL_S | PST_POL_P; output pol axis has popcount(pol_mask) entries, s first */
+  unsigned flags;
+  const double* wl;        /* [dev] n_wl */
+  const double* theta;     /* [dev] n_theta, radians */
+  const double* cos_theta; /* [dev] n_theta or NULL.  When given it is used instead of cos(theta[i]) so a host
+                              that already evaluated np.cos (as tm.py:209,270 do) gets the same bits */
+  const double* mat_n;     /* [dev] [n_mat][n_wl] real index on the grid */
+  const double* mat_k;     /* [dev] [n_mat][n_wl] extinction coefficient (k > 0 absorbs) */
+  const int* layer_mat;    /* [host] n_layers: column of mat_n/mat_k used by each layer */
+  const double* layer_d;   /* [host] n_layers: thickness (entries 0 and n_layers-1 are ignored, tm.py:561-563) */
+  const double* sweep_d;   /* [dev] n_sweep or NULL */
+  double* R;               /* [dev] outputs [n_sweep][n_pol][n_wl][n_theta]; any may be NULL */
+  double* T;
+  double* A;               /* A = 1 - R - T (not computed by the reference; north_star) */
+  double* M;               /* [dev] or NULL: total 2x2 matrices, complex128 [n_sweep][n_pol][n_wl][n_theta][2][2] */
+} pst_grid_args;
+
+int pst_eval_grid(pst_handle_t h, const pst_grid_args* args, void* stream);
+
+/* Same computation with HOST buffers: wl, theta, cos_theta, mat_n, mat_k, sweep_d and the outputs are host
+ * pointers (pinned memory recommended).  The wavelength axis is cut into chunks whose device->host copies overlap
+ * the next chunk's kernels on internal streams.  Blocks until the results are in host memory.  This is the call
+ * bench.py times as `e2e`. */
+int pst_eval_grid_host(pst_handle_t h, const pst_grid_args* args_with_host_pointers);
+
+/* ---- per-layer matrices (API parity) ------------------------------------------------------------------
+ * Replaces Layer.calculate_all_transfer_matrices / calculate_transfer_matrix (tm.py:236-305) incl.
+ * dynamical_matrix (190-215) and propagation_matrix (217-234): for each wavelength the four 2x2 matrices
+ * [D, P, D^-1, M].  out: complex128 [n_wl][4][2][2].  cos_theta as in pst_grid_args (pass cos(theta)). */
+int pst_layer_matrices(pst_handle_t h, const double* n_re /*[dev]*/, const double* n_im /*[dev]*/,
+                       const double* wl /*[dev]*/, int n_wl, double theta, double cos_theta, unsigned pol,
+                       double thickness, double* out /*[dev]*/, void* stream);
+
+/* Replaces Layer.propagation_matrix (tm.py:217-234) for explicit (kx, d): out complex128 [n][2][2]. */
+int pst_propagation_matrices(pst_handle_t h, const double* kx /*[dev] complex n*/, int n, double thickness,
+                             double* out /*[dev]*/, void* stream);
+
+/* Replaces Layer.calculate_wavenumbers (tm.py:172-188): kx = n w/c cos(theta), kz = n w/c sin(theta);
+ * outputs complex128 [n_wl]. */
+int pst_wavenumbers(pst_handle_t h, const double* n_re /*[dev]*/, const double* n_im /*[dev]*/,
+                    const double* wl /*[dev]*/, int n_wl, double cos_theta, double sin_theta,
+                    double* kx /*[dev]*/, double* kz /*[dev]*/, void* stream);
+
+/* Replaces Structure.calculate_t_r / calculate_all_t_r (tm.py:464-514) for caller-supplied matrices:
+ * M complex128 [n][2][2] -> T[n], R[n] with T = Re(det(M) |1/M00|^2), R = |M10/M00|^2. */
+int pst_t_r_from_matrices(pst_handle_t h, const double* M /*[dev]*/, int64_t n, double* T /*[dev]*/,
+                          double* R /*[dev]*/, void* stream);
+
+/* Replaces the per-wavelength chain of Structure.calculate_all_transfer_matrices (tm.py:559-568) for explicit,
+ * already-built layer matrices (the reference's cached Layer.transfer_matrices): for each wavelength i
+ *   acc = I;  for j = n_interior-1 .. 0: acc = interior[j][i] . acc;   out[i] = first_inv[i] . (acc . last_d[i]).
+ * first_inv, last_d, out: complex128 [n_wl][2][2]; interior: complex128 [n_interior][n_wl][2][2] (may be NULL
+ * when n_interior == 0). */
+int pst_chain_matrices(pst_handle_t h, const double* first_inv /*[dev]*/, const double* interior /*[dev]*/,
+                       const double* last_d /*[dev]*/, int n_interior, int n_wl, double* out /*[dev]*/, void* stream);
+
+/* Fresnel coefficients and interface matrices (tm.py:730-751; unused by the reference's own chain but part of
+ * the path's vocabulary): for n pairs, out_rt complex128 [n][4] = (r_s, t_s, r_p, t_p); out_D (optional)
+ * complex128 [n][2 (s,p)][2][2] = (1/t)[[1,r],[r,1]]. */
+int pst_fresnel(pst_handle_t h, const double* n1 /*[dev] complex n*/, const double* n2, const double* k1x,
+                const double* k2x, int64_t n, double* out_rt /*[dev]*/, double* out_D /*[dev] or NULL*/, void* stream);
+
+/* ---- measurement helpers ------------------------------------------------------------------------------ */
+/* Independent-DFMA micro-benchmark: the measured FP64 (non-tensor) peak used as the roofline denominator.
+ * Runs `iters` dependent FMAs on 8 independent chains per thread over a full-chip grid, returns TFLOP/s. */
+int pst_fp64_peak_probe(pst_handle_t h, int iters, double* tflops_out, void* stream);
+/* Overwrite a scratch buffer larger than L2 (flushes L2 between timed iterations). */
+int pst_flush_l2(pst_handle_t h, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PISTACHIO_B200_H */

@@ -1,0 +1,528 @@
+// C ABI of libpistachio_b200.so (declared in include/pistachio_b200.h).
+// Host-side responsibilities only: argument validation, scratch memory, kernel-variant choice,
+// launch geometry, and the host-buffer pipeline.  No CPU implementation of any numeric step lives here.
+#include "../../include/pistachio_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pst_kernels.cuh"
+
+using namespace pst;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define PST_CUDA(call)                                                                              \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return fail(PST_E_CUDA, std::string(#call) + ": " + cudaGetErrorName(e__) + " - " + cudaGetErrorString(e__)); \
+  } while (0)
+
+#define PST_TRY(expr)          \
+  do {                         \
+    int rc__ = (expr);         \
+    if (rc__ != PST_OK) return rc__; \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  int ensure(size_t n) {
+    if (n <= cap) return PST_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max(n, (size_t)256);
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e != cudaSuccess) return fail(PST_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    cap = want;
+    return PST_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct pst_handle_s {
+  int device = 0;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  int64_t launches = 0;
+  DevBuf<double> opt;
+  DevBuf<double2> trig;
+  DevBuf<LayerEntry> layers_dev;
+  std::vector<LayerEntry> layers_host;  // what layers_dev currently holds
+  DevBuf<int> taboff;
+  DevBuf<unsigned char> l2buf;
+  DevBuf<double> sink;
+  // host-buffer pipeline (pst_eval_grid_host)
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  DevBuf<double> hp_in;       // wl | theta | cos | mat_n | mat_k | sweep_d
+  DevBuf<double> hp_out[2];   // per-chunk R|T|A (|M)
+};
+
+// ------------------------------------------------------------------------------------------------ lifetime
+extern "C" int pst_abi_version(void) { return PST_ABI_VERSION; }
+extern "C" const char* pst_last_error(void) { return g_err.c_str(); }
+
+extern "C" int pst_create(int device, pst_handle_t* out) {
+  if (!out) return fail(PST_E_INVALID, "pst_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(PST_E_NODEVICE, std::string("pst_create: no CUDA device visible (") + cudaGetErrorString(e) +
+                                    "); this library has no CPU fallback");
+  if (device < 0 || device >= count) return fail(PST_E_INVALID, "pst_create: device ordinal out of range");
+  cudaDeviceProp prop;
+  PST_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(PST_E_NODEVICE, std::string("pst_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                    std::to_string(prop.minor) + "; this build carries sm_100a code only");
+  pst_handle_s* h = new (std::nothrow) pst_handle_s();
+  if (!h) return fail(PST_E_NOMEM, "pst_create: out of host memory");
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  *out = h;
+  return PST_OK;
+}
+
+extern "C" int pst_destroy(pst_handle_t h) {
+  if (!h) return PST_OK;
+  DeviceGuard g(h->device);
+  cudaDeviceSynchronize();
+  h->opt.release(); h->trig.release(); h->layers_dev.release(); h->taboff.release(); h->l2buf.release();
+  h->sink.release(); h->hp_in.release(); h->hp_out[0].release(); h->hp_out[1].release();
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+  }
+  if (h->s_compute) cudaStreamDestroy(h->s_compute);
+  if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  delete h;
+  return PST_OK;
+}
+
+extern "C" int64_t pst_launch_count(pst_handle_t h) { return h ? h->launches : -1; }
+
+// ------------------------------------------------------------------------------------------------ K0
+extern "C" int pst_resample_tables(pst_handle_t h, int n_tab, const int* tab_off, const double* tab_wl,
+                                   const double* tab_n, const double* tab_k, const double* wl, int n_wl,
+                                   double* out_n, double* out_k, void* stream) {
+  if (!h) return fail(PST_E_INVALID, "pst_resample_tables: NULL handle");
+  if (n_tab <= 0 || n_wl <= 0) return fail(PST_E_INVALID, "pst_resample_tables: n_tab and n_wl must be positive");
+  if (!tab_off || !tab_wl || !tab_n || !tab_k || !wl || !out_n || !out_k)
+    return fail(PST_E_INVALID, "pst_resample_tables: NULL pointer argument");
+  if (n_tab > 65535) return fail(PST_E_INVALID, "pst_resample_tables: at most 65535 tables per call");
+  int max_rows = 0;
+  for (int t = 0; t < n_tab; ++t) {
+    int rows = tab_off[t + 1] - tab_off[t];
+    if (rows < 1) return fail(PST_E_INVALID, "pst_resample_tables: every table needs at least one row");
+    max_rows = std::max(max_rows, rows);
+  }
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  PST_TRY(h->taboff.ensure(n_tab + 1));
+  PST_CUDA(cudaMemcpyAsync(h->taboff.p, tab_off, (n_tab + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  const size_t smem = (size_t)max_rows * sizeof(double) <= 32 * 1024 ? (size_t)max_rows * sizeof(double) : 0;
+  dim3 grid((n_wl + 255) / 256, n_tab);
+  resample_kernel<<<grid, 256, smem, st>>>(n_tab, h->taboff.p, tab_wl, tab_n, tab_k, wl, n_wl, out_n, out_k);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ grid
+namespace {
+
+using ChainKernel = void (*)(const GridParams);
+
+template <int NPOL, int NCOL, bool SO, bool SL, bool SEG>
+ChainKernel chain_variant() {
+  return tmm_chain_kernel<NPOL, NCOL, SO, SL, SEG>;
+}
+
+ChainKernel pick_chain(int npol, int ncol, bool so, bool sl, bool seg) {
+#define PST_V(P, C, O, L, S) \
+  if (npol == P && ncol == C && so == O && sl == L && seg == S) return chain_variant<P, C, O, L, S>();
+#define PST_V4(P, C)                                                                          \
+  PST_V(P, C, true, true, false) PST_V(P, C, true, false, false) PST_V(P, C, false, true, false) \
+  PST_V(P, C, false, false, false) PST_V(P, C, true, true, true) PST_V(P, C, true, false, true)  \
+  PST_V(P, C, false, true, true) PST_V(P, C, false, false, true)
+  PST_V4(1, 1) PST_V4(1, 2) PST_V4(2, 1) PST_V4(2, 2)
+#undef PST_V4
+#undef PST_V
+  return nullptr;
+}
+
+int validate_grid(const pst_grid_args* a, const char* who) {
+  std::string w(who);
+  if (!a) return fail(PST_E_INVALID, w + ": args is NULL");
+  if (a->struct_size != sizeof(pst_grid_args))
+    return fail(PST_E_INVALID, w + ": struct_size mismatch (header/library ABI skew)");
+  if (a->n_wl <= 0 || a->n_theta <= 0 || a->n_mat <= 0) return fail(PST_E_INVALID, w + ": n_wl, n_theta, n_mat must be positive");
+  if (a->n_layers < 2) return fail(PST_E_INVALID, w + ": a structure needs at least an incidence and an exit layer (n_layers >= 2)");
+  if (a->pol_mask == 0 || (a->pol_mask & ~3u)) return fail(PST_E_INVALID, w + ": pol_mask must be PST_POL_S, PST_POL_P or both");
+  if (!a->wl || !a->mat_n || !a->mat_k || !a->layer_mat || !a->layer_d) return fail(PST_E_INVALID, w + ": NULL input pointer");
+  if (!a->theta && !a->cos_theta) return fail(PST_E_INVALID, w + ": theta and cos_theta are both NULL");
+  if (!a->R && !a->T && !a->A && !a->M) return fail(PST_E_INVALID, w + ": no output requested");
+  if (a->sweep_layer >= 0) {
+    if (a->sweep_layer < 1 || a->sweep_layer > a->n_layers - 2)
+      return fail(PST_E_INVALID, w + ": sweep_layer must be an interior layer");
+    if (a->n_sweep <= 0 || !a->sweep_d) return fail(PST_E_INVALID, w + ": sweep needs n_sweep > 0 and sweep_d");
+  } else if (a->n_sweep != 1) {
+    return fail(PST_E_INVALID, w + ": n_sweep must be 1 without a sweep_layer");
+  }
+  if ((a->flags & PST_FLAG_FORCE_POINT_KERNEL) && (a->flags & PST_FLAG_FORCE_DEEP_KERNEL))
+    return fail(PST_E_INVALID, w + ": contradictory kernel flags");
+  if ((a->flags & PST_FLAG_NUMERIC_DET) && !a->M) return fail(PST_E_INVALID, w + ": PST_FLAG_NUMERIC_DET needs the matrix output M");
+  for (int j = 0; j < a->n_layers; ++j)
+    if (a->layer_mat[j] < 0 || a->layer_mat[j] >= a->n_mat) return fail(PST_E_INVALID, w + ": layer_mat entry out of range");
+  if ((long long)a->n_wl * a->n_theta > (1LL << 40)) return fail(PST_E_INVALID, w + ": grid too large");
+  return PST_OK;
+}
+
+// Upload the layer list when it differs from what the device copy holds.
+int sync_layers(pst_handle_t h, const pst_grid_args* a, cudaStream_t st) {
+  std::vector<LayerEntry> cur(a->n_layers);
+  for (int j = 0; j < a->n_layers; ++j) cur[j] = LayerEntry{a->layer_d[j], a->layer_mat[j], 0};
+  const bool same = cur.size() == h->layers_host.size() &&
+                    std::memcmp(cur.data(), h->layers_host.data(), cur.size() * sizeof(LayerEntry)) == 0;
+  if (same) return PST_OK;
+  PST_TRY(h->layers_dev.ensure(cur.size()));
+  PST_CUDA(cudaMemcpyAsync(h->layers_dev.p, cur.data(), cur.size() * sizeof(LayerEntry), cudaMemcpyHostToDevice, st));
+  h->layers_host.swap(cur);
+  return PST_OK;
+}
+
+// opt table + trig table for the whole grid (device pointers)
+int run_prep(pst_handle_t h, const pst_grid_args* a, const double* wl, const double* theta, const double* cos_theta,
+             const double* mat_n, const double* mat_k, cudaStream_t st) {
+  const long long nm = (long long)a->n_wl * a->n_mat;
+  PST_TRY(h->opt.ensure((size_t)nm * 6));
+  PST_TRY(h->trig.ensure(a->n_theta));
+  prep_optical_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(wl, mat_n, mat_k, a->n_wl, a->n_mat, h->opt.p);
+  PST_CUDA(cudaGetLastError());
+  prep_trig_kernel<<<(a->n_theta + 255) / 256, 256, 0, st>>>(theta, cos_theta, a->n_theta, h->trig.p);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 2;
+  return PST_OK;
+}
+
+struct ChainPlan {
+  int npol, ncol, W, PB, tl;
+  bool so, sl, seg;
+  size_t smem;
+  ChainKernel fn;
+};
+
+int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPlan* pl) {
+  pl->npol = __builtin_popcount(a->pol_mask);
+  pl->ncol = a->M ? 2 : 1;
+  const int Li = a->n_layers - 2;
+  const long long threads1 = (long long)n_wl_launch * a->n_theta * a->n_sweep;
+  int W = 1;
+  if (a->flags & PST_FLAG_FORCE_DEEP_KERNEL) {
+    W = 8;
+  } else if (!(a->flags & PST_FLAG_FORCE_POINT_KERNEL)) {
+    const long long want = (long long)h->sm_count * 512;
+    if (threads1 < want && Li >= 128) {
+      while (W < 16 && threads1 * W < want && Li / (2 * W) >= 32) W *= 2;
+    }
+  }
+  W = std::max(1, std::min(W, std::max(Li, 1)));
+  pl->W = W;
+  pl->seg = W > 1;
+  pl->PB = pl->seg ? 32 : 128;
+  pl->tl = std::min(n_wl_launch, (pl->PB - 1) / a->n_theta + 2);
+  const size_t budget = std::min<size_t>(h->smem_optin, 200 * 1024);
+  const size_t seg_bytes = pl->seg ? (size_t)W * pl->npol * 9 * pl->PB * sizeof(double) : 0;
+  const size_t lay_bytes = (size_t)a->n_layers * sizeof(LayerEntry);
+  const size_t opt_bytes = (size_t)a->n_mat * 6 * pl->tl * sizeof(double);
+  pl->sl = lay_bytes <= 64 * 1024 && seg_bytes + lay_bytes <= budget;
+  size_t used = seg_bytes + (pl->sl ? lay_bytes : 0);
+  pl->so = !(a->flags & PST_FLAG_NO_SMEM_STAGING) && used + opt_bytes <= std::min<size_t>(budget, 96 * 1024);
+  used += pl->so ? opt_bytes : 0;
+  if (used > budget) return fail(PST_E_INVALID, "pst_eval_grid: shared-memory plan exceeds the device limit");
+  pl->smem = used;
+  pl->fn = pick_chain(pl->npol, pl->ncol, pl->so, pl->sl, pl->seg);
+  if (!pl->fn) return fail(PST_E_INVALID, "pst_eval_grid: no kernel variant for this configuration");
+  if (used > 48 * 1024) PST_CUDA(cudaFuncSetAttribute((const void*)pl->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+  return PST_OK;
+}
+
+// Launch the chain kernel for wavelengths [il0, il0 + n_wl_launch) of the prepared grid.  Output pointers address
+// the first element of that wavelength window; `plane` is the element distance between (sweep, pol) planes.
+int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, int il0, int n_wl_launch,
+                 const double* sweep_d_dev, double* R, double* T, double* A, double* M, cudaStream_t st) {
+  GridParams prm;
+  prm.n_wl = a->n_wl;
+  prm.n_theta = a->n_theta;
+  prm.n_mat = a->n_mat;
+  prm.n_layers = a->n_layers;
+  prm.sweep_layer = a->sweep_layer;
+  prm.pol_first = (a->pol_mask & PST_POL_S) ? 0 : 1;
+  prm.tl_stride = pl.tl;
+  prm.flags = a->flags;
+  prm.il0 = il0;
+  prm.points = (long long)n_wl_launch * a->n_theta;
+  prm.opt = h->opt.p;
+  prm.trig = h->trig.p;
+  prm.layers = h->layers_dev.p;
+  const long long nblk = (prm.points + pl.PB - 1) / pl.PB;
+  if (nblk > 0x7fffffffLL) return fail(PST_E_INVALID, "pst_eval_grid: too many blocks");
+  const size_t per_sweep = (size_t)pl.npol * (size_t)prm.points;
+  for (int s0 = 0; s0 < a->n_sweep; s0 += 65535) {
+    const int ns = std::min(65535, a->n_sweep - s0);
+    prm.sweep_d = sweep_d_dev ? sweep_d_dev + s0 : nullptr;
+    prm.R = R ? R + (size_t)s0 * per_sweep : nullptr;
+    prm.T = T ? T + (size_t)s0 * per_sweep : nullptr;
+    prm.A = A ? A + (size_t)s0 * per_sweep : nullptr;
+    prm.M = M ? M + (size_t)s0 * per_sweep * 8 : nullptr;
+    dim3 grid((unsigned)nblk, (unsigned)ns), block(pl.PB, pl.W);
+    pl.fn<<<grid, block, pl.smem, st>>>(prm);
+    PST_CUDA(cudaGetLastError());
+    h->launches += 1;
+  }
+  return PST_OK;
+}
+
+}  // namespace
+
+extern "C" int pst_eval_grid(pst_handle_t h, const pst_grid_args* a, void* stream) {
+  if (!h) return fail(PST_E_INVALID, "pst_eval_grid: NULL handle");
+  PST_TRY(validate_grid(a, "pst_eval_grid"));
+  DeviceGuard g(h->device);
+  if (!g.ok) return fail(PST_E_CUDA, "pst_eval_grid: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  PST_TRY(sync_layers(h, a, st));
+  PST_TRY(run_prep(h, a, a->wl, a->theta, a->cos_theta, a->mat_n, a->mat_k, st));
+  ChainPlan pl;
+  PST_TRY(plan_chain(h, a, a->n_wl, &pl));
+  return launch_chain(h, a, pl, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, a->M, st);
+}
+
+extern "C" int pst_eval_grid_host(pst_handle_t h, const pst_grid_args* a) {
+  if (!h) return fail(PST_E_INVALID, "pst_eval_grid_host: NULL handle");
+  PST_TRY(validate_grid(a, "pst_eval_grid_host"));
+  DeviceGuard g(h->device);
+  if (!g.ok) return fail(PST_E_CUDA, "pst_eval_grid_host: cudaSetDevice failed");
+  if (!h->s_compute) {
+    PST_CUDA(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    PST_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      PST_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+      PST_CUDA(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t sc = h->s_compute, sd = h->s_copy;
+  const int npol = __builtin_popcount(a->pol_mask);
+  const size_t nwl = a->n_wl, nth = a->n_theta, nm = a->n_mat, nsw = a->n_sweep;
+  // ---- inputs: one device block, host -> device on the compute stream
+  const size_t in_elems = nwl + 2 * nth + 2 * nm * nwl + nsw;
+  PST_TRY(h->hp_in.ensure(in_elems));
+  double* d_wl = h->hp_in.p;
+  double* d_th = d_wl + nwl;
+  double* d_ct = d_th + nth;
+  double* d_n = d_ct + nth;
+  double* d_k = d_n + nm * nwl;
+  double* d_sw = d_k + nm * nwl;
+  PST_CUDA(cudaMemcpyAsync(d_wl, a->wl, nwl * 8, cudaMemcpyHostToDevice, sc));
+  if (a->theta) PST_CUDA(cudaMemcpyAsync(d_th, a->theta, nth * 8, cudaMemcpyHostToDevice, sc));
+  if (a->cos_theta) PST_CUDA(cudaMemcpyAsync(d_ct, a->cos_theta, nth * 8, cudaMemcpyHostToDevice, sc));
+  PST_CUDA(cudaMemcpyAsync(d_n, a->mat_n, nm * nwl * 8, cudaMemcpyHostToDevice, sc));
+  PST_CUDA(cudaMemcpyAsync(d_k, a->mat_k, nm * nwl * 8, cudaMemcpyHostToDevice, sc));
+  if (a->sweep_d) PST_CUDA(cudaMemcpyAsync(d_sw, a->sweep_d, nsw * 8, cudaMemcpyHostToDevice, sc));
+  PST_TRY(sync_layers(h, a, sc));
+  PST_TRY(run_prep(h, a, d_wl, a->theta ? d_th : nullptr, a->cos_theta ? d_ct : nullptr, d_n, d_k, sc));
+
+  // ---- wavelength chunks: kernel on s_compute, device -> host on s_copy, two output buffers in flight
+  const int n_out = (a->R ? 1 : 0) + (a->T ? 1 : 0) + (a->A ? 1 : 0) + (a->M ? 8 : 0);
+  const size_t row_elems = (size_t)nsw * npol * nth;               // result elements per wavelength and real output
+  const size_t target = (size_t)48 << 20;                          // ~48 MiB of results per chunk
+  size_t chunk = std::max<size_t>(1, target / std::max<size_t>(1, row_elems * n_out * 8));
+  chunk = std::min(chunk, nwl);
+  if (chunk < nwl) chunk = std::max<size_t>(1, (nwl + ((nwl + chunk - 1) / chunk) - 1) / ((nwl + chunk - 1) / chunk));
+  for (int b = 0; b < 2; ++b) PST_TRY(h->hp_out[b].ensure(row_elems * n_out * chunk));
+  int nchunk = 0;
+  for (size_t l0 = 0; l0 < nwl; l0 += chunk, ++nchunk) {
+    const int b = nchunk & 1;
+    const size_t cw = std::min(chunk, nwl - l0);
+    const size_t plane_c = cw * nth;           // chunk-local (sweep, pol) plane
+    const size_t plane_f = nwl * nth;          // plane in the caller's arrays
+    const size_t planes = nsw * npol;
+    double* base = h->hp_out[b].p;
+    double* dR = a->R ? base : nullptr; if (a->R) base += planes * plane_c;
+    double* dT = a->T ? base : nullptr; if (a->T) base += planes * plane_c;
+    double* dA = a->A ? base : nullptr; if (a->A) base += planes * plane_c;
+    double* dM = a->M ? base : nullptr;
+    if (nchunk >= 2) PST_CUDA(cudaStreamWaitEvent(sc, h->ev_copied[b], 0));
+    ChainPlan pl;
+    pst_grid_args loc = *a;
+    loc.R = dR; loc.T = dT; loc.A = dA; loc.M = dM;
+    PST_TRY(plan_chain(h, &loc, (int)cw, &pl));
+    PST_TRY(launch_chain(h, &loc, pl, (int)l0, (int)cw, a->sweep_d ? d_sw : nullptr, dR, dT, dA, dM, sc));
+    PST_CUDA(cudaEventRecord(h->ev_done[b], sc));
+    PST_CUDA(cudaStreamWaitEvent(sd, h->ev_done[b], 0));
+    auto copy_back = [&](double* host, const double* dev, size_t width) -> int {
+      // planes rows of `width*cw*nth` doubles; the caller's rows are plane_f*width apart
+      PST_CUDA(cudaMemcpy2DAsync(host + l0 * nth * width, plane_f * width * 8, dev, plane_c * width * 8,
+                                 plane_c * width * 8, planes, cudaMemcpyDeviceToHost, sd));
+      return PST_OK;
+    };
+    if (a->R) PST_TRY(copy_back(a->R, dR, 1));
+    if (a->T) PST_TRY(copy_back(a->T, dT, 1));
+    if (a->A) PST_TRY(copy_back(a->A, dA, 1));
+    if (a->M) PST_TRY(copy_back(a->M, dM, 8));
+    PST_CUDA(cudaEventRecord(h->ev_copied[b], sd));
+  }
+  PST_CUDA(cudaStreamSynchronize(sd));
+  PST_CUDA(cudaStreamSynchronize(sc));
+  return PST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ API-parity kernels
+extern "C" int pst_layer_matrices(pst_handle_t h, const double* n_re, const double* n_im, const double* wl, int n_wl,
+                                  double theta, double cos_theta, unsigned pol, double thickness, double* out,
+                                  void* stream) {
+  (void)theta;
+  if (!h) return fail(PST_E_INVALID, "pst_layer_matrices: NULL handle");
+  if (!n_re || !n_im || !wl || !out || n_wl <= 0) return fail(PST_E_INVALID, "pst_layer_matrices: bad argument");
+  if (pol != PST_POL_S && pol != PST_POL_P)
+    return fail(PST_E_INVALID, "pst_layer_matrices: Must specify 's-wave' or 'p-wave'.");
+  DeviceGuard g(h->device);
+  layer_matrices_kernel<<<(n_wl + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_re, n_im, wl, n_wl, cos_theta, pol,
+                                                                             thickness, out);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PST_OK;
+}
+
+extern "C" int pst_propagation_matrices(pst_handle_t h, const double* kx, int n, double thickness, double* out,
+                                        void* stream) {
+  if (!h) return fail(PST_E_INVALID, "pst_propagation_matrices: NULL handle");
+  if (!kx || !out || n <= 0) return fail(PST_E_INVALID, "pst_propagation_matrices: bad argument");
+  DeviceGuard g(h->device);
+  propagation_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(kx, n, thickness, out);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PST_OK;
+}
+
+extern "C" int pst_wavenumbers(pst_handle_t h, const double* n_re, const double* n_im, const double* wl, int n_wl,
+                               double cos_theta, double sin_theta, double* kx, double* kz, void* stream) {
+  if (!h) return fail(PST_E_INVALID, "pst_wavenumbers: NULL handle");
+  if (!n_re || !n_im || !wl || !kx || !kz || n_wl <= 0) return fail(PST_E_INVALID, "pst_wavenumbers: bad argument");
+  DeviceGuard g(h->device);
+  wavenumbers_kernel<<<(n_wl + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_re, n_im, wl, n_wl, cos_theta, sin_theta,
+                                                                          kx, kz);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PST_OK;
+}
+
+extern "C" int pst_t_r_from_matrices(pst_handle_t h, const double* M, int64_t n, double* T, double* R, void* stream) {
+  if (!h) return fail(PST_E_INVALID, "pst_t_r_from_matrices: NULL handle");
+  if (!M || !T || !R || n <= 0) return fail(PST_E_INVALID, "pst_t_r_from_matrices: bad argument");
+  DeviceGuard g(h->device);
+  t_r_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(M, n, T, R);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PST_OK;
+}
+
+extern "C" int pst_chain_matrices(pst_handle_t h, const double* first_inv, const double* interior, const double* last_d,
+                                  int n_interior, int n_wl, double* out, void* stream) {
+  if (!h) return fail(PST_E_INVALID, "pst_chain_matrices: NULL handle");
+  if (!first_inv || !last_d || !out || n_wl <= 0 || n_interior < 0 || (n_interior > 0 && !interior))
+    return fail(PST_E_INVALID, "pst_chain_matrices: bad argument");
+  DeviceGuard g(h->device);
+  chain_matrices_kernel<<<(n_wl + 127) / 128, 128, 0, (cudaStream_t)stream>>>(first_inv, interior, last_d, n_interior,
+                                                                             n_wl, out);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PST_OK;
+}
+
+extern "C" int pst_fresnel(pst_handle_t h, const double* n1, const double* n2, const double* k1x, const double* k2x,
+                           int64_t n, double* out_rt, double* out_D, void* stream) {
+  if (!h) return fail(PST_E_INVALID, "pst_fresnel: NULL handle");
+  if (!n1 || !n2 || !k1x || !k2x || !out_rt || n <= 0) return fail(PST_E_INVALID, "pst_fresnel: bad argument");
+  DeviceGuard g(h->device);
+  fresnel_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n1, n2, k1x, k2x, n, out_rt, out_D);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ measurement
+extern "C" int pst_fp64_peak_probe(pst_handle_t h, int iters, double* tflops_out, void* stream) {
+  if (!h || !tflops_out || iters <= 0) return fail(PST_E_INVALID, "pst_fp64_peak_probe: bad argument");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  PST_TRY(h->sink.ensure(1));
+  const int blocks = h->sm_count * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  PST_CUDA(cudaEventCreate(&e0));
+  PST_CUDA(cudaEventCreate(&e1));
+  dfma_probe_kernel<<<blocks, threads, 0, st>>>(iters / 8 + 1, 1.0, h->sink.p);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    PST_CUDA(cudaEventRecord(e0, st));
+    dfma_probe_kernel<<<blocks, threads, 0, st>>>(iters, 1.0, h->sink.p);
+    PST_CUDA(cudaEventRecord(e1, st));
+    PST_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    PST_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = 2.0 * 64.0 * (double)iters * (double)blocks * threads;  // 8 chains x 8 unrolled FMAs x 2 flop
+    best = std::max(best, flop / (ms * 1e-3) / 1e12);
+  }
+  PST_CUDA(cudaGetLastError());
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  h->launches += 6;
+  *tflops_out = best;
+  return PST_OK;
+}
+
+extern "C" int pst_flush_l2(pst_handle_t h, void* stream) {
+  if (!h) return fail(PST_E_INVALID, "pst_flush_l2: NULL handle");
+  DeviceGuard g(h->device);
+  const size_t bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+  PST_TRY(h->l2buf.ensure(bytes));
+  PST_CUDA(cudaMemsetAsync(h->l2buf.p, 0, bytes, (cudaStream_t)stream));
+  return PST_OK;
+}

@@ -1,0 +1,204 @@
+// Per-point arithmetic of the TMM chain: layer step, exact rescaling, ordered segment combine, epilogue.
+// Everything here is __host__ __device__ so that tests/host_emul can execute the same source on the CPU box;
+// the shipped library only ever calls it from kernels (pst_kernels.cuh).
+//
+// Model (reference tm.py:190-277, 559-568, 482-486), phi = kx d, a = n g with
+// g = cos(theta) for s-waves and 1/cos(theta) for p-waves (same theta in every layer: the reference has no Snell
+// refraction):
+//   M_j = D_j P_j D_j^-1 = [[cos phi, -i sin phi / a], [-i a sin phi, cos phi]]
+//   M   = D_0^-1 (M_1 ... M_{N-2}) D_{N-1},  t = 1/M00, r = M10/M00, R = |r|^2, T = Re(det M |t|^2)
+// Only the requested columns of M are propagated, from the exit side: v <- M_j v.
+#pragma once
+#include "pst_math.cuh"
+
+namespace pst {
+
+// State per polarisation and column: v = (v0.re, v0.im, v1.re, v1.im); true value = v * 2^kexp.
+template <int NPOL, int NC>
+struct ChainState {
+  double v[NPOL][NC][4];
+  int kexp[NPOL];
+};
+
+struct OptRow {  // optical constants of one (material, wavelength): q = (n w)(1/c), n, 1/n
+  double qr, qi, nr, ni, inr, ini;
+};
+
+template <int NPOL>
+PST_HD bool pol_is_s(int p, int pol_first) {
+  return (NPOL == 2) ? (p == 0) : (pol_first == 0);
+}
+
+// v <- M_j v for every polarisation/column held by the thread.  sincos of the real phase and cosh/sinh of the
+// attenuation are polarisation independent and evaluated once.
+template <int NPOL, int NC>
+PST_HD void apply_layer(ChainState<NPOL, NC>& st, const OptRow& o, double d, double ct, double ict, int pol_first) {
+  // phase in the reference's rounding order: kx = q cos(theta) (tm.py:270), argument = kx d (tm.py:234)
+  const double x = mul_rn(mul_rn(o.qr, ct), d);
+  double sx, cx;
+  sincos(x, &sx, &cx);
+  if (o.ni == 0.0) {
+    // lossless layer: phi and n real, M = [[c, -i s/(n g)], [-i s n g, c]]
+    const double sn = sx * o.nr, si = sx * o.inr;
+#pragma unroll
+    for (int p = 0; p < NPOL; ++p) {
+      const bool is_s = pol_is_s<NPOL>(p, pol_first);
+      const double al = (is_s ? ct : ict) * sn;  // a sin(phi)
+      const double be = (is_s ? ict : ct) * si;  // sin(phi) / a
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        double* v = st.v[p][c];
+        const double v0r = v[0], v0i = v[1], v1r = v[2], v1i = v[3];
+        v[0] = fma(cx, v0r, be * v1i);
+        v[1] = fma(cx, v0i, -(be * v1r));
+        v[2] = fma(cx, v1r, al * v0i);
+        v[3] = fma(cx, v1i, -(al * v0r));
+      }
+    }
+    return;
+  }
+  const double y = mul_rn(mul_rn(o.qi, ct), d);
+  double ch, sh;
+  const int sc = cosh_sinh_scaled(y, ch, sh);
+  // cos(x+iy) = cos x cosh y - i sin x sinh y ; sin(x+iy) = sin x cosh y + i cos x sinh y   (both times 2^sc)
+  const cplx cphi = {cx * ch, -(sx * sh)};
+  const cplx sphi = {sx * ch, cx * sh};
+  const cplx sn = cmul(sphi, {o.nr, o.ni});
+  const cplx si = cmul(sphi, {o.inr, o.ini});
+#pragma unroll
+  for (int p = 0; p < NPOL; ++p) {
+    const bool is_s = pol_is_s<NPOL>(p, pol_first);
+    const double g = is_s ? ct : ict, gi = is_s ? ict : ct;
+    const cplx m10 = {g * sn.im, -(g * sn.re)};    // -i a sin(phi)
+    const cplx m01 = {gi * si.im, -(gi * si.re)};  // -i sin(phi) / a
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      double* v = st.v[p][c];
+      const cplx v0 = {v[0], v[1]}, v1 = {v[2], v[3]};
+      v[0] = fma(cphi.re, v0.re, fma(-cphi.im, v0.im, fma(m01.re, v1.re, -(m01.im * v1.im))));
+      v[1] = fma(cphi.re, v0.im, fma(cphi.im, v0.re, fma(m01.re, v1.im, m01.im * v1.re)));
+      v[2] = fma(m10.re, v0.re, fma(-m10.im, v0.im, fma(cphi.re, v1.re, -(cphi.im * v1.im))));
+      v[3] = fma(m10.re, v0.im, fma(m10.im, v0.re, fma(cphi.re, v1.im, cphi.im * v1.re)));
+    }
+    st.kexp[p] += sc;
+  }
+}
+
+// Pull a power of two out of the state (exact) so that products cannot overflow in deep stop bands.
+template <int NPOL, int NC>
+PST_HD void renormalise(ChainState<NPOL, NC>& st) {
+#pragma unroll
+  for (int p = 0; p < NPOL; ++p) {
+    double m = 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) m = fmax(m, fabs(st.v[p][c][k]));
+    int e = exponent_of(m);
+    e = e > 1000 ? 1000 : (e < -1000 ? -1000 : e);
+    const double s = pow2i(-e);
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) st.v[p][c][k] *= s;
+    st.kexp[p] += e;
+  }
+}
+
+// Exit-medium columns D_f[:, c]:  s: (1, +-n_f cos)   p: (cos, +-n_f)                       (tm.py:209,212)
+template <int NPOL, int NC>
+PST_HD void init_exit_columns(ChainState<NPOL, NC>& st, double nfr, double nfi, double ct, int pol_first) {
+#pragma unroll
+  for (int p = 0; p < NPOL; ++p) {
+    const bool is_s = pol_is_s<NPOL>(p, pol_first);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double sg = c == 0 ? 1.0 : -1.0;
+      st.v[p][c][0] = is_s ? 1.0 : ct;
+      st.v[p][c][1] = 0.0;
+      st.v[p][c][2] = sg * (is_s ? nfr * ct : nfr);
+      st.v[p][c][3] = sg * (is_s ? nfi * ct : nfi);
+    }
+    st.kexp[p] = 0;
+  }
+}
+
+template <int NPOL>
+PST_HD void init_identity(ChainState<NPOL, 2>& st) {
+#pragma unroll
+  for (int p = 0; p < NPOL; ++p) {
+    st.v[p][0][0] = 1.0; st.v[p][0][1] = 0.0; st.v[p][0][2] = 0.0; st.v[p][0][3] = 0.0;
+    st.v[p][1][0] = 0.0; st.v[p][1][1] = 0.0; st.v[p][1][2] = 1.0; st.v[p][1][3] = 0.0;
+    st.kexp[p] = 0;
+  }
+}
+
+// v <- S v for one polarisation, S = [col0 col1] given as 8 doubles (a00, a10 | a01, a11) + exponent.
+template <int NPOL, int NC>
+PST_HD void apply_segment(ChainState<NPOL, NC>& st, int p, const double (&s)[8], int s_exp) {
+  const cplx a00 = {s[0], s[1]}, a10 = {s[2], s[3]}, a01 = {s[4], s[5]}, a11 = {s[6], s[7]};
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    double* v = st.v[p][c];
+    const cplx v0 = {v[0], v[1]}, v1 = {v[2], v[3]};
+    const cplx n0 = cadd(cmul(a00, v0), cmul(a01, v1));
+    const cplx n1 = cadd(cmul(a10, v0), cmul(a11, v1));
+    v[0] = n0.re; v[1] = n0.im; v[2] = n1.re; v[3] = n1.im;
+  }
+  st.kexp[p] += s_exp;
+}
+
+struct PointOut {
+  double R, T, A;
+  double M[8];  // row-major 2x2 complex, only filled when NCOL == 2
+};
+
+// Rows of D_0^-1, then t, r, R, T, A for one polarisation                            (tm.py:482-486, 568)
+//   D_0^-1 = 1/2 [[w0, w1], [w0, -w1]]:  s: w0 = 1, w1 = 1/(n_0 cos)    p: w0 = 1/cos, w1 = 1/n_0
+template <int NPOL, int NCOL>
+PST_HD PointOut finish_point(const ChainState<NPOL, NCOL>& fin, int p, double in0r, double in0i, double nfr, double nfi,
+                             double ict, int pol_first, unsigned flags) {
+  const bool is_s = pol_is_s<NPOL>(p, pol_first);
+  const double w0 = is_s ? 1.0 : ict;
+  const cplx w1 = is_s ? cplx{in0r * ict, in0i * ict} : cplx{in0r, in0i};
+  cplx m[NCOL][2];
+#pragma unroll
+  for (int c = 0; c < NCOL; ++c) {
+    const double* v = fin.v[p][c];
+    const cplx a = {0.5 * w0 * v[0], 0.5 * w0 * v[1]};
+    const cplx b = cscale(cmul(w1, {v[2], v[3]}), 0.5);
+    m[c][0] = cadd(a, b);  // M[0][c]
+    m[c][1] = csub(a, b);  // M[1][c]
+  }
+  PointOut out;
+  const double den = fma(m[0][0].re, m[0][0].re, m[0][0].im * m[0][0].im);  // |M00|^2 (scaled by 2^-2kexp)
+  const double num = fma(m[0][1].re, m[0][1].re, m[0][1].im * m[0][1].im);  // |M10|^2
+  out.R = num / den;
+  // det M = a_last / a_first = n_f / n_0 for both polarisations (the cos factors cancel)
+  const double det_re = fma(nfr, in0r, -(nfi * in0i));
+  out.T = ldexp(det_re / den, -2 * fin.kexp[p]);
+  if constexpr (NCOL == 2) {
+    if (flags & 4u) {
+      // numeric determinant like np.linalg.det (tm.py:486); the 2^kexp factors cancel
+      const cplx det = csub(cmul(m[0][0], m[1][1]), cmul(m[1][0], m[0][1]));
+      out.T = det.re / den;
+    }
+    const int e = fin.kexp[p];
+    out.M[0] = ldexp(m[0][0].re, e); out.M[1] = ldexp(m[0][0].im, e);
+    out.M[2] = ldexp(m[1][0].re, e); out.M[3] = ldexp(m[1][0].im, e);
+    out.M[4] = ldexp(m[0][1].re, e); out.M[5] = ldexp(m[0][1].im, e);
+    out.M[6] = ldexp(m[1][1].re, e); out.M[7] = ldexp(m[1][1].im, e);
+  }
+  out.A = (1.0 - out.R) - out.T;
+  return out;
+}
+
+// q, n, 1/n of one (material, wavelength) in the reference's rounding order (tm.py:269-270; numpy divides a
+// complex by a real by multiplying with the rounded reciprocal, see pst_math.cuh)
+PST_HD OptRow make_opt_row(double wl, double nr, double ni) {
+  const double omega = div_rn(kTwoPiC, wl);
+  const cplx inv = crecip({nr, ni});
+  return {mul_rn(mul_rn(nr, omega), kInvC0), mul_rn(mul_rn(ni, omega), kInvC0), nr, ni, inv.re, inv.im};
+}
+
+}  // namespace pst

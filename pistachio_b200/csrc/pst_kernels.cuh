@@ -1,0 +1,408 @@
+// CUDA kernels of the transfer-matrix hot path (sm_100a, fp64, FP64-pipe bound -- no tensor cores:
+// a chain of 2x2 complex products is not a dense contraction).
+//
+//   resample_kernel      K0  dispersion-table lookup            (reference tm.py:117-170)
+//   prep_optical_kernel      per (material, lambda): q = (n w)(1/c), n, 1/n   (tm.py:269-270)
+//   prep_trig_kernel         per theta: cos, 1/cos
+//   tmm_chain_kernel     K1  one thread per (lambda, theta) point, both polarisations in the thread,
+//                            optical table + layer list staged in shared memory once per block
+//                        K2  same kernel with SEG=true: the interior layers are cut into blockDim.y
+//                            ordered segments, one warp row per segment builds the 2x2 product of its
+//                            segment, and the segment products are combined in order through shared
+//                            memory (associative, non-commutative scan over layers)
+//   layer_matrices_kernel    [D, P, D^-1, M] per wavelength          (tm.py:190-305)
+//   t_r_kernel               (T, R) from caller-supplied matrices    (tm.py:464-514)
+//
+// Model: with phi = kx d, a = n cos(theta) (s) or n / cos(theta) (p),
+//   M_j = D_j P_j D_j^-1 = [[cos phi, -i sin phi / a], [-i a sin phi, cos phi]],
+//   M   = D_0^-1 (M_1 ... M_{N-2}) D_{N-1},   t = 1/M00, r = M10/M00, R = |r|^2, T = Re(det M |t|^2).
+// Only the columns of M that are asked for are propagated: v <- M_j v from the exit side.
+#pragma once
+#include "pst_chain.cuh"
+
+namespace pst {
+
+struct LayerEntry {  // 16 bytes: one LDS.128 / LDG.128 per layer
+  double d;
+  int mat;
+  int pad;
+};
+
+struct GridParams {
+  int n_wl, n_theta, n_mat, n_layers;
+  int sweep_layer;   // -1: none
+  int pol_first;     // NPOL == 1: 0 = s, 1 = p
+  int tl_stride;     // doubles per (mat, param) row in shared memory (>= max lambdas per block)
+  int il0;           // first wavelength index of this launch (host pipeline launches wavelength windows)
+  unsigned flags;
+  long long points;  // n_wl * n_theta
+  const double* opt;        // [n_mat][6][n_wl]: q.re q.im n.re n.im (1/n).re (1/n).im
+  const double2* trig;      // [n_theta] (cos, 1/cos)
+  const LayerEntry* layers; // [n_layers]
+  const double* sweep_d;    // [gridDim.y] or nullptr
+  double* R;
+  double* T;
+  double* A;
+  double* M;
+};
+
+// ---------------------------------------------------------------------------------------------- K0
+// One thread per (table, wavelength).  lower_bound on the sorted table, then scipy's two-term formula
+// with every operation rounded separately (no FMA) -- bit-identical to interp1d's linear branch.
+__global__ void resample_kernel(int n_tab, const int* __restrict__ tab_off, const double* __restrict__ tab_wl,
+                                const double* __restrict__ tab_n, const double* __restrict__ tab_k,
+                                const double* __restrict__ wl, int n_wl, double* __restrict__ out_n,
+                                double* __restrict__ out_k) {
+  extern __shared__ double s_x[];  // the table's wavelength column when it fits (binary search in smem)
+  const int t = blockIdx.y;
+  const int off = tab_off[t];
+  const int rows = tab_off[t + 1] - off;
+  const bool staged = rows * sizeof(double) <= 32 * 1024;
+  if (staged) {
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) s_x[i] = tab_wl[off + i];
+    __syncthreads();
+  }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_wl) return;
+  const double x = wl[i];
+  if (rows == 1) {
+    out_n[(size_t)t * n_wl + i] = tab_n[off];
+    out_k[(size_t)t * n_wl + i] = tab_k[off];
+    return;
+  }
+  const double* xs = staged ? s_x : tab_wl + off;
+  int lo = 0, hi = rows;  // first index with xs[idx] >= x  (np.searchsorted side='left'; NaN sorts last)
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (xs[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  if (x != x) lo = rows;
+  int ih = min(max(lo, 1), rows - 1);
+  int il = ih - 1;
+  const double x_lo = xs[il], x_hi = xs[ih];
+  const double den = sub_rn(x_hi, x_lo);
+  const double w_hi = div_rn(sub_rn(x, x_lo), den);
+  const double w_lo = div_rn(sub_rn(x_hi, x), den);
+  out_n[(size_t)t * n_wl + i] = add_rn(mul_rn(w_hi, tab_n[off + ih]), mul_rn(w_lo, tab_n[off + il]));
+  out_k[(size_t)t * n_wl + i] = add_rn(mul_rn(w_hi, tab_k[off + ih]), mul_rn(w_lo, tab_k[off + il]));
+}
+
+// ------------------------------------------------------------------------------------------- prep
+__global__ void prep_optical_kernel(const double* __restrict__ wl, const double* __restrict__ mat_n,
+                                    const double* __restrict__ mat_k, int n_wl, int n_mat,
+                                    double* __restrict__ opt) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_wl * n_mat) return;
+  const int m = (int)(idx / n_wl);
+  const int i = (int)(idx - (long long)m * n_wl);
+  const OptRow r = make_opt_row(wl[i], mat_n[idx], mat_k[idx]);
+  double* o = opt + (size_t)m * 6 * n_wl + i;
+  o[0] = r.qr;
+  o[(size_t)n_wl] = r.qi;
+  o[(size_t)2 * n_wl] = r.nr;
+  o[(size_t)3 * n_wl] = r.ni;
+  o[(size_t)4 * n_wl] = r.inr;
+  o[(size_t)5 * n_wl] = r.ini;
+}
+
+__global__ void prep_trig_kernel(const double* __restrict__ theta, const double* __restrict__ cos_theta, int n_theta,
+                                 double2* __restrict__ trig) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_theta) return;
+  const double c = cos_theta ? cos_theta[i] : cos(theta[i]);
+  trig[i] = make_double2(c, 1.0 / c);
+}
+
+// ------------------------------------------------------------------------------------ K1 / K2
+constexpr int kRenormEvery = 8;
+
+template <int NPOL, int NCOL, bool STAGE_OPT, bool STAGE_LAYERS, bool SEG>
+__global__ void __launch_bounds__(SEG ? 512 : 256)
+tmm_chain_kernel(const GridParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NC = SEG ? 2 : NCOL;  // a segment product needs both columns
+  const int PB = blockDim.x;          // points per block
+  const int W = blockDim.y;           // ordered layer segments per point (1 unless SEG)
+  const int tid = threadIdx.y * PB + threadIdx.x;
+  const int nthr = PB * W;
+  const long long p0 = (long long)blockIdx.x * PB;
+  const long long p_last = min(p0 + PB, prm.points) - 1;
+  const int l_lo = prm.il0 + (int)(p0 / prm.n_theta);
+  const int TL = prm.il0 + (int)(p_last / prm.n_theta) - l_lo + 1;
+  const int L = prm.n_layers;
+
+  // ---- shared-memory carve-up: [optical table][layer list][segment products]
+  double* s_opt = reinterpret_cast<double*>(smem_raw);
+  size_t off = STAGE_OPT ? (size_t)prm.n_mat * 6 * prm.tl_stride * sizeof(double) : 0;
+  LayerEntry* s_layers = reinterpret_cast<LayerEntry*>(smem_raw + off);
+  off += STAGE_LAYERS ? (size_t)L * sizeof(LayerEntry) : 0;
+  double* s_seg = reinterpret_cast<double*>(smem_raw + off);
+
+  if constexpr (STAGE_OPT) {
+    // rows of TL consecutive wavelengths, one row per (material, parameter): coalesced when TL is large,
+    // a handful of scalar loads when a block sits on a single wavelength
+    const int rows = prm.n_mat * 6;
+    for (int idx = tid; idx < rows * TL; idx += nthr) {
+      const int r = idx / TL, c = idx - r * TL;
+      s_opt[r * prm.tl_stride + c] = __ldg(prm.opt + (size_t)r * prm.n_wl + l_lo + c);
+    }
+  }
+  if constexpr (STAGE_LAYERS) {
+    const int4* src = reinterpret_cast<const int4*>(prm.layers);
+    int4* dst = reinterpret_cast<int4*>(s_layers);
+    for (int idx = tid; idx < L; idx += nthr) dst[idx] = __ldg(src + idx);
+  }
+  if constexpr (STAGE_OPT || STAGE_LAYERS) __syncthreads();
+
+  const long long p = min(p0 + threadIdx.x, prm.points - 1);
+  const bool valid = (p0 + threadIdx.x) < prm.points;
+  const int il_loc = (int)(p / prm.n_theta);
+  const int it = (int)(p - (long long)il_loc * prm.n_theta);
+  const int il = prm.il0 + il_loc;
+  const double2 tr = __ldg(prm.trig + it);
+  const double ct = tr.x, ict = tr.y;
+  const int sweep = blockIdx.y;
+  const double d_sweep = prm.sweep_d ? __ldg(prm.sweep_d + sweep) : 0.0;
+
+  // optical-table accessor for this thread's wavelength
+  const double* optp = STAGE_OPT ? (s_opt + (il - l_lo)) : (prm.opt + il);
+  const size_t pstride = STAGE_OPT ? (size_t)prm.tl_stride : (size_t)prm.n_wl;
+  const LayerEntry* lay = STAGE_LAYERS ? s_layers : prm.layers;
+  auto opt_row = [&](int mat) {
+    const double* o = optp + (size_t)mat * 6 * pstride;
+    return OptRow{o[0], o[pstride], o[2 * pstride], o[3 * pstride], o[4 * pstride], o[5 * pstride]};
+  };
+  const OptRow exit_row = opt_row(lay[L - 1].mat);
+
+  // ---- the ordered chain over this thread's segment of interior layers
+  const int Li = L - 2;
+  const int seg = SEG ? threadIdx.y : 0;
+  const int j_lo = 1 + (int)(((long long)Li * seg) / W);
+  const int j_hi = 1 + (int)(((long long)Li * (seg + 1)) / W);  // exclusive
+
+  ChainState<NPOL, NC> st;
+  if constexpr (SEG) init_identity<NPOL>(st);
+  else init_exit_columns<NPOL, NC>(st, exit_row.nr, exit_row.ni, ct, prm.pol_first);
+
+  int since = 0;
+  for (int j = j_hi - 1; j >= j_lo; --j) {
+    const LayerEntry le = lay[j];
+    const double d = (j == prm.sweep_layer) ? d_sweep : le.d;
+    apply_layer<NPOL, NC>(st, opt_row(le.mat), d, ct, ict, prm.pol_first);
+    if (++since == kRenormEvery) { renormalise<NPOL, NC>(st); since = 0; }
+  }
+  renormalise<NPOL, NC>(st);
+
+  ChainState<NPOL, NCOL> fin;
+  if constexpr (SEG) {
+    // ---- ordered combine: S_0 S_1 ... S_{W-1} applied to the exit columns, by the seg-0 row of threads
+    constexpr int REC = 9;  // 8 doubles + exponent per (segment, polarisation); lanes contiguous
+    double* mine = s_seg + ((size_t)(seg * NPOL) * REC) * PB + threadIdx.x;
+#pragma unroll
+    for (int pp = 0; pp < NPOL; ++pp) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mine[((size_t)pp * REC + c * 4 + k) * PB] = st.v[pp][c][k];
+      mine[((size_t)pp * REC + 8) * PB] = (double)st.kexp[pp];
+    }
+    __syncthreads();
+    if (threadIdx.y != 0) return;
+    init_exit_columns<NPOL, NCOL>(fin, exit_row.nr, exit_row.ni, ct, prm.pol_first);
+    for (int w = W - 1; w >= 0; --w) {
+      const double* rec = s_seg + ((size_t)(w * NPOL) * REC) * PB + threadIdx.x;
+#pragma unroll
+      for (int pp = 0; pp < NPOL; ++pp) {
+        double s[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] = rec[((size_t)pp * REC + k) * PB];
+        apply_segment<NPOL, NCOL>(fin, pp, s, (int)rec[((size_t)pp * REC + 8) * PB]);
+      }
+      renormalise<NPOL, NCOL>(fin);
+    }
+  } else {
+    fin = st;
+  }
+  if (!valid) return;
+
+  // ---- epilogue
+  const OptRow in_row = opt_row(lay[0].mat);
+  const size_t plane = (size_t)prm.points;
+#pragma unroll
+  for (int pp = 0; pp < NPOL; ++pp) {
+    const PointOut r = finish_point<NPOL, NCOL>(fin, pp, in_row.inr, in_row.ini, exit_row.nr, exit_row.ni, ict,
+                                                prm.pol_first, prm.flags);
+    const size_t o = ((size_t)sweep * NPOL + pp) * plane + (size_t)p;
+    if (prm.R) prm.R[o] = r.R;
+    if (prm.T) prm.T[o] = r.T;
+    if (prm.A) prm.A[o] = r.A;
+    if constexpr (NCOL == 2) {
+      if (prm.M) {
+        double4* mo = reinterpret_cast<double4*>(prm.M + o * 8);
+        mo[0] = make_double4(r.M[0], r.M[1], r.M[2], r.M[3]);
+        mo[1] = make_double4(r.M[4], r.M[5], r.M[6], r.M[7]);
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------- per-layer matrices (API parity)
+// out[i] = [D, P, D^-1, M] (each 2x2 complex128, row major) for wavelength i.  Closed forms of what the
+// reference obtains with np.linalg.inv and multi_dot (tm.py:272-275).
+__global__ void layer_matrices_kernel(const double* __restrict__ n_re, const double* __restrict__ n_im,
+                                      const double* __restrict__ wl, int n_wl, double ct, unsigned pol, double d,
+                                      double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_wl) return;
+  const double nr = n_re[i], ni = n_im[i];
+  const double omega = div_rn(kTwoPiC, wl[i]);
+  const double kxr = mul_rn(mul_rn(mul_rn(nr, omega), kInvC0), ct);
+  const double kxi = mul_rn(mul_rn(mul_rn(ni, omega), kInvC0), ct);
+  const double x = mul_rn(kxr, d), y = mul_rn(kxi, d);
+  double sx, cx;
+  sincos(x, &sx, &cx);
+  const double ep = exp(y), em = exp(-y);
+  const bool is_s = pol == 1u;
+  const double ict = 1.0 / ct;
+  // D
+  const cplx d0 = is_s ? cplx{1.0, 0.0} : cplx{ct, 0.0};
+  const cplx d1 = is_s ? cplx{nr * ct, ni * ct} : cplx{nr, ni};
+  // D^-1 = 1/2 [[1/d0, 1/d1], [1/d0, -1/d1]]
+  const cplx h0 = {0.5 / d0.re, 0.0};
+  const cplx h1 = cscale(crecip(d1), 0.5);
+  // P = diag(e^{y}(cos x - i sin x), e^{-y}(cos x + i sin x))                    (tm.py:234)
+  const cplx p0 = {ep * cx, -(ep * sx)};
+  const cplx p1 = {em * cx, em * sx};
+  // M = [[cos phi, -i sin phi / a], [-i a sin phi, cos phi]], a = d1/d0
+  const double ch = 0.5 * (ep + em), sh = 0.5 * (ep - em);
+  const cplx cphi = {cx * ch, -(sx * sh)};
+  const cplx sphi = {sx * ch, cx * sh};
+  const cplx a = is_s ? d1 : cplx{nr * ict, ni * ict};
+  const cplx as = cmul(a, sphi);
+  const cplx sa = cmul(sphi, crecip(a));
+  double* o = out + (size_t)i * 32;
+  // D
+  o[0] = d0.re; o[1] = 0.0; o[2] = d0.re; o[3] = 0.0;
+  o[4] = d1.re; o[5] = d1.im; o[6] = -d1.re; o[7] = -d1.im;
+  // P
+  o[8] = p0.re; o[9] = p0.im; o[10] = 0.0; o[11] = 0.0;
+  o[12] = 0.0; o[13] = 0.0; o[14] = p1.re; o[15] = p1.im;
+  // D^-1
+  o[16] = h0.re; o[17] = 0.0; o[18] = h1.re; o[19] = h1.im;
+  o[20] = h0.re; o[21] = 0.0; o[22] = -h1.re; o[23] = -h1.im;
+  // M
+  o[24] = cphi.re; o[25] = cphi.im; o[26] = sa.im; o[27] = -sa.re;
+  o[28] = as.im; o[29] = -as.re; o[30] = cphi.re; o[31] = cphi.im;
+}
+
+__global__ void propagation_kernel(const double* __restrict__ kx, int n, double d, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = mul_rn(kx[2 * i], d), y = mul_rn(kx[2 * i + 1], d);
+  double sx, cx;
+  sincos(x, &sx, &cx);
+  const double ep = exp(y), em = exp(-y);
+  double* o = out + (size_t)i * 8;
+  o[0] = ep * cx; o[1] = -(ep * sx); o[2] = 0.0; o[3] = 0.0;
+  o[4] = 0.0; o[5] = 0.0; o[6] = em * cx; o[7] = em * sx;
+}
+
+__global__ void wavenumbers_kernel(const double* __restrict__ n_re, const double* __restrict__ n_im,
+                                   const double* __restrict__ wl, int n_wl, double ct, double stheta,
+                                   double* __restrict__ kx, double* __restrict__ kz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_wl) return;
+  const double omega = div_rn(kTwoPiC, wl[i]);
+  const double qr = mul_rn(mul_rn(n_re[i], omega), kInvC0), qi = mul_rn(mul_rn(n_im[i], omega), kInvC0);
+  kx[2 * i] = mul_rn(qr, ct); kx[2 * i + 1] = mul_rn(qi, ct);
+  kz[2 * i] = mul_rn(qr, stheta); kz[2 * i + 1] = mul_rn(qi, stheta);
+}
+
+// (T, R) from arbitrary matrices: t = 1/M00, r = M10/M00, T = Re(det M |t|^2)      (tm.py:482-486)
+__global__ void t_r_kernel(const double* __restrict__ M, long long n, double* __restrict__ T, double* __restrict__ R) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 r0 = reinterpret_cast<const double4*>(M)[2 * i];      // M00, M01
+  const double4 r1 = reinterpret_cast<const double4*>(M)[2 * i + 1];  // M10, M11
+  const cplx m00 = {r0.x, r0.y}, m01 = {r0.z, r0.w}, m10 = {r1.x, r1.y}, m11 = {r1.z, r1.w};
+  // scale by a power of two so that |M00|^2 cannot overflow/underflow (exact)
+  const int e = max(min(exponent_of(fmax(fabs(m00.re), fabs(m00.im))), 1000), -1000);
+  const double s = pow2i(-e);
+  const cplx a = cscale(m00, s), b = cscale(m10, s), c = cscale(m01, s), d = cscale(m11, s);
+  const double den = fma(a.re, a.re, a.im * a.im);
+  const cplx det = csub(cmul(a, d), cmul(c, b));
+  T[i] = det.re / den;
+  R[i] = fma(b.re, b.re, b.im * b.im) / den;
+}
+
+// Ordered chain over explicit layer matrices, one thread per wavelength             (tm.py:559-568)
+struct mat2 {
+  cplx a, b, c, d;  // [[a, b], [c, d]]
+};
+__device__ __forceinline__ mat2 load_mat2(const double* p) {
+  const double4 r0 = reinterpret_cast<const double4*>(p)[0], r1 = reinterpret_cast<const double4*>(p)[1];
+  return {{r0.x, r0.y}, {r0.z, r0.w}, {r1.x, r1.y}, {r1.z, r1.w}};
+}
+__device__ __forceinline__ mat2 matmul2(const mat2& x, const mat2& y) {
+  return {cadd(cmul(x.a, y.a), cmul(x.b, y.c)), cadd(cmul(x.a, y.b), cmul(x.b, y.d)),
+          cadd(cmul(x.c, y.a), cmul(x.d, y.c)), cadd(cmul(x.c, y.b), cmul(x.d, y.d))};
+}
+__global__ void chain_matrices_kernel(const double* __restrict__ first_inv, const double* __restrict__ interior,
+                                      const double* __restrict__ last_d, int n_int, int n_wl, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_wl) return;
+  mat2 acc = {{1.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {1.0, 0.0}};
+  for (int j = n_int - 1; j >= 0; --j) acc = matmul2(load_mat2(interior + ((size_t)j * n_wl + i) * 8), acc);
+  const mat2 m = matmul2(load_mat2(first_inv + (size_t)i * 8), matmul2(acc, load_mat2(last_d + (size_t)i * 8)));
+  double4* o = reinterpret_cast<double4*>(out + (size_t)i * 8);
+  o[0] = make_double4(m.a.re, m.a.im, m.b.re, m.b.im);
+  o[1] = make_double4(m.c.re, m.c.im, m.d.re, m.d.im);
+}
+
+// Fresnel coefficients / interface matrices                                         (tm.py:730-751)
+__global__ void fresnel_kernel(const double* __restrict__ n1, const double* __restrict__ n2,
+                               const double* __restrict__ k1, const double* __restrict__ k2, long long n,
+                               double* __restrict__ rt, double* __restrict__ D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const cplx a = {n1[2 * i], n1[2 * i + 1]}, b = {n2[2 * i], n2[2 * i + 1]};
+  const cplx k1x = {k1[2 * i], k1[2 * i + 1]}, k2x = {k2[2 * i], k2[2 * i + 1]};
+  const cplx isum = crecip(cadd(k1x, k2x));
+  const cplx rs = cmul(csub(k1x, k2x), isum);
+  const cplx ts = cmul(cscale(k1x, 2.0), isum);
+  const cplx a2k2 = cmul(cmul(a, a), k2x), b2k1 = cmul(cmul(b, b), k1x);
+  const cplx ip = crecip(cadd(a2k2, b2k1));
+  const cplx rp = cmul(csub(a2k2, b2k1), ip);
+  const cplx tp = cmul(cscale(a2k2, 2.0), ip);
+  double* o = rt + i * 8;
+  o[0] = rs.re; o[1] = rs.im; o[2] = ts.re; o[3] = ts.im; o[4] = rp.re; o[5] = rp.im; o[6] = tp.re; o[7] = tp.im;
+  if (D) {
+    const cplx r[2] = {rs, rp}, t[2] = {ts, tp};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const cplx it = crecip(t[q]);
+      const cplx ro = cmul(r[q], it);
+      double* m = D + (i * 2 + q) * 8;
+      m[0] = it.re; m[1] = it.im; m[2] = ro.re; m[3] = ro.im;
+      m[4] = ro.re; m[5] = ro.im; m[6] = it.re; m[7] = it.im;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ measurement helpers
+// 8 independent dependent-FMA chains per thread: the non-tensor FP64 peak of the chip.
+__global__ void dfma_probe_kernel(int iters, double seed, double* __restrict__ sink) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double m = 0.9999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
+}
+
+}  // namespace pst

@@ -1,0 +1,130 @@
+// Device-side fp64 building blocks of the TMM path (sm_100a).
+//
+// Two rules shape this file:
+//  (1) The propagation phase must carry the reference's rounding sequence, because a
+//      cavity of finesse F amplifies a phase error by F.  The reference evaluates
+//          omega = (2*pi*c)/lambda                                  tm.py:269
+//          kx    = ((n*omega) * (1/c)) * cos(theta)                 tm.py:270 (numpy divides a
+//                   complex by a real by multiplying with the rounded reciprocal)
+//          arg   = (Im kx * d, -Re kx * d)                          tm.py:234
+//      each step rounded once.  mul_rn/div_rn below forbid FMA contraction for these.
+//  (2) Everything after the phase is free of catastrophic amplification, so it is
+//      written for the FP64 pipe: FMA everywhere, no divisions in the layer loop,
+//      exponentials split into mantissa and a power of two that is carried as an
+//      integer so that thick absorbers and deep stop bands cannot overflow.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+// Device math is also compilable for the host (nvcc host pass) so that tests/host_emul can run the *same*
+// layer-step / epilogue source on the CPU box before GPU time is spent.  That harness is test infrastructure;
+// libpistachio_b200.so never calls these functions from host code.
+#define PST_HD __host__ __device__ __forceinline__
+
+namespace pst {
+
+#ifdef __CUDA_ARCH__
+PST_HD double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+PST_HD double add_rn(double a, double b) { return __dadd_rn(a, b); }
+PST_HD double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+PST_HD double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+PST_HD int hi_word(double x) { return __double2hiint(x); }
+PST_HD double from_words(int hi, int lo) { return __hiloint2double(hi, lo); }
+#else
+// host emulation: separate statements through volatiles keep the compiler from contracting a*b+c
+PST_HD double mul_rn(double a, double b) { volatile double r = a * b; return r; }
+PST_HD double add_rn(double a, double b) { volatile double r = a + b; return r; }
+PST_HD double sub_rn(double a, double b) { volatile double r = a - b; return r; }
+PST_HD double div_rn(double a, double b) { volatile double r = a / b; return r; }
+PST_HD int hi_word(double x) { long long u; memcpy(&u, &x, 8); return (int)(u >> 32); }
+PST_HD double from_words(int hi, int lo) {
+  long long u = ((long long)(unsigned)hi << 32) | (unsigned)lo; double x; memcpy(&x, &u, 8); return x;
+}
+#endif
+
+constexpr double kC0 = 299792458.0;                        // scipy.constants.c
+constexpr double kTwoPiC = (2.0 * 3.141592653589793) * kC0;  // (2*np.pi)*c, one rounding, folded on the host
+constexpr double kInvC0 = 1.0 / kC0;                       // numpy's reciprocal-scale in complex/real division
+
+// 2^e as a double for e in [-1022, 1023]; 0 below, +inf above.
+PST_HD double pow2i(int e) {
+  if (e < -1022) return 0.0;
+  if (e > 1023) return from_words(0x7ff00000, 0);
+  return from_words((e + 1023) << 20, 0);
+}
+
+// Unbiased exponent of |x| (floor(log2|x|)) for normal x; 0 for zero/denormal, 1024 for inf/nan.
+PST_HD int exponent_of(double x) {
+  int hi = hi_word(x);
+  int e = (hi >> 20) & 0x7ff;
+  return e == 0 ? 0 : e - 1023;
+}
+
+// y = k*ln2 + r, |r| <= ln2/2:  e^{+-r} = E(r^2) +- r*O(r^2) with one shared even/odd Taylor
+// split (degree 13, truncation < 4e-18).  Returns even = E, odd = r*O; k is returned, not applied.
+PST_HD void exp_split(double y, double& even, double& odd, int& k) {
+  const double kLog2e = 1.4426950408889634;
+  const double kLn2Hi = 6.93147180369123816490e-01;  // split of ln2, low 21 bits of Hi are zero
+  const double kLn2Lo = 1.90821492927058770002e-10;
+  double kd = rint(y * kLog2e);
+  kd = fmin(fmax(kd, -1.0e9), 1.0e9);
+  double r = fma(-kd, kLn2Hi, y);
+  r = fma(-kd, kLn2Lo, r);
+  k = (int)kd;
+  double r2 = r * r;
+  double e = 1.0 / 479001600.0;            // 1/12!
+  e = fma(e, r2, 1.0 / 3628800.0);         // 1/10!
+  e = fma(e, r2, 1.0 / 40320.0);           // 1/8!
+  e = fma(e, r2, 1.0 / 720.0);             // 1/6!
+  e = fma(e, r2, 1.0 / 24.0);              // 1/4!
+  e = fma(e, r2, 0.5);                     // 1/2!
+  e = fma(e, r2, 1.0);
+  double o = 1.0 / 6227020800.0;           // 1/13!
+  o = fma(o, r2, 1.0 / 39916800.0);        // 1/11!
+  o = fma(o, r2, 1.0 / 362880.0);          // 1/9!
+  o = fma(o, r2, 1.0 / 5040.0);            // 1/7!
+  o = fma(o, r2, 1.0 / 120.0);             // 1/5!
+  o = fma(o, r2, 1.0 / 6.0);               // 1/3!
+  o = fma(o, r2, 1.0);
+  even = e;
+  odd = r * o;
+}
+
+// cosh(y) = 2^s * ch, sinh(y) = 2^s * sh with ch, sh of order one; returns s = |k| - 1.
+// With f = 2^(-2|k|):  cosh|y| = 2^(|k|-1) [E(1+f) + rO(1-f)],  sinh|y| = 2^(|k|-1) [E(1-f) + rO(1+f)].
+// Never overflows (the huge factor stays in the integer) and keeps sinh accurate for tiny y (f = 1).
+PST_HD int cosh_sinh_scaled(double y, double& ch, double& sh) {
+  double e, ro;
+  int k;
+  exp_split(y, e, ro, k);
+  int ka = k < 0 ? -k : k;
+  double f = pow2i(ka > 600 ? -1200 : -2 * ka);
+  double sg = k >= 0 ? 1.0 : -1.0;  // for k < 0 evaluate at -y: r -> -r, sinh flips sign
+  double opf = 1.0 + f, omf = 1.0 - f;
+  ch = fma(sg * ro, omf, e * opf);
+  sh = fma(ro, opf, sg * e * omf);
+  return ka - 1;
+}
+
+struct cplx {
+  double re, im;
+};
+PST_HD cplx cmul(cplx a, cplx b) {
+  return {fma(a.re, b.re, -(a.im * b.im)), fma(a.re, b.im, a.im * b.re)};
+}
+PST_HD cplx cadd(cplx a, cplx b) { return {a.re + b.re, a.im + b.im}; }
+PST_HD cplx csub(cplx a, cplx b) { return {a.re - b.re, a.im - b.im}; }
+PST_HD cplx cscale(cplx a, double s) { return {a.re * s, a.im * s}; }
+PST_HD cplx crecip(cplx a) {
+  // scaled to dodge overflow of |a|^2; used outside the layer loop only
+  double m = fmax(fabs(a.re), fabs(a.im));
+  if (m == 0.0) return {1.0 / a.re, 0.0};
+  double sr = a.re / m, si = a.im / m;
+  double den = (sr * sr + si * si) * m;
+  return {sr / den, -si / den};
+}
+PST_HD cplx cdiv(cplx a, cplx b) { return cmul(a, crecip(b)); }
+
+}  // namespace pst

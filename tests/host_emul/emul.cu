@@ -1,0 +1,76 @@
+// TEST INFRASTRUCTURE ONLY.  Runs the SAME per-point source the CUDA kernels execute
+// (pistachio_b200/csrc/pst_chain.cuh, compiled by nvcc's host pass) in a plain CPU loop, so that the algebra of
+// the layer step, the exact rescaling, the ordered segment combine and the epilogue can be checked against the
+// oracle on the GPU-less build box.  Built into tests/host_emul/_build/ by tests/test_host_emul.py; never part of
+// libpistachio_b200.so and never reachable from the pistachio_b200 package.
+#include <vector>
+#include "../../pistachio_b200/csrc/pst_chain.cuh"
+
+using namespace pst;
+
+template <int NPOL, int NCOL>
+static void run(int n_wl, int n_theta, int L, const double* wl, const double* cos_theta, const double* n_re,
+                const double* n_im, const double* d, int pol_first, int W, unsigned flags, double* R, double* T,
+                double* A, double* M) {
+  const int Li = L - 2;
+  for (int il = 0; il < n_wl; ++il) {
+    std::vector<OptRow> rows(L);
+    for (int j = 0; j < L; ++j) rows[j] = make_opt_row(wl[il], n_re[(size_t)j * n_wl + il], n_im[(size_t)j * n_wl + il]);
+    for (int it = 0; it < n_theta; ++it) {
+      const double ct = cos_theta[it], ict = 1.0 / ct;
+      ChainState<NPOL, NCOL> fin;
+      if (W <= 1) {
+        init_exit_columns<NPOL, NCOL>(fin, rows[L - 1].nr, rows[L - 1].ni, ct, pol_first);
+        int since = 0;
+        for (int j = L - 2; j >= 1; --j) {
+          apply_layer<NPOL, NCOL>(fin, rows[j], d[j], ct, ict, pol_first);
+          if (++since == 8) { renormalise<NPOL, NCOL>(fin); since = 0; }
+        }
+        renormalise<NPOL, NCOL>(fin);
+      } else {
+        std::vector<ChainState<NPOL, 2>> segs(W);
+        for (int w = 0; w < W; ++w) {
+          const int j_lo = 1 + (int)(((long long)Li * w) / W), j_hi = 1 + (int)(((long long)Li * (w + 1)) / W);
+          init_identity<NPOL>(segs[w]);
+          int since = 0;
+          for (int j = j_hi - 1; j >= j_lo; --j) {
+            apply_layer<NPOL, 2>(segs[w], rows[j], d[j], ct, ict, pol_first);
+            if (++since == 8) { renormalise<NPOL, 2>(segs[w]); since = 0; }
+          }
+          renormalise<NPOL, 2>(segs[w]);
+        }
+        init_exit_columns<NPOL, NCOL>(fin, rows[L - 1].nr, rows[L - 1].ni, ct, pol_first);
+        for (int w = W - 1; w >= 0; --w) {
+          for (int p = 0; p < NPOL; ++p) {
+            double s[8];
+            for (int c = 0; c < 2; ++c) for (int k = 0; k < 4; ++k) s[c * 4 + k] = segs[w].v[p][c][k];
+            apply_segment<NPOL, NCOL>(fin, p, s, segs[w].kexp[p]);
+          }
+          renormalise<NPOL, NCOL>(fin);
+        }
+      }
+      for (int p = 0; p < NPOL; ++p) {
+        const PointOut r = finish_point<NPOL, NCOL>(fin, p, rows[0].inr, rows[0].ini, rows[L - 1].nr, rows[L - 1].ni,
+                                                    ict, pol_first, flags);
+        const size_t o = ((size_t)p * n_wl + il) * n_theta + it;
+        R[o] = r.R; T[o] = r.T; A[o] = r.A;
+        if (NCOL == 2 && M) for (int k = 0; k < 8; ++k) M[o * 8 + k] = r.M[k];
+      }
+    }
+  }
+}
+
+// pol: 0 = s only, 1 = p only, 2 = both.  n_re/n_im: [L][n_wl].  Outputs [n_pol][n_wl][n_theta].
+extern "C" int emul_eval_grid(int n_wl, int n_theta, int L, const double* wl, const double* cos_theta,
+                              const double* n_re, const double* n_im, const double* d, int pol, int ncol, int W,
+                              unsigned flags, double* R, double* T, double* A, double* M) {
+  if (L < 2) return -1;
+  if (pol == 2) {
+    if (ncol == 2) run<2, 2>(n_wl, n_theta, L, wl, cos_theta, n_re, n_im, d, 0, W, flags, R, T, A, M);
+    else run<2, 1>(n_wl, n_theta, L, wl, cos_theta, n_re, n_im, d, 0, W, flags, R, T, A, M);
+  } else {
+    if (ncol == 2) run<1, 2>(n_wl, n_theta, L, wl, cos_theta, n_re, n_im, d, pol, W, flags, R, T, A, M);
+    else run<1, 1>(n_wl, n_theta, L, wl, cos_theta, n_re, n_im, d, pol, W, flags, R, T, A, M);
+  }
+  return 0;
+}

@@ -1,0 +1,115 @@
+"""CPU-side check of the DEVICE arithmetic: tests/host_emul/emul.cu compiles the per-point source of the CUDA
+kernels (pistachio_b200/csrc/pst_chain.cuh) with nvcc's host pass and loops over the grid on the CPU.  This is test
+infrastructure (it exists to catch algebra mistakes before GPU time is spent); the product has no CPU path."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import parity
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_emul", "emul.cu")
+OUT = os.path.join(HERE, "host_emul", "_build", "libemul.so")
+DEPS = [SRC] + [os.path.join(HERE, "..", "pistachio_b200", "csrc", f) for f in ("pst_chain.cuh", "pst_math.cuh")]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC],
+                       check=True)
+    lib = C.CDLL(OUT)
+    lib.emul_eval_grid.restype = C.c_int
+    return lib
+
+
+def run_emul(lib, wl, n_list, d_list, thetas, pol=2, ncol=1, W=1, flags=0):
+    wl = np.ascontiguousarray(wl, dtype=np.float64)
+    n = np.ascontiguousarray(np.array(n_list, dtype=np.complex128))
+    nre, nim = np.ascontiguousarray(n.real), np.ascontiguousarray(n.imag)
+    d = np.ascontiguousarray(d_list, dtype=np.float64)
+    ct = np.ascontiguousarray(np.cos(np.atleast_1d(thetas)))
+    npol = 2 if pol == 2 else 1
+    shape = (npol, len(wl), len(ct))
+    R, T, A = np.empty(shape), np.empty(shape), np.empty(shape)
+    M = np.empty(shape + (2, 2), dtype=np.complex128)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.emul_eval_grid(len(wl), len(ct), len(d), p(wl), p(ct), p(nre), p(nim), p(d), pol, ncol, W, flags, p(R), p(T),
+                            p(A), p(M))
+    assert rc == 0
+    return R, T, A, M
+
+
+@pytest.mark.parametrize("name", ["c1", "c2_sub", "c3_sub_d0", "c3_sub_d66666", "c4_sub"])
+def test_emul_matches_reference_cases(emul, ref_cases, name):
+    c = ref_cases[name]
+    R, T, A, _ = run_emul(emul, c["wl"], list(c["n"]), list(c["d"]), c["theta"])
+    rep = parity.compare_grid(name, T, R, c["wl"], list(c["n"]), list(c["d"]), c["theta"], c["T"], c["R"], got_A=A)
+    rep.check(max_loose_fraction=0.05)
+
+
+def test_emul_segmented_combine_matches_pointwise(emul, ref_cases):
+    c = ref_cases["c4_sub"]
+    R1, T1, _, M1 = run_emul(emul, c["wl"], list(c["n"]), list(c["d"]), c["theta"], ncol=2, W=1)
+    for W in (2, 7, 16):
+        R, T, A, M = run_emul(emul, c["wl"], list(c["n"]), list(c["d"]), c["theta"], ncol=2, W=W)
+        np.testing.assert_allclose(R, R1, rtol=0, atol=2e-12)
+        np.testing.assert_allclose(T, T1, rtol=0, atol=2e-12)
+    c = ref_cases["c2_sub"]
+    R1, T1, _, _ = run_emul(emul, c["wl"], list(c["n"]), list(c["d"]), c["theta"])
+    R, T, _, _ = run_emul(emul, c["wl"], list(c["n"]), list(c["d"]), c["theta"], W=4)
+    rep = parity.compare_grid("c2_sub_W4", T, R, c["wl"], list(c["n"]), list(c["d"]), c["theta"], c["T"], c["R"])
+    rep.check(max_loose_fraction=0.05)
+
+
+def test_emul_full_matrix_and_numeric_det(emul, ref_cases):
+    c = ref_cases["c1"]
+    every = int(c["m_every"])
+    R, T, A, M = run_emul(emul, c["wl"], list(c["n"]), list(c["d"]), c["theta"], ncol=2, flags=4)
+    ref_m = c["M"]
+    scale = np.abs(ref_m).max(axis=(-1, -2), keepdims=True)
+    assert np.all(np.abs(M[:, ::every] - ref_m) <= 1e-12 * scale)
+    np.testing.assert_allclose(T, c["T"], rtol=0, atol=1e-12)
+
+
+def test_emul_fuzz(emul, ref_cases):
+    n = int(ref_cases["fuzz"]["count"])
+    loose = total = 0
+    for i in range(0, n, 2):
+        c = ref_cases[f"fuzz{i}"]
+        R, T, A, M = run_emul(emul, c["wl"], list(c["n"]), list(c["d"]), c["theta"], ncol=2)
+        rep = parity.compare_grid(f"fuzz{i}", T, R, c["wl"], list(c["n"]), list(c["d"]), c["theta"], c["T"], c["R"], got_A=A)
+        assert rep.n_fail == 0, (rep.summary(), rep.worst)
+        loose += rep.n_loose
+        total += rep.n
+        ref_m = c["M"]
+        ok = np.isfinite(ref_m).all(axis=(-1, -2))
+        scale = np.abs(ref_m).max(axis=(-1, -2), keepdims=True)
+        assert np.all(np.abs(M - ref_m)[ok] <= 1e-11 * scale[ok]), f"fuzz{i}: matrix mismatch"
+    print(f"fuzz: {total} values, {loose} needed the conditioning clause")
+    assert loose <= 0.05 * total
+
+
+def test_emul_thick_absorber_and_deep_bragg_stay_finite(emul):
+    wl = np.linspace(0.8, 1.25, 16)
+    # 200 um of k = 10: the reference overflows to NaN; T must underflow to 0 cleanly
+    n_list = [np.full(16, 1.0 + 0j), np.full(16, 2.0 + 10.0j), np.full(16, 1.5 + 0j)]
+    R, T, A, _ = run_emul(emul, wl, n_list, [0.0, 200.0, 0.0], [0.0, 0.7])
+    assert np.isfinite(R).all() and np.isfinite(T).all() and (T == 0).all() and (R > 0).all() and (R < 1).all()
+    # 2000-layer high-contrast Bragg stack: reference returns NaN at 7 of 16 wavelengths
+    L = 2000
+    n_list = [np.full(16, 1.0 + 0j)] + [np.full(16, (2.32 if j % 2 == 0 else 1.36) + 0j) for j in range(L)] + [np.full(16, 1.5 + 0j)]
+    d = [0.0] + [1.0 / (4 * (2.32 if j % 2 == 0 else 1.36)) for j in range(L)] + [0.0]
+    for W in (1, 8):
+        R, T, A, _ = run_emul(emul, wl, n_list, d, [0.0], W=W)
+        assert np.isfinite(R).all() and np.isfinite(T).all()
+        assert (R >= 0).all() and (R <= 1 + 1e-12).all() and (T >= 0).all()
+        np.testing.assert_allclose(R + T, 1.0, atol=1e-9)
