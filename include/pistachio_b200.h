@@ -122,8 +122,9 @@ int pst_layer_matrices(pst_handle_t h, const double* n_re /*[dev]*/, const doubl
                        const double* wl /*[dev]*/, int n_wl, double theta, double cos_theta, unsigned pol,
                        double thickness, double* out /*[dev]*/, void* stream);
 
-/* Replaces Layer.propagation_matrix (tm.py:217-234) for explicit (kx, d): out complex128 [n][2][2]. */
-int pst_propagation_matrices(pst_handle_t h, const double* kx /*[dev] complex n*/, int n, double thickness,
+/* Replaces Layer.propagation_matrix (tm.py:217-234) for explicit (kx, d): out complex128 [n][2][2].
+ * d may be complex (the reference's own test passes d = pi/(2 kx) with a complex kx); d_im = 0 for a thickness. */
+int pst_propagation_matrices(pst_handle_t h, const double* kx /*[dev] complex n*/, int n, double d_re, double d_im,
                              double* out /*[dev]*/, void* stream);
 
 /* Replaces Layer.calculate_wavenumbers (tm.py:172-188): kx = n w/c cos(theta), kz = n w/c sin(theta);

@@ -63,7 +63,7 @@ SYMBOLS = {
     "pst_eval_grid_host": (C.c_int, [C.c_void_p, C.POINTER(GridArgs)]),
     "pst_layer_matrices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double,
                                       C.c_uint, C.c_double, C.c_void_p, C.c_void_p]),
-    "pst_propagation_matrices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
+    "pst_propagation_matrices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "pst_wavenumbers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "pst_t_r_from_matrices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -431,12 +431,12 @@ extern "C" int pst_layer_matrices(pst_handle_t h, const double* n_re, const doub
   return PST_OK;
 }
 
-extern "C" int pst_propagation_matrices(pst_handle_t h, const double* kx, int n, double thickness, double* out,
+extern "C" int pst_propagation_matrices(pst_handle_t h, const double* kx, int n, double d_re, double d_im, double* out,
                                         void* stream) {
   if (!h) return fail(PST_E_INVALID, "pst_propagation_matrices: NULL handle");
   if (!kx || !out || n <= 0) return fail(PST_E_INVALID, "pst_propagation_matrices: bad argument");
   DeviceGuard g(h->device);
-  propagation_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(kx, n, thickness, out);
+  propagation_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(kx, n, d_re, d_im, out);
   PST_CUDA(cudaGetLastError());
   h->launches += 1;
   return PST_OK;

@@ -295,10 +295,14 @@ __global__ void layer_matrices_kernel(const double* __restrict__ n_re, const dou
   o[28] = as.im; o[29] = -as.re; o[30] = cphi.re; o[31] = cphi.im;
 }
 
-__global__ void propagation_kernel(const double* __restrict__ kx, int n, double d, double* __restrict__ out) {
+__global__ void propagation_kernel(const double* __restrict__ kx, int n, double dr, double di,
+                                   double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double x = mul_rn(kx[2 * i], d), y = mul_rn(kx[2 * i + 1], d);
+  // -1j*kx*d = (b, -a)(dr + i di) in numpy's complex-product order: (b dr + a di) + i (b di - a dr)   (tm.py:234)
+  const double a = kx[2 * i], b = kx[2 * i + 1];
+  const double y = add_rn(mul_rn(b, dr), mul_rn(a, di));
+  const double x = sub_rn(mul_rn(a, dr), mul_rn(b, di));
   double sx, cx;
   sincos(x, &sx, &cx);
   const double ep = exp(y), em = exp(-y);

@@ -1,0 +1,85 @@
+"""Multi-GPU sharding of a sweep: one process per GPU, no data-path collective.
+
+Every spectral point is independent, so the grid is cut into contiguous slabs along its
+slowest axis (the thickness sweep if there is one, otherwise wavelength) and each rank evaluates its slab with the
+full (tiny) material/layer tables.  Results stay sharded unless the caller asks for them on every device, in which
+case one all-gather (NCCL over NVLink on GPUs; gloo in the CPU tests) assembles [sweep][pol][wl][theta] arrays.
+Reference seam: Structure.angle_resolved_spectra's multiprocessing fan-out (transfer_matrix.py:597-628).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous, balanced [lo, hi) of `n` items for `rank`; the first n % world ranks get one extra item."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_axis(n_sweep: int, n_wl: int) -> str:
+    return "sweep" if n_sweep > 1 else "wl"
+
+
+def init_from_env(backend: str | None = None):
+    """(rank, world, local_rank) from torchrun's environment; initialises torch.distributed when world > 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_prepared(prep: dict, world: int, rank: int) -> dict:
+    """Slice the tensors of `TMMEngine.prepare_workload` to this rank's slab (views, no copies of tables)."""
+    out = dict(prep)
+    n_sweep = 1 if prep["sweep_d"] is None else prep["sweep_d"].numel()
+    n_wl = prep["wl"].numel()
+    axis = shard_axis(n_sweep, n_wl)
+    if axis == "sweep":
+        lo, hi = shard_bounds(n_sweep, world, rank)
+        out["sweep_d"] = prep["sweep_d"][lo:hi].contiguous()
+    else:
+        lo, hi = shard_bounds(n_wl, world, rank)
+        out["wl"] = prep["wl"][lo:hi].contiguous()
+        out["mat_n"] = prep["mat_n"][:, lo:hi].contiguous()
+        out["mat_k"] = prep["mat_k"][:, lo:hi].contiguous()
+    out["shard"] = (axis, lo, hi)
+    return out
+
+
+def allgather_result(local: torch.Tensor, axis: str, sizes, group=None) -> torch.Tensor:
+    """Assemble a [sweep][pol][wl][theta] tensor from per-rank slabs cut along `axis` ('sweep' -> dim 0,
+    'wl' -> dim 2).  `sizes` lists every rank's extent along that axis.  Equal slabs use one
+    all_gather_into_tensor; ragged slabs fall back to all_gather on padded buffers."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    dim = 0 if axis == "sweep" else 2
+    moved = local.movedim(dim, 0).contiguous()  # shard axis first so that the gather is a plain concatenation
+    if len(set(sizes)) == 1:
+        full = torch.empty((world * moved.shape[0],) + tuple(moved.shape[1:]), dtype=moved.dtype, device=moved.device)
+        dist.all_gather_into_tensor(full, moved, group=group)
+    else:
+        cap = max(sizes)
+        pad = torch.zeros((cap,) + tuple(moved.shape[1:]), dtype=moved.dtype, device=moved.device)
+        pad[: moved.shape[0]] = moved
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+        full = torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+    return full.movedim(0, dim).contiguous()

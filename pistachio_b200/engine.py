@@ -272,7 +272,8 @@ class TMMEngine:
         kx = np.asarray(kx, dtype=np.complex128).ravel()
         kx_d = torch.from_numpy(kx).to(self.device)
         out = torch.empty((kx.size, 2, 2), dtype=torch.complex128, device=self.device)
-        check(self.lib.pst_propagation_matrices(self.handle.raw, _ptr(kx_d), kx.size, float(thickness), _ptr(out),
+        d = complex(thickness)
+        check(self.lib.pst_propagation_matrices(self.handle.raw, _ptr(kx_d), kx.size, d.real, d.imag, _ptr(out),
                                                 self._stream()), "pst_propagation_matrices")
         return out
 

@@ -1,0 +1,277 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (engine.py -> libpistachio_b200.so), against
+the golden fixtures made by the real reference and against the CPU oracle on the same seeded inputs.
+Tolerances are defined in tests/parity.py.  Nothing here reads /root/reference."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+pytestmark = pytest.mark.gpu
+
+from oracle import tmm_oracle as orc  # noqa: E402
+from tests import parity  # noqa: E402
+
+POLS = ("s-wave", "p-wave")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pistachio_b200.engine import get_engine
+
+    return get_engine(0)
+
+
+def run_case(eng, c, pols=POLS, flags=0, want_matrix=False, theta_on_device=False):
+    """Each layer of a fixture carries its own n(lambda): one material column per layer."""
+    n = np.asarray(c["n"])
+    kw = dict(cos_theta=np.cos(c["theta"])) if not theta_on_device else {}
+    res = eng.eval_grid(c["wl"], c["theta"], n.real, n.imag, list(range(n.shape[0])), list(c["d"]), pols, flags=flags,
+                        want_matrix=want_matrix, **kw)
+    torch.cuda.synchronize()
+    return res.numpy()
+
+
+# ------------------------------------------------------------------------------------------------ K0
+def test_resample_bit_identical_to_reference(eng, ref_cases):
+    from pistachio_b200.workloads import load_material
+
+    for name, mat in (("interp_au", "Au"), ("interp_caf2_extrap", "CaF2")):
+        c = ref_cases[name]
+        n, k = eng.resample_tables([load_material(mat)], c["wl"])
+        assert np.array_equal(n[0].cpu().numpy(), c["n"]) and np.array_equal(k[0].cpu().numpy(), c["k"]), name
+    c = ref_cases["interp_unsorted"]
+    n, k = eng.resample_tables([(c["tab_wl"], c["tab_n"], c["tab_k"]), ([0.0], [1.5], [0.25])], c["wl"])
+    assert np.array_equal(n[0].cpu().numpy(), c["n"]) and np.array_equal(k[0].cpu().numpy(), c["k"])
+    assert (n[1] == 1.5).all() and (k[1] == 0.25).all()
+
+
+def test_resample_large_table_global_search(eng):
+    rng = np.random.default_rng(3)
+    tw = np.sort(rng.uniform(1.0, 25.0, 15347))  # size of the largest refractiveindex.info table in the reference
+    tn, tk = rng.uniform(1, 2, tw.size), rng.uniform(0, 1, tw.size)
+    q = np.concatenate([rng.uniform(0.5, 26.0, 5000), tw[::97]])
+    n, k = eng.resample_tables([(tw, tn, tk)], q)
+    rn, rk = orc.resample_table(tw, tn, tk, q)
+    assert np.array_equal(n[0].cpu().numpy(), rn) and np.array_equal(k[0].cpu().numpy(), rk)
+
+
+# ------------------------------------------------------------------------------------------------ grid parity
+@pytest.mark.parametrize("name", ["c1", "c2_sub", "c3_sub_d0", "c3_sub_d33333", "c3_sub_d66666", "c3_sub_d99999", "c4_sub"])
+def test_baseline_config_cases(eng, ref_cases, name):
+    c = ref_cases[name]
+    out = run_case(eng, c)
+    rep = parity.compare_grid(name, out["T"][0], out["R"][0], c["wl"], list(c["n"]), list(c["d"]), c["theta"], c["T"], c["R"],
+                              got_A=out["A"][0])
+    rep.check(max_loose_fraction=0.05)
+
+
+@pytest.mark.parametrize("name", ["c4_sub", "c2_sub"])
+def test_deep_scan_kernel_matches_reference(eng, ref_cases, name):
+    from pistachio_b200._cabi import FLAG_FORCE_DEEP_KERNEL, FLAG_FORCE_POINT_KERNEL
+
+    c = ref_cases[name]
+    deep = run_case(eng, c, flags=FLAG_FORCE_DEEP_KERNEL)
+    rep = parity.compare_grid(name + "_deep", deep["T"][0], deep["R"][0], c["wl"], list(c["n"]), list(c["d"]), c["theta"],
+                              c["T"], c["R"], got_A=deep["A"][0])
+    rep.check(max_loose_fraction=0.05)
+    point = run_case(eng, c, flags=FLAG_FORCE_POINT_KERNEL)
+    np.testing.assert_allclose(deep["R"], point["R"], rtol=0, atol=5e-12)
+    np.testing.assert_allclose(deep["T"], point["T"], rtol=0, atol=5e-12)
+
+
+def test_full_matrix_output(eng, ref_cases):
+    from pistachio_b200._cabi import FLAG_NUMERIC_DET
+
+    c = ref_cases["c1"]
+    every = int(c["m_every"])
+    out = run_case(eng, c, want_matrix=True, flags=FLAG_NUMERIC_DET)
+    ref_m = c["M"]
+    scale = np.abs(ref_m).max(axis=(-1, -2), keepdims=True)
+    assert np.all(np.abs(out["M"][0][:, ::every] - ref_m) <= 1e-12 * scale)
+    np.testing.assert_allclose(out["T"][0], c["T"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(out["R"][0], c["R"], rtol=0, atol=1e-12)
+
+
+def test_fuzz_stacks(eng, ref_cases):
+    n = int(ref_cases["fuzz"]["count"])
+    loose = total = 0
+    for i in range(n):
+        c = ref_cases[f"fuzz{i}"]
+        out = run_case(eng, c, want_matrix=True)
+        rep = parity.compare_grid(f"fuzz{i}", out["T"][0], out["R"][0], c["wl"], list(c["n"]), list(c["d"]), c["theta"], c["T"],
+                                  c["R"], got_A=out["A"][0])
+        assert rep.n_fail == 0, (rep.summary(), rep.worst)
+        loose += rep.n_loose
+        total += rep.n
+        ref_m = c["M"]
+        ok = np.isfinite(ref_m).all(axis=(-1, -2))
+        scale = np.abs(ref_m).max(axis=(-1, -2), keepdims=True)
+        assert np.all(np.abs(out["M"][0] - ref_m)[ok] <= 1e-11 * scale[ok]), f"fuzz{i}: matrix mismatch"
+    print(f"fuzz: {total} values over {n} stacks, {loose} needed the conditioning clause")
+    assert loose <= 0.05 * total
+
+
+def test_single_polarisation_and_device_cos(eng, ref_cases):
+    c = ref_cases["c2_sub"]
+    both = run_case(eng, c)
+    for ip, pol in enumerate(POLS):
+        one = run_case(eng, c, pols=(pol,))
+        assert np.array_equal(one["R"][0, 0], both["R"][0, ip]) and np.array_equal(one["T"][0, 0], both["T"][0, ip])
+    dev = run_case(eng, c, theta_on_device=True)  # cos(theta) evaluated by the device
+    rep = parity.compare_grid("c2_sub_devcos", dev["T"][0], dev["R"][0], c["wl"], list(c["n"]), list(c["d"]), c["theta"],
+                              c["T"], c["R"])
+    rep.check(max_loose_fraction=0.10)
+
+
+def test_no_smem_staging_variant_is_bit_identical(eng, ref_cases):
+    from pistachio_b200._cabi import FLAG_NO_SMEM_STAGING
+
+    c = ref_cases["c2_sub"]
+    a, b = run_case(eng, c), run_case(eng, c, flags=FLAG_NO_SMEM_STAGING)
+    assert np.array_equal(a["R"], b["R"]) and np.array_equal(a["T"], b["T"])
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def test_two_layer_structure_is_a_bare_interface(eng):
+    # N = 2: M = D_0^-1 D_f; 1.0 -> 1.5 gives T = 0.96, R = 0.04 at normal incidence
+    out = eng.eval_grid([1.0, 2.0], [0.0], [[1.0, 1.0], [1.5, 1.5]], np.zeros((2, 2)), [0, 1], [0.0, 0.0]).numpy()
+    np.testing.assert_allclose(out["R"], 0.04, rtol=1e-14)
+    np.testing.assert_allclose(out["T"], 0.96, rtol=1e-14)
+    np.testing.assert_allclose(out["A"], 0.0, atol=1e-15)
+
+
+@pytest.mark.parametrize("n_wl,n_theta", [(1, 1), (3, 1), (1, 37), (129, 1), (5, 33), (257, 3)])
+def test_ragged_grid_shapes(eng, n_wl, n_theta):
+    rng = np.random.default_rng(n_wl * 100 + n_theta)
+    L = 7
+    wl = np.sort(rng.uniform(0.5, 2.0, n_wl))
+    th = np.sort(rng.uniform(0.0, 1.4, n_theta))
+    n = rng.uniform(1, 3, (L, 1)) * np.ones((1, n_wl)) + 1j * np.where(rng.random((L, 1)) < 0.5, 0.0, rng.uniform(0, 0.3, (L, 1)))
+    n[0] = n[0].real
+    d = rng.uniform(0.05, 1.0, L)
+    out = eng.eval_grid(wl, th, n.real, n.imag, list(range(L)), list(d), cos_theta=np.cos(th)).numpy()
+    T, R = orc.spectrum_closed_form(orc.Stack(wl, list(n), list(d)), th)
+    np.testing.assert_allclose(out["T"][0], T, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(out["R"][0], R, rtol=0, atol=1e-12)
+
+
+def test_thickness_sweep_axis(eng, ref_cases):
+    cases = [ref_cases[f"c3_sub_d{k}"] for k in (0, 33333, 66666, 99999)]
+    c = cases[0]
+    n = np.asarray(c["n"])
+    sweep_d = np.array([cc["d"][2] for cc in cases])
+    res = eng.eval_grid(c["wl"], c["theta"], n.real, n.imag, list(range(n.shape[0])), list(c["d"]), POLS, sweep_layer=2,
+                        sweep_d=sweep_d, cos_theta=np.cos(c["theta"])).numpy()
+    assert res["R"].shape == (4, 2, len(c["wl"]), len(c["theta"]))
+    for i, cc in enumerate(cases):
+        single = run_case(eng, cc)
+        assert np.array_equal(res["R"][i], single["R"][0]) and np.array_equal(res["T"][i], single["T"][0])
+
+
+def test_thick_absorber_and_deep_bragg_stay_finite(eng):
+    from pistachio_b200._cabi import FLAG_FORCE_DEEP_KERNEL
+
+    wl = np.linspace(0.8, 1.25, 16)
+    n = np.array([np.full(16, 1.0 + 0j), np.full(16, 2.0 + 10.0j), np.full(16, 1.5 + 0j)])
+    out = eng.eval_grid(wl, [0.0, 0.7], n.real, n.imag, [0, 1, 2], [0.0, 200.0, 0.0]).numpy()
+    assert np.isfinite(out["R"]).all() and (out["T"] == 0).all() and (out["R"] > 0).all() and (out["R"] < 1).all()
+    L = 2000
+    mat_n = np.array([np.full(16, 1.0), np.full(16, 2.32), np.full(16, 1.36), np.full(16, 1.5)])
+    layer_mat = [0] + [1 if j % 2 == 0 else 2 for j in range(L)] + [3]
+    d = [0.0] + [1.0 / (4 * (2.32 if j % 2 == 0 else 1.36)) for j in range(L)] + [0.0]
+    for flags in (0, FLAG_FORCE_DEEP_KERNEL):
+        out = eng.eval_grid(wl, [0.0], mat_n, np.zeros_like(mat_n), layer_mat, d, ("s-wave",), flags=flags).numpy()
+        assert np.isfinite(out["R"]).all() and np.isfinite(out["T"]).all()
+        assert (out["R"] >= 0).all() and (out["R"] <= 1 + 1e-12).all() and (out["T"] >= 0).all()
+        np.testing.assert_allclose(out["R"] + out["T"], 1.0, atol=1e-9)
+
+
+def test_invalid_arguments_raise(eng):
+    wl, th = [1.0], [0.0]
+    n, k = [[1.0], [1.5]], [[0.0], [0.0]]
+    with pytest.raises(ValueError):
+        eng.eval_grid(wl, th, n, k, [0], [0.0])  # fewer than two layers
+    with pytest.raises(ValueError):
+        eng.eval_grid(wl, th, n, k, [0, 2], [0.0, 0.0])  # material index out of range
+    with pytest.raises(ValueError):
+        eng.eval_grid(wl, th, n, k, [0, 1], [0.0, 0.0], ("x-wave",))
+    with pytest.raises(ValueError):
+        eng.eval_grid(wl, th, n, k, [0, 1], [0.0, 0.0], sweep_layer=1, sweep_d=[1.0])  # sweep layer must be interior
+
+
+# ------------------------------------------------------------------------------------------------ host-buffer call
+def test_host_pipeline_equals_device_path(eng, ref_cases):
+    from pistachio_b200 import workloads
+
+    w = workloads.c2_dbr_cavity(n_wl=700, n_theta=129, pairs=6)
+    prep = eng.prepare_workload(w)
+    dev = eng.eval_prepared(prep).numpy()
+    mat_n, mat_k = prep["mat_n"].cpu().numpy(), prep["mat_k"].cpu().numpy()
+    host = eng.eval_grid_host(w.wl, w.theta, mat_n, mat_k, prep["layer_mat"], prep["layer_d"])
+    for key in ("R", "T", "A"):
+        assert np.array_equal(host[key], dev[key]), key
+    # pinned, caller-provided outputs and a thickness sweep (several chunks in flight)
+    w = workloads.c5_box_sweep(n_wl=300, n_theta=40, n_d=30)
+    prep = eng.prepare_workload(w)
+    dev = eng.eval_prepared(prep).numpy()
+    shape = dev["R"].shape
+    outs = {k: torch.empty(shape, dtype=torch.float64).pin_memory() for k in ("R", "T", "A")}
+    host = eng.eval_grid_host(w.wl, w.theta, prep["mat_n"].cpu().numpy(), prep["mat_k"].cpu().numpy(), prep["layer_mat"],
+                              prep["layer_d"], sweep_layer=w.sweep_layer, sweep_d=w.sweep_d, out=outs)
+    for key in ("R", "T", "A"):
+        assert np.array_equal(host[key], dev[key]), key
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_c2_full_size_properties(eng):
+    """BASELINE configs[1] at full size (8192 x 1024 x 2 = 16.8M points, 83 layers): size-independent properties plus a
+    live oracle comparison on a strided sub-grid."""
+    from pistachio_b200 import workloads
+
+    w = workloads.c2_dbr_cavity()
+    prep = eng.prepare_workload(w)
+    res = eng.eval_prepared(prep)
+    torch.cuda.synchronize()
+    R, T, A = res.R[0], res.T[0], res.A[0]
+    assert R.shape == (2, 8192, 1024)
+    assert bool(torch.isfinite(R).all()) and bool(torch.isfinite(T).all())
+    assert bool((R >= 0).all()) and bool((R <= 1 + 1e-12).all()) and bool((T >= -1e-15).all())
+    assert bool(((1.0 - R) - T == A).all())                         # A is exactly (1 - R) - T
+    assert float(A.min()) > -1e-9                                    # passive stack: no gain
+    # in the reference's model (same theta in every layer) s and p differ only by rounding
+    assert float((R[0] - R[1]).abs().max()) < 1e-7 and float((T[0] - T[1]).abs().max()) < 1e-7
+    # the theta = 0 column equals a separate normal-incidence launch, bit for bit
+    single = eng.eval_grid(prep["wl"], prep["theta"][:1], prep["mat_n"], prep["mat_k"], prep["layer_mat"], prep["layer_d"])
+    assert bool((single.R[0, :, :, 0] == R[:, :, 0]).all()) and bool((single.T[0, :, :, 0] == T[:, :, 0]).all())
+    # live oracle on a sub-grid
+    sel_l = np.arange(5, 8192, 512)
+    sel_t = np.array([0, 400, 1023])
+    n_list = []
+    mat_n, mat_k = prep["mat_n"].cpu().numpy(), prep["mat_k"].cpu().numpy()
+    for m in prep["layer_mat"]:
+        n_list.append(mat_n[m][sel_l] + 1j * mat_k[m][sel_l])
+    got_T = T.cpu().numpy()[:, sel_l][:, :, sel_t]
+    got_R = R.cpu().numpy()[:, sel_l][:, :, sel_t]
+    rep = parity.compare_grid("c2_full_sub", got_T, got_R, w.wl[sel_l], n_list, prep["layer_d"], w.theta[sel_t])
+    rep.check(max_loose_fraction=0.10)
+
+
+def test_c4_full_size_properties(eng):
+    """BASELINE configs[3]: 10 000 lossless layers x 16 384 wavelengths through the scan kernel."""
+    from pistachio_b200 import workloads
+    from pistachio_b200._cabi import FLAG_FORCE_POINT_KERNEL
+
+    w = workloads.c4_chirped()
+    prep = eng.prepare_workload(w)
+    assert prep["mat_n"].shape[0] == 4  # air, H, L, substrate: 10 002 layers share 4 material columns
+    deep = eng.eval_prepared(prep, pols=("s-wave",))
+    point = eng.eval_prepared(prep, pols=("s-wave",), flags=FLAG_FORCE_POINT_KERNEL)
+    torch.cuda.synchronize()
+    R, T = deep.R[0, 0, :, 0], deep.T[0, 0, :, 0]
+    assert bool(torch.isfinite(R).all()) and bool((R >= 0).all()) and bool((R <= 1).all())
+    assert float((R + T - 1.0).abs().max()) < 1e-10  # lossless: R + T = 1
+    assert float((deep.R - point.R).abs().max()) < 5e-11 and float((deep.T - point.T).abs().max()) < 5e-11
