@@ -221,8 +221,10 @@ def run_ours(args):
     out = {k: torch.empty(shape, dtype=torch.float64, device=eng.device) for k in ("R", "T", "A")}
     stream = torch.cuda.current_stream()
 
+    flags = 16 if args.no_layer_cse else 0  # PST_FLAG_NO_LAYER_CSE
+
     def step():
-        eng.eval_prepared(prep, pols=pols, out=out)
+        eng.eval_prepared(prep, pols=pols, out=out, flags=flags)
 
     def barrier():
         torch.cuda.synchronize()
@@ -268,7 +270,7 @@ def run_ours(args):
 
     def e2e_step():
         eng.eval_grid_host(wl_h, th_h, mat_n_h, mat_k_h, prep["layer_mat"], prep["layer_d"], pols,
-                           sweep_layer=w.sweep_layer, sweep_d=sw_h, out=out_h)
+                           sweep_layer=w.sweep_layer, sweep_d=sw_h, out=out_h, flags=flags)
 
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(2):
@@ -314,7 +316,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": desc, "points_per_gpu": points_rank, "interior_layers": w.interior_layers,
+        "config": {"workload": desc, "layer_cse": not args.no_layer_cse, "points_per_gpu": points_rank, "interior_layers": w.interior_layers,
                    "layer_steps_per_s": value * w.interior_layers, "l2": "flushed between steps (256 MiB memset); outputs 403 MB/step > L2",
                    "timing": "CUDA events per step on the launch stream, max over ranks", "wall_s_incl_flush": t_wall},
         "roofline": {"bound": "fp64_pipe", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -344,6 +346,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-layer-cse", action="store_true", help="ablation: rebuild every layer matrix (PST_FLAG_NO_LAYER_CSE)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

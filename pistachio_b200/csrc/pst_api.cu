@@ -84,6 +84,9 @@ struct pst_handle_s {
   DevBuf<LayerEntry> layers_dev;
   std::vector<LayerEntry> layers_host;  // what layers_dev currently holds
   DevBuf<int> taboff;
+  DevBuf<int> mat_flags;
+  int n_types = 0;                 // layer-type analysis of the current layer list (sync_layers)
+  int type_layer[kMaxTypes] = {0};
   DevBuf<unsigned char> l2buf;
   DevBuf<double> sink;
   // host-buffer pipeline (pst_eval_grid_host)
@@ -124,7 +127,7 @@ extern "C" int pst_destroy(pst_handle_t h) {
   if (!h) return PST_OK;
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
-  h->opt.release(); h->trig.release(); h->layers_dev.release(); h->taboff.release(); h->l2buf.release();
+  h->opt.release(); h->trig.release(); h->layers_dev.release(); h->taboff.release(); h->mat_flags.release(); h->l2buf.release();
   h->sink.release(); h->hp_in.release(); h->hp_out[0].release(); h->hp_out[1].release();
   for (int i = 0; i < 2; ++i) {
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -170,21 +173,22 @@ namespace {
 
 using ChainKernel = void (*)(const GridParams);
 
-template <int NPOL, int NCOL, bool SO, bool SL, bool SEG>
-ChainKernel chain_variant() {
-  return tmm_chain_kernel<NPOL, NCOL, SO, SL, SEG>;
+template <int P, int C>
+ChainKernel chain_variant(bool so, bool sl, bool seg, bool typed) {
+#define PST_V(O, L, S, T) \
+  if (so == O && sl == L && seg == S && typed == T) return tmm_chain_kernel<P, C, O, L, S, T>;
+#define PST_V2(O, L) PST_V(O, L, false, false) PST_V(O, L, false, true) PST_V(O, L, true, false) PST_V(O, L, true, true)
+  PST_V2(true, true) PST_V2(true, false) PST_V2(false, true) PST_V2(false, false)
+#undef PST_V2
+#undef PST_V
+  return nullptr;
 }
 
-ChainKernel pick_chain(int npol, int ncol, bool so, bool sl, bool seg) {
-#define PST_V(P, C, O, L, S) \
-  if (npol == P && ncol == C && so == O && sl == L && seg == S) return chain_variant<P, C, O, L, S>();
-#define PST_V4(P, C)                                                                          \
-  PST_V(P, C, true, true, false) PST_V(P, C, true, false, false) PST_V(P, C, false, true, false) \
-  PST_V(P, C, false, false, false) PST_V(P, C, true, true, true) PST_V(P, C, true, false, true)  \
-  PST_V(P, C, false, true, true) PST_V(P, C, false, false, true)
-  PST_V4(1, 1) PST_V4(1, 2) PST_V4(2, 1) PST_V4(2, 2)
-#undef PST_V4
-#undef PST_V
+ChainKernel pick_chain(int npol, int ncol, bool so, bool sl, bool seg, bool typed) {
+  if (npol == 1 && ncol == 1) return chain_variant<1, 1>(so, sl, seg, typed);
+  if (npol == 1 && ncol == 2) return chain_variant<1, 2>(so, sl, seg, typed);
+  if (npol == 2 && ncol == 1) return chain_variant<2, 1>(so, sl, seg, typed);
+  if (npol == 2 && ncol == 2) return chain_variant<2, 2>(so, sl, seg, typed);
   return nullptr;
 }
 
@@ -215,10 +219,39 @@ int validate_grid(const pst_grid_args* a, const char* who) {
   return PST_OK;
 }
 
-// Upload the layer list when it differs from what the device copy holds.
+// Layer list -> device, with the layer-type analysis of the typed path: interior layers with the same
+// (material, thickness) get the same type id; the swept layer is a type of its own.
 int sync_layers(pst_handle_t h, const pst_grid_args* a, cudaStream_t st) {
   std::vector<LayerEntry> cur(a->n_layers);
-  for (int j = 0; j < a->n_layers; ++j) cur[j] = LayerEntry{a->layer_d[j], a->layer_mat[j], 0};
+  h->n_types = 0;
+  bool overflow = false;
+  for (int j = 0; j < a->n_layers; ++j) {
+    cur[j] = LayerEntry{a->layer_d[j], a->layer_mat[j], -1};
+    if (j == 0 || j == a->n_layers - 1 || overflow) continue;
+    int t = -1;
+    if (j != a->sweep_layer) {
+      for (int u = 0; u < h->n_types; ++u) {
+        const int r = h->type_layer[u];
+        if (r != a->sweep_layer && cur[r].mat == cur[j].mat && std::memcmp(&cur[r].d, &cur[j].d, sizeof(double)) == 0) {
+          t = u;
+          break;
+        }
+      }
+    }
+    if (t < 0) {
+      if (h->n_types == kMaxTypes) {
+        overflow = true;
+        continue;
+      }
+      t = h->n_types++;
+      h->type_layer[t] = j;
+    }
+    cur[j].type = t;
+  }
+  if (overflow) {
+    h->n_types = 0;
+    for (auto& e : cur) e.type = -1;
+  }
   const bool same = cur.size() == h->layers_host.size() &&
                     std::memcmp(cur.data(), h->layers_host.data(), cur.size() * sizeof(LayerEntry)) == 0;
   if (same) return PST_OK;
@@ -228,13 +261,16 @@ int sync_layers(pst_handle_t h, const pst_grid_args* a, cudaStream_t st) {
   return PST_OK;
 }
 
-// opt table + trig table for the whole grid (device pointers)
+// opt table + material flags + trig table for the whole grid (device pointers)
 int run_prep(pst_handle_t h, const pst_grid_args* a, const double* wl, const double* theta, const double* cos_theta,
              const double* mat_n, const double* mat_k, cudaStream_t st) {
   const long long nm = (long long)a->n_wl * a->n_mat;
   PST_TRY(h->opt.ensure((size_t)nm * 6));
   PST_TRY(h->trig.ensure(a->n_theta));
-  prep_optical_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(wl, mat_n, mat_k, a->n_wl, a->n_mat, h->opt.p);
+  PST_TRY(h->mat_flags.ensure(a->n_mat));
+  PST_CUDA(cudaMemsetAsync(h->mat_flags.p, 0, a->n_mat * sizeof(int), st));
+  prep_optical_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(wl, mat_n, mat_k, a->n_wl, a->n_mat, h->opt.p,
+                                                                   h->mat_flags.p);
   PST_CUDA(cudaGetLastError());
   prep_trig_kernel<<<(a->n_theta + 255) / 256, 256, 0, st>>>(theta, cos_theta, a->n_theta, h->trig.p);
   PST_CUDA(cudaGetLastError());
@@ -243,8 +279,8 @@ int run_prep(pst_handle_t h, const pst_grid_args* a, const double* wl, const dou
 }
 
 struct ChainPlan {
-  int npol, ncol, W, PB, tl;
-  bool so, sl, seg;
+  int npol, ncol, W, PB, tl_rows, opt_row_bytes, type_stride;
+  bool so, sl, seg, typed;
   size_t smem;
   ChainKernel fn;
 };
@@ -267,39 +303,60 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
   pl->W = W;
   pl->seg = W > 1;
   pl->PB = pl->seg ? 32 : 128;
-  pl->tl = std::min(n_wl_launch, (pl->PB - 1) / a->n_theta + 2);
+  const int nthr = pl->PB * W;
+  // typed path: worth it when layer matrices repeat (fewer distinct types than interior layers per segment)
+  pl->typed = !(a->flags & PST_FLAG_NO_LAYER_CSE) && h->n_types > 0 && Li / W > h->n_types;
+  pl->type_stride = 0;
+  if (pl->typed) {
+    int units = h->n_types * (kTypeRecBytes / 16);
+    if (units % 2 == 0) units += 1;
+    pl->type_stride = units * 16;
+  }
+  pl->tl_rows = std::min(n_wl_launch, (pl->PB - 1) / a->n_theta + 2);
+  pl->opt_row_bytes = a->n_mat * 48 + ((a->n_mat % 2 == 0) ? 16 : 0);
   const size_t budget = std::min<size_t>(h->smem_optin, 200 * 1024);
   const size_t seg_bytes = pl->seg ? (size_t)W * pl->npol * 9 * pl->PB * sizeof(double) : 0;
+  size_t type_bytes = pl->typed ? (size_t)nthr * pl->type_stride : 0;
+  if (seg_bytes + type_bytes > budget * 3 / 4) {
+    pl->typed = false;
+    type_bytes = 0;
+  }
   const size_t lay_bytes = (size_t)a->n_layers * sizeof(LayerEntry);
-  const size_t opt_bytes = (size_t)a->n_mat * 6 * pl->tl * sizeof(double);
-  pl->sl = lay_bytes <= 64 * 1024 && seg_bytes + lay_bytes <= budget;
-  size_t used = seg_bytes + (pl->sl ? lay_bytes : 0);
-  pl->so = !(a->flags & PST_FLAG_NO_SMEM_STAGING) && used + opt_bytes <= std::min<size_t>(budget, 96 * 1024);
+  const size_t opt_bytes = (size_t)pl->tl_rows * pl->opt_row_bytes;
+  pl->sl = lay_bytes <= 64 * 1024 && seg_bytes + type_bytes + lay_bytes <= budget;
+  size_t used = seg_bytes + type_bytes + (pl->sl ? lay_bytes : 0);
+  pl->so = !(a->flags & PST_FLAG_NO_SMEM_STAGING) && used + opt_bytes <= std::min<size_t>(budget, std::max<size_t>(96 * 1024, used + 16 * 1024));
   used += pl->so ? opt_bytes : 0;
   if (used > budget) return fail(PST_E_INVALID, "pst_eval_grid: shared-memory plan exceeds the device limit");
   pl->smem = used;
-  pl->fn = pick_chain(pl->npol, pl->ncol, pl->so, pl->sl, pl->seg);
+  pl->fn = pick_chain(pl->npol, pl->ncol, pl->so, pl->sl, pl->seg, pl->typed);
   if (!pl->fn) return fail(PST_E_INVALID, "pst_eval_grid: no kernel variant for this configuration");
   if (used > 48 * 1024) PST_CUDA(cudaFuncSetAttribute((const void*)pl->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
   return PST_OK;
 }
 
 // Launch the chain kernel for wavelengths [il0, il0 + n_wl_launch) of the prepared grid.  Output pointers address
-// the first element of that wavelength window; `plane` is the element distance between (sweep, pol) planes.
+// the first element of that wavelength window; a (sweep, pol) plane holds n_wl_launch * n_theta elements.
 int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, int il0, int n_wl_launch,
                  const double* sweep_d_dev, double* R, double* T, double* A, double* M, cudaStream_t st) {
   GridParams prm;
+  std::memset(&prm, 0, sizeof(prm));
   prm.n_wl = a->n_wl;
   prm.n_theta = a->n_theta;
   prm.n_mat = a->n_mat;
   prm.n_layers = a->n_layers;
   prm.sweep_layer = a->sweep_layer;
   prm.pol_first = (a->pol_mask & PST_POL_S) ? 0 : 1;
-  prm.tl_stride = pl.tl;
-  prm.flags = a->flags;
+  prm.tl_rows = pl.tl_rows;
+  prm.opt_row_bytes = pl.opt_row_bytes;
   prm.il0 = il0;
+  prm.n_types = pl.typed ? h->n_types : 0;
+  prm.type_stride = pl.type_stride;
+  for (int t = 0; t < kMaxTypes; ++t) prm.type_layer[t] = h->type_layer[t];
+  prm.flags = a->flags;
   prm.points = (long long)n_wl_launch * a->n_theta;
   prm.opt = h->opt.p;
+  prm.mat_flags = h->mat_flags.p;
   prm.trig = h->trig.p;
   prm.layers = h->layers_dev.p;
   const long long nblk = (prm.points + pl.PB - 1) / pl.PB;

@@ -1,6 +1,6 @@
-// Per-point arithmetic of the TMM chain: layer step, exact rescaling, ordered segment combine, epilogue.
-// Everything here is __host__ __device__ so that tests/host_emul can execute the same source on the CPU box;
-// the shipped library only ever calls it from kernels (pst_kernels.cuh).
+// Per-point arithmetic of the TMM chain: layer-matrix build, layer step, exact rescaling, ordered segment combine,
+// epilogue.  Everything here is __host__ __device__ so that tests/host_emul can execute the same source on the CPU
+// box; the shipped library only ever calls it from kernels (pst_kernels.cuh).
 //
 // Model (reference tm.py:190-277, 559-568, 482-486), phi = kx d, a = n g with
 // g = cos(theta) for s-waves and 1/cos(theta) for p-waves (same theta in every layer: the reference has no Snell
@@ -20,8 +20,10 @@ struct ChainState {
   int kexp[NPOL];
 };
 
-struct OptRow {  // optical constants of one (material, wavelength): q = (n w)(1/c), n, 1/n
-  double qr, qi, nr, ni, inr, ini;
+// Optical constants of one (material, wavelength), in shared-memory order (48 bytes, three 16-byte loads):
+//   q = (n w)(1/c) in the reference's rounding order, n, 1/n.  The lossless path reads only the first 24 bytes + ni.
+struct OptRow {
+  double qr, nr, inr, ni, qi, ini;
 };
 
 template <int NPOL>
@@ -29,39 +31,51 @@ PST_HD bool pol_is_s(int p, int pol_first) {
   return (NPOL == 2) ? (p == 0) : (pol_first == 0);
 }
 
-// v <- M_j v for every polarisation/column held by the thread.  sincos of the real phase and cosh/sinh of the
-// attenuation are polarisation independent and evaluated once.
-template <int NPOL, int NC>
-PST_HD void apply_layer(ChainState<NPOL, NC>& st, const OptRow& o, double d, double ct, double ict, int pol_first) {
+// ---- layer matrices ------------------------------------------------------------------------------------------
+// Lossless layer (k = 0 at every wavelength of its material): phi and n real,
+//   M = [[c, -i be], [-i al, c]],  al = a sin(phi), be = sin(phi)/a, one (al, be) pair per polarisation.
+template <int NPOL>
+struct RealLayer {
+  double c;
+  double al[NPOL], be[NPOL];
+};
+// General layer: M = 2^sc [[cphi, m01], [m10, cphi]] with complex entries.
+template <int NPOL>
+struct CplxLayer {
+  cplx cphi;
+  cplx m10[NPOL], m01[NPOL];
+  int sc;
+};
+
+template <int NPOL>
+PST_HD RealLayer<NPOL> build_real_layer(double qr, double nr, double inr, double d, double ct, double ict,
+                                        int pol_first) {
   // phase in the reference's rounding order: kx = q cos(theta) (tm.py:270), argument = kx d (tm.py:234)
-  const double x = mul_rn(mul_rn(o.qr, ct), d);
+  const double x = mul_rn(mul_rn(qr, ct), d);
   double sx, cx;
-  sincos(x, &sx, &cx);
-  if (o.ni == 0.0) {
-    // lossless layer: phi and n real, M = [[c, -i s/(n g)], [-i s n g, c]]
-    const double sn = sx * o.nr, si = sx * o.inr;
+  sincos_fast(x, sx, cx);
+  const double sn = sx * nr, si = sx * inr;
+  RealLayer<NPOL> m;
+  m.c = cx;
 #pragma unroll
-    for (int p = 0; p < NPOL; ++p) {
-      const bool is_s = pol_is_s<NPOL>(p, pol_first);
-      const double al = (is_s ? ct : ict) * sn;  // a sin(phi)
-      const double be = (is_s ? ict : ct) * si;  // sin(phi) / a
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        double* v = st.v[p][c];
-        const double v0r = v[0], v0i = v[1], v1r = v[2], v1i = v[3];
-        v[0] = fma(cx, v0r, be * v1i);
-        v[1] = fma(cx, v0i, -(be * v1r));
-        v[2] = fma(cx, v1r, al * v0i);
-        v[3] = fma(cx, v1i, -(al * v0r));
-      }
-    }
-    return;
+  for (int p = 0; p < NPOL; ++p) {
+    const bool is_s = pol_is_s<NPOL>(p, pol_first);
+    m.al[p] = (is_s ? ct : ict) * sn;
+    m.be[p] = (is_s ? ict : ct) * si;
   }
+  return m;
+}
+
+template <int NPOL>
+PST_HD CplxLayer<NPOL> build_cplx_layer(const OptRow& o, double d, double ct, double ict, int pol_first) {
+  const double x = mul_rn(mul_rn(o.qr, ct), d);
   const double y = mul_rn(mul_rn(o.qi, ct), d);
-  double ch, sh;
-  const int sc = cosh_sinh_scaled(y, ch, sh);
+  double sx, cx, ch, sh;
+  sincos_fast(x, sx, cx);
+  CplxLayer<NPOL> m;
+  m.sc = cosh_sinh_scaled(y, ch, sh);
   // cos(x+iy) = cos x cosh y - i sin x sinh y ; sin(x+iy) = sin x cosh y + i cos x sinh y   (both times 2^sc)
-  const cplx cphi = {cx * ch, -(sx * sh)};
+  m.cphi = {cx * ch, -(sx * sh)};
   const cplx sphi = {sx * ch, cx * sh};
   const cplx sn = cmul(sphi, {o.nr, o.ni});
   const cplx si = cmul(sphi, {o.inr, o.ini});
@@ -69,34 +83,72 @@ PST_HD void apply_layer(ChainState<NPOL, NC>& st, const OptRow& o, double d, dou
   for (int p = 0; p < NPOL; ++p) {
     const bool is_s = pol_is_s<NPOL>(p, pol_first);
     const double g = is_s ? ct : ict, gi = is_s ? ict : ct;
-    const cplx m10 = {g * sn.im, -(g * sn.re)};    // -i a sin(phi)
-    const cplx m01 = {gi * si.im, -(gi * si.re)};  // -i sin(phi) / a
+    m.m10[p] = {g * sn.im, -(g * sn.re)};    // -i a sin(phi)
+    m.m01[p] = {gi * si.im, -(gi * si.re)};  // -i sin(phi) / a
+  }
+  return m;
+}
+
+// v <- M v for every polarisation/column held by the thread
+template <int NPOL, int NC>
+PST_HD void apply_real_layer(ChainState<NPOL, NC>& st, const RealLayer<NPOL>& m) {
+#pragma unroll
+  for (int p = 0; p < NPOL; ++p) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      double* v = st.v[p][c];
+      const double v0r = v[0], v0i = v[1], v1r = v[2], v1i = v[3];
+      v[0] = fma(m.c, v0r, m.be[p] * v1i);
+      v[1] = fma(m.c, v0i, -(m.be[p] * v1r));
+      v[2] = fma(m.c, v1r, m.al[p] * v0i);
+      v[3] = fma(m.c, v1i, -(m.al[p] * v0r));
+    }
+  }
+}
+
+template <int NPOL, int NC>
+PST_HD void apply_cplx_layer(ChainState<NPOL, NC>& st, const CplxLayer<NPOL>& m) {
+#pragma unroll
+  for (int p = 0; p < NPOL; ++p) {
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       double* v = st.v[p][c];
       const cplx v0 = {v[0], v[1]}, v1 = {v[2], v[3]};
-      v[0] = fma(cphi.re, v0.re, fma(-cphi.im, v0.im, fma(m01.re, v1.re, -(m01.im * v1.im))));
-      v[1] = fma(cphi.re, v0.im, fma(cphi.im, v0.re, fma(m01.re, v1.im, m01.im * v1.re)));
-      v[2] = fma(m10.re, v0.re, fma(-m10.im, v0.im, fma(cphi.re, v1.re, -(cphi.im * v1.im))));
-      v[3] = fma(m10.re, v0.im, fma(m10.im, v0.re, fma(cphi.re, v1.im, cphi.im * v1.re)));
+      v[0] = fma(m.cphi.re, v0.re, fma(-m.cphi.im, v0.im, fma(m.m01[p].re, v1.re, -(m.m01[p].im * v1.im))));
+      v[1] = fma(m.cphi.re, v0.im, fma(m.cphi.im, v0.re, fma(m.m01[p].re, v1.im, m.m01[p].im * v1.re)));
+      v[2] = fma(m.m10[p].re, v0.re, fma(-m.m10[p].im, v0.im, fma(m.cphi.re, v1.re, -(m.cphi.im * v1.im))));
+      v[3] = fma(m.m10[p].re, v0.im, fma(m.m10[p].im, v0.re, fma(m.cphi.re, v1.im, m.cphi.im * v1.re)));
     }
-    st.kexp[p] += sc;
+    st.kexp[p] += m.sc;
   }
 }
 
-// Pull a power of two out of the state (exact) so that products cannot overflow in deep stop bands.
+// Build + apply in one go (the untyped path).  `lossless` is the MATERIAL's flag (k = 0 at every wavelength), so
+// the branch is uniform over the block.
+template <int NPOL, int NC>
+PST_HD void apply_layer(ChainState<NPOL, NC>& st, const OptRow& o, bool lossless, double d, double ct, double ict,
+                        int pol_first) {
+  if (lossless) apply_real_layer<NPOL, NC>(st, build_real_layer<NPOL>(o.qr, o.nr, o.inr, d, ct, ict, pol_first));
+  else apply_cplx_layer<NPOL, NC>(st, build_cplx_layer<NPOL>(o, d, ct, ict, pol_first));
+}
+
+// Pull a power of two out of the state (exact) so that products cannot overflow in deep stop bands.  The largest
+// magnitude is found on the high words with integer max (one issue slot each instead of an FP64 compare + selects).
 template <int NPOL, int NC>
 PST_HD void renormalise(ChainState<NPOL, NC>& st) {
 #pragma unroll
   for (int p = 0; p < NPOL; ++p) {
-    double m = 0.0;
+    unsigned m = 0;
 #pragma unroll
     for (int c = 0; c < NC; ++c)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) m = fmax(m, fabs(st.v[p][c][k]));
-    int e = exponent_of(m);
-    e = e > 1000 ? 1000 : (e < -1000 ? -1000 : e);
-    const double s = pow2i(-e);
+      for (int k = 0; k < 4; ++k) {
+        const unsigned h = (unsigned)hi_word(st.v[p][c][k]) & 0x7fffffffu;
+        m = h > m ? h : m;
+      }
+    int e = (int)(m >> 20) - 1023;  // floor(log2 max|v|); -1023 for zero/denormal, 1024 for inf/nan
+    e = e > 1000 ? 1000 : (e < -1000 ? 0 : e);
+    const double s = from_words((1023 - e) << 20, 0);
 #pragma unroll
     for (int c = 0; c < NC; ++c)
 #pragma unroll
@@ -173,15 +225,16 @@ PST_HD PointOut finish_point(const ChainState<NPOL, NCOL>& fin, int p, double in
   PointOut out;
   const double den = fma(m[0][0].re, m[0][0].re, m[0][0].im * m[0][0].im);  // |M00|^2 (scaled by 2^-2kexp)
   const double num = fma(m[0][1].re, m[0][1].re, m[0][1].im * m[0][1].im);  // |M10|^2
-  out.R = num / den;
+  const double iden = 1.0 / den;
+  out.R = num * iden;
   // det M = a_last / a_first = n_f / n_0 for both polarisations (the cos factors cancel)
   const double det_re = fma(nfr, in0r, -(nfi * in0i));
-  out.T = ldexp(det_re / den, -2 * fin.kexp[p]);
+  out.T = ldexp(det_re * iden, -2 * fin.kexp[p]);
   if constexpr (NCOL == 2) {
     if (flags & 4u) {
       // numeric determinant like np.linalg.det (tm.py:486); the 2^kexp factors cancel
       const cplx det = csub(cmul(m[0][0], m[1][1]), cmul(m[1][0], m[0][1]));
-      out.T = det.re / den;
+      out.T = det.re * iden;
     }
     const int e = fin.kexp[p];
     out.M[0] = ldexp(m[0][0].re, e); out.M[1] = ldexp(m[0][0].im, e);
@@ -198,7 +251,11 @@ PST_HD PointOut finish_point(const ChainState<NPOL, NCOL>& fin, int p, double in
 PST_HD OptRow make_opt_row(double wl, double nr, double ni) {
   const double omega = div_rn(kTwoPiC, wl);
   const cplx inv = crecip({nr, ni});
-  return {mul_rn(mul_rn(nr, omega), kInvC0), mul_rn(mul_rn(ni, omega), kInvC0), nr, ni, inv.re, inv.im};
+  OptRow r;
+  r.qr = mul_rn(mul_rn(nr, omega), kInvC0);
+  r.qi = mul_rn(mul_rn(ni, omega), kInvC0);
+  r.nr = nr; r.ni = ni; r.inr = inv.re; r.ini = inv.im;
+  return r;
 }
 
 }  // namespace pst

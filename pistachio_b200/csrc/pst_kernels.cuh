@@ -25,18 +25,27 @@ namespace pst {
 struct LayerEntry {  // 16 bytes: one LDS.128 / LDG.128 per layer
   double d;
   int mat;
-  int pad;
+  int type;  // index into the per-thread layer-matrix cache (typed path); -1 when unused
 };
+
+constexpr int kMaxTypes = 8;        // distinct (material, thickness) pairs the typed path caches per thread
+constexpr int kTypeRecBytes = 96;   // one cached layer matrix: 12 doubles (complex form) or 6 (real form)
+constexpr int kRenormEvery = 16;
 
 struct GridParams {
   int n_wl, n_theta, n_mat, n_layers;
   int sweep_layer;   // -1: none
   int pol_first;     // NPOL == 1: 0 = s, 1 = p
-  int tl_stride;     // doubles per (mat, param) row in shared memory (>= max lambdas per block)
+  int tl_rows;       // wavelength rows of the shared-memory optical table (>= max wavelengths per block)
+  int opt_row_bytes; // bytes per wavelength row in shared memory: n_mat*48 (+16 pad when n_mat is even)
   int il0;           // first wavelength index of this launch (host pipeline launches wavelength windows)
+  int n_types;       // typed path: number of cached layer types
+  int type_stride;   // typed path: bytes of cache per thread (odd multiple of 16: conflict-free LDS.128)
+  int type_layer[kMaxTypes];  // representative layer index of each type
   unsigned flags;
-  long long points;  // n_wl * n_theta
-  const double* opt;        // [n_mat][6][n_wl]: q.re q.im n.re n.im (1/n).re (1/n).im
+  long long points;  // wavelengths of this launch * n_theta
+  const double* opt;        // [n_wl][n_mat][6]: OptRow order qr nr inr ni qi ini
+  const int* mat_flags;     // [n_mat] bit0: k != 0 at some wavelength
   const double2* trig;      // [n_theta] (cos, 1/cos)
   const LayerEntry* layers; // [n_layers]
   const double* sweep_d;    // [gridDim.y] or nullptr
@@ -90,19 +99,18 @@ __global__ void resample_kernel(int n_tab, const int* __restrict__ tab_off, cons
 // ------------------------------------------------------------------------------------------- prep
 __global__ void prep_optical_kernel(const double* __restrict__ wl, const double* __restrict__ mat_n,
                                     const double* __restrict__ mat_k, int n_wl, int n_mat,
-                                    double* __restrict__ opt) {
+                                    double* __restrict__ opt, int* __restrict__ mat_flags) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)n_wl * n_mat) return;
   const int m = (int)(idx / n_wl);
   const int i = (int)(idx - (long long)m * n_wl);
-  const OptRow r = make_opt_row(wl[i], mat_n[idx], mat_k[idx]);
-  double* o = opt + (size_t)m * 6 * n_wl + i;
-  o[0] = r.qr;
-  o[(size_t)n_wl] = r.qi;
-  o[(size_t)2 * n_wl] = r.nr;
-  o[(size_t)3 * n_wl] = r.ni;
-  o[(size_t)4 * n_wl] = r.inr;
-  o[(size_t)5 * n_wl] = r.ini;
+  const double nk = mat_k[idx];
+  const OptRow r = make_opt_row(wl[i], mat_n[idx], nk);
+  double2* o = reinterpret_cast<double2*>(opt + ((size_t)i * n_mat + m) * 6);
+  o[0] = make_double2(r.qr, r.nr);
+  o[1] = make_double2(r.inr, r.ni);
+  o[2] = make_double2(r.qi, r.ini);
+  if (nk != 0.0) atomicOr(mat_flags + m, 1);  // the material absorbs (or amplifies) somewhere on the grid
 }
 
 __global__ void prep_trig_kernel(const double* __restrict__ theta, const double* __restrict__ cos_theta, int n_theta,
@@ -114,9 +122,14 @@ __global__ void prep_trig_kernel(const double* __restrict__ theta, const double*
 }
 
 // ------------------------------------------------------------------------------------ K1 / K2
-constexpr int kRenormEvery = 8;
-
-template <int NPOL, int NCOL, bool STAGE_OPT, bool STAGE_LAYERS, bool SEG>
+// One launch covers `points` = (wavelengths of the launch) x n_theta spectral points (theta fastest) for gridDim.y
+// thickness-sweep values; each thread owns one point and both polarisations.
+//   STAGE_OPT / STAGE_LAYERS  optical table window and layer list staged in shared memory once per block
+//   SEG    blockDim.y ordered layer segments per point, combined in order through shared memory (deep stacks)
+//   TYPED  layers with identical (material, thickness) share one layer matrix: every distinct matrix is built once
+//          per thread into a shared-memory cache and the chain loop only applies cached matrices (pure common-
+//          subexpression elimination: the applied matrices are bit-identical to the untyped path's)
+template <int NPOL, int NCOL, bool STAGE_OPT, bool STAGE_LAYERS, bool SEG, bool TYPED>
 __global__ void __launch_bounds__(SEG ? 512 : 256)
 tmm_chain_kernel(const GridParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -131,26 +144,33 @@ tmm_chain_kernel(const GridParams prm) {
   const int TL = prm.il0 + (int)(p_last / prm.n_theta) - l_lo + 1;
   const int L = prm.n_layers;
 
-  // ---- shared-memory carve-up: [optical table][layer list][segment products]
-  double* s_opt = reinterpret_cast<double*>(smem_raw);
-  size_t off = STAGE_OPT ? (size_t)prm.n_mat * 6 * prm.tl_stride * sizeof(double) : 0;
+  // ---- shared-memory carve-up: [optical table][layer list][layer-matrix cache][segment products]
+  unsigned char* s_opt = smem_raw;
+  size_t off = STAGE_OPT ? (size_t)prm.tl_rows * prm.opt_row_bytes : 0;
   LayerEntry* s_layers = reinterpret_cast<LayerEntry*>(smem_raw + off);
   off += STAGE_LAYERS ? (size_t)L * sizeof(LayerEntry) : 0;
+  unsigned char* s_types = smem_raw + off;
+  off += TYPED ? (size_t)nthr * prm.type_stride : 0;
   double* s_seg = reinterpret_cast<double*>(smem_raw + off);
 
   if constexpr (STAGE_OPT) {
-    // rows of TL consecutive wavelengths, one row per (material, parameter): coalesced when TL is large,
-    // a handful of scalar loads when a block sits on a single wavelength
-    const int rows = prm.n_mat * 6;
-    for (int idx = tid; idx < rows * TL; idx += nthr) {
-      const int r = idx / TL, c = idx - r * TL;
-      s_opt[r * prm.tl_stride + c] = __ldg(prm.opt + (size_t)r * prm.n_wl + l_lo + c);
+    // the block's wavelength window of the [wl][mat][6] table is one contiguous global range; rows are re-pitched
+    // to opt_row_bytes so that lanes on different wavelengths hit different 16-byte bank groups
+    const int per_row = prm.n_mat * 3;  // 16-byte pieces per wavelength row
+    const int4* src = reinterpret_cast<const int4*>(prm.opt + (size_t)l_lo * prm.n_mat * 6);
+    for (int idx = tid; idx < per_row * TL; idx += nthr) {
+      const int r = idx / per_row, c = idx - r * per_row;
+      *reinterpret_cast<int4*>(s_opt + (size_t)r * prm.opt_row_bytes + c * 16) = __ldg(src + idx);
     }
   }
   if constexpr (STAGE_LAYERS) {
     const int4* src = reinterpret_cast<const int4*>(prm.layers);
     int4* dst = reinterpret_cast<int4*>(s_layers);
-    for (int idx = tid; idx < L; idx += nthr) dst[idx] = __ldg(src + idx);
+    for (int idx = tid; idx < L; idx += nthr) {
+      int4 e = __ldg(src + idx);
+      if constexpr (!TYPED) e.w = __ldg(prm.mat_flags + e.z);  // untyped path: `type` carries the material's flag
+      dst[idx] = e;
+    }
   }
   if constexpr (STAGE_OPT || STAGE_LAYERS) __syncthreads();
 
@@ -164,15 +184,53 @@ tmm_chain_kernel(const GridParams prm) {
   const int sweep = blockIdx.y;
   const double d_sweep = prm.sweep_d ? __ldg(prm.sweep_d + sweep) : 0.0;
 
-  // optical-table accessor for this thread's wavelength
-  const double* optp = STAGE_OPT ? (s_opt + (il - l_lo)) : (prm.opt + il);
-  const size_t pstride = STAGE_OPT ? (size_t)prm.tl_stride : (size_t)prm.n_wl;
+  // optical-table accessor for this thread's wavelength: 48-byte rows, three 16-byte loads
+  const unsigned char* optp = STAGE_OPT ? (s_opt + (size_t)(il - l_lo) * prm.opt_row_bytes)
+                                        : reinterpret_cast<const unsigned char*>(prm.opt + (size_t)il * prm.n_mat * 6);
   const LayerEntry* lay = STAGE_LAYERS ? s_layers : prm.layers;
   auto opt_row = [&](int mat) {
-    const double* o = optp + (size_t)mat * 6 * pstride;
-    return OptRow{o[0], o[pstride], o[2 * pstride], o[3 * pstride], o[4 * pstride], o[5 * pstride]};
+    const double2* o = reinterpret_cast<const double2*>(optp + (size_t)mat * 48);
+    const double2 a = o[0], b = o[1], c = o[2];
+    OptRow r;
+    r.qr = a.x; r.nr = a.y; r.inr = b.x; r.ni = b.y; r.qi = c.x; r.ini = c.y;
+    return r;
+  };
+  auto opt_row_real = [&](int mat, double& qr, double& nr, double& inr) {
+    const double2* o = reinterpret_cast<const double2*>(optp + (size_t)mat * 48);
+    const double2 a = o[0];
+    qr = a.x; nr = a.y; inr = o[1].x;
   };
   const OptRow exit_row = opt_row(lay[L - 1].mat);
+
+  // ---- typed path: build each distinct layer matrix once into this thread's cache
+  unsigned char* my_types = s_types + (size_t)tid * prm.type_stride;
+  unsigned lossy_mask = 0;
+  if constexpr (TYPED) {
+    for (int t = 0; t < prm.n_types; ++t) {
+      const int j = prm.type_layer[t];
+      const LayerEntry le = lay[j];
+      const double d = (j == prm.sweep_layer) ? d_sweep : le.d;
+      double2* rec = reinterpret_cast<double2*>(my_types + t * kTypeRecBytes);
+      if (__ldg(prm.mat_flags + le.mat) == 0) {
+        double qr, nr, inr;
+        opt_row_real(le.mat, qr, nr, inr);
+        const RealLayer<NPOL> m = build_real_layer<NPOL>(qr, nr, inr, d, ct, ict, prm.pol_first);
+        rec[0] = make_double2(m.c, 0.0);
+#pragma unroll
+        for (int pp = 0; pp < NPOL; ++pp) rec[1 + pp] = make_double2(m.al[pp], m.be[pp]);
+      } else {
+        lossy_mask |= 1u << t;
+        const CplxLayer<NPOL> m = build_cplx_layer<NPOL>(opt_row(le.mat), d, ct, ict, prm.pol_first);
+        rec[0] = make_double2(m.cphi.re, m.cphi.im);
+#pragma unroll
+        for (int pp = 0; pp < NPOL; ++pp) {
+          rec[1 + 2 * pp] = make_double2(m.m10[pp].re, m.m10[pp].im);
+          rec[2 + 2 * pp] = make_double2(m.m01[pp].re, m.m01[pp].im);
+        }
+        rec[5] = make_double2(__longlong_as_double((long long)m.sc), 0.0);
+      }
+    }
+  }
 
   // ---- the ordered chain over this thread's segment of interior layers
   const int Li = L - 2;
@@ -184,14 +242,47 @@ tmm_chain_kernel(const GridParams prm) {
   if constexpr (SEG) init_identity<NPOL>(st);
   else init_exit_columns<NPOL, NC>(st, exit_row.nr, exit_row.ni, ct, prm.pol_first);
 
-  int since = 0;
-  for (int j = j_hi - 1; j >= j_lo; --j) {
-    const LayerEntry le = lay[j];
-    const double d = (j == prm.sweep_layer) ? d_sweep : le.d;
-    apply_layer<NPOL, NC>(st, opt_row(le.mat), d, ct, ict, prm.pol_first);
-    if (++since == kRenormEvery) { renormalise<NPOL, NC>(st); since = 0; }
+  int j = j_hi - 1;
+  while (j >= j_lo) {
+    const int j_stop = max(j - kRenormEvery, j_lo - 1);
+    for (; j > j_stop; --j) {
+      if constexpr (TYPED) {
+        const int t = lay[j].type;
+        const double2* rec = reinterpret_cast<const double2*>(my_types + t * kTypeRecBytes);
+        if (!((lossy_mask >> t) & 1u)) {
+          RealLayer<NPOL> m;
+          m.c = rec[0].x;
+#pragma unroll
+          for (int pp = 0; pp < NPOL; ++pp) { const double2 ab = rec[1 + pp]; m.al[pp] = ab.x; m.be[pp] = ab.y; }
+          apply_real_layer<NPOL, NC>(st, m);
+        } else {
+          CplxLayer<NPOL> m;
+          const double2 c0 = rec[0];
+          m.cphi = {c0.x, c0.y};
+#pragma unroll
+          for (int pp = 0; pp < NPOL; ++pp) {
+            const double2 a = rec[1 + 2 * pp], b = rec[2 + 2 * pp];
+            m.m10[pp] = {a.x, a.y};
+            m.m01[pp] = {b.x, b.y};
+          }
+          m.sc = (int)__double_as_longlong(rec[5].x);
+          apply_cplx_layer<NPOL, NC>(st, m);
+        }
+      } else {
+        const LayerEntry le = lay[j];
+        const double d = (j == prm.sweep_layer) ? d_sweep : le.d;
+        const int lossy = STAGE_LAYERS ? le.type : __ldg(prm.mat_flags + le.mat);
+        if (lossy == 0) {
+          double qr, nr, inr;
+          opt_row_real(le.mat, qr, nr, inr);
+          apply_real_layer<NPOL, NC>(st, build_real_layer<NPOL>(qr, nr, inr, d, ct, ict, prm.pol_first));
+        } else {
+          apply_cplx_layer<NPOL, NC>(st, build_cplx_layer<NPOL>(opt_row(le.mat), d, ct, ict, prm.pol_first));
+        }
+      }
+    }
+    renormalise<NPOL, NC>(st);
   }
-  renormalise<NPOL, NC>(st);
 
   ChainState<NPOL, NCOL> fin;
   if constexpr (SEG) {

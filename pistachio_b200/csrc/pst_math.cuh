@@ -108,6 +108,70 @@ PST_HD int cosh_sinh_scaled(double y, double& ch, double& sh) {
   return ka - 1;
 }
 
+// ---- sincos for the layer loop ---------------------------------------------------------------------------
+// Coefficients live in the constant bank so that DFMA takes them as c[bank][offset] operands: the library
+// sincos() materialises each 64-bit constant with two moves, which made kernel v1 issue-bound (profiles/r01_v1).
+// 0..5: sin minimax S1..S6, 6..11: cos minimax C1..C6 on |r| <= pi/4 (fdlibm __kernel_sin/__kernel_cos, error < 2^-58)
+#define PST_SINCOS_COEFS                                                                                       \
+  {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,                       \
+   2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,                        \
+   4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,                        \
+   -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11}
+#ifdef __CUDACC__
+__constant__ double c_sincos[12] = PST_SINCOS_COEFS;
+#endif
+static const double h_sincos[12] = PST_SINCOS_COEFS;
+#ifdef __CUDA_ARCH__
+#define PST_SC(i) c_sincos[i]
+#else
+#define PST_SC(i) h_sincos[i]
+#endif
+
+// sin and cos of x.  |x| < 2^30: k = rint(x 2/pi) by the magic-number add (no F2I/I2F), three-term Cody-Waite
+// reduction with FMA (pi/2 split into three doubles), two degree-6 polynomials in r^2, quadrant fix-up with integer
+// selects.  Larger |x| (and inf/nan) take the library's Payne-Hanek path.  Accuracy ~1 ulp.
+PST_HD void sincos_fast(double x, double& s, double& c) {
+  if (!(fabs(x) < 1073741824.0)) {  // also catches nan
+    sincos(x, &s, &c);
+    return;
+  }
+  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+  const double t = fma(x, 6.36619772367581382433e-01, kMagic);
+  const double kd = t - kMagic;
+  int q;
+  {
+    long long u;
+#ifdef __CUDA_ARCH__
+    u = __double_as_longlong(t);
+#else
+    memcpy(&u, &t, 8);
+#endif
+    q = (int)u;  // low word of the magic sum = k mod 2^32
+  }
+  // pi/2 = hi + mid + lo; mid is truncated (trailing zero bits) so that kd*mid stays exact for |kd| < 2^30
+  double r = fma(kd, -1.5707963267948966, x);       // 0x3ff921fb54442d18
+  r = fma(kd, -6.123233995736757e-17, r);           // 0x3c91a62633145c00
+  r = fma(kd, -8.478427660368898e-32, r);           // 0x397b839a252049c0
+  const double z = r * r;
+  double ps = fma(PST_SC(5), z, PST_SC(4));
+  double pc = fma(PST_SC(11), z, PST_SC(10));
+  ps = fma(ps, z, PST_SC(3));
+  pc = fma(pc, z, PST_SC(9));
+  ps = fma(ps, z, PST_SC(2));
+  pc = fma(pc, z, PST_SC(8));
+  ps = fma(ps, z, PST_SC(1));
+  pc = fma(pc, z, PST_SC(7));
+  ps = fma(ps, z, PST_SC(0));
+  pc = fma(pc, z, PST_SC(6));
+  const double sr = fma(r * z, ps, r);
+  const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+  // quadrant: q&1 swaps, q&2 negates sin, (q+1)&2 negates cos
+  const double ss = (q & 1) ? cr : sr;
+  const double cc = (q & 1) ? sr : cr;
+  s = (q & 2) ? -ss : ss;
+  c = ((q + 1) & 2) ? -cc : cc;
+}
+
 struct cplx {
   double re, im;
 };

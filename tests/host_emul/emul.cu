@@ -13,6 +13,10 @@ static void run(int n_wl, int n_theta, int L, const double* wl, const double* co
                 const double* n_im, const double* d, int pol_first, int W, unsigned flags, double* R, double* T,
                 double* A, double* M) {
   const int Li = L - 2;
+  std::vector<char> lossless(L, 1);  // the kernels branch on the MATERIAL's flag: k = 0 at every wavelength
+  for (int j = 0; j < L; ++j)
+    for (int il = 0; il < n_wl; ++il)
+      if (n_im[(size_t)j * n_wl + il] != 0.0) lossless[j] = 0;
   for (int il = 0; il < n_wl; ++il) {
     std::vector<OptRow> rows(L);
     for (int j = 0; j < L; ++j) rows[j] = make_opt_row(wl[il], n_re[(size_t)j * n_wl + il], n_im[(size_t)j * n_wl + il]);
@@ -23,8 +27,8 @@ static void run(int n_wl, int n_theta, int L, const double* wl, const double* co
         init_exit_columns<NPOL, NCOL>(fin, rows[L - 1].nr, rows[L - 1].ni, ct, pol_first);
         int since = 0;
         for (int j = L - 2; j >= 1; --j) {
-          apply_layer<NPOL, NCOL>(fin, rows[j], d[j], ct, ict, pol_first);
-          if (++since == 8) { renormalise<NPOL, NCOL>(fin); since = 0; }
+          apply_layer<NPOL, NCOL>(fin, rows[j], lossless[j], d[j], ct, ict, pol_first);
+          if (++since == 16) { renormalise<NPOL, NCOL>(fin); since = 0; }
         }
         renormalise<NPOL, NCOL>(fin);
       } else {
@@ -34,8 +38,8 @@ static void run(int n_wl, int n_theta, int L, const double* wl, const double* co
           init_identity<NPOL>(segs[w]);
           int since = 0;
           for (int j = j_hi - 1; j >= j_lo; --j) {
-            apply_layer<NPOL, 2>(segs[w], rows[j], d[j], ct, ict, pol_first);
-            if (++since == 8) { renormalise<NPOL, 2>(segs[w]); since = 0; }
+            apply_layer<NPOL, 2>(segs[w], rows[j], lossless[j], d[j], ct, ict, pol_first);
+            if (++since == 16) { renormalise<NPOL, 2>(segs[w]); since = 0; }
           }
           renormalise<NPOL, 2>(segs[w]);
         }

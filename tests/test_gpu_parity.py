@@ -135,6 +135,26 @@ def test_no_smem_staging_variant_is_bit_identical(eng, ref_cases):
     assert np.array_equal(a["R"], b["R"]) and np.array_equal(a["T"], b["T"])
 
 
+def test_layer_cse_is_bit_identical(eng):
+    """The typed path (identical layers share one cached matrix) is pure common-subexpression elimination."""
+    from pistachio_b200 import workloads
+    from pistachio_b200._cabi import FLAG_FORCE_DEEP_KERNEL, FLAG_NO_LAYER_CSE
+
+    w = workloads.c2_dbr_cavity(n_wl=96, n_theta=70, pairs=20)
+    prep = eng.prepare_workload(w)
+    for extra in (0, FLAG_FORCE_DEEP_KERNEL):
+        a = eng.eval_prepared(prep, flags=extra, want_matrix=True).numpy()
+        b = eng.eval_prepared(prep, flags=extra | FLAG_NO_LAYER_CSE, want_matrix=True).numpy()
+        for key in ("R", "T", "A", "M"):
+            assert np.array_equal(a[key], b[key]), (key, extra)
+    w = workloads.c5_box_sweep(n_wl=64, n_theta=33, n_d=5)  # sweep layer is a type of its own
+    prep = eng.prepare_workload(w)
+    a = eng.eval_prepared(prep).numpy()
+    b = eng.eval_prepared(prep, flags=FLAG_NO_LAYER_CSE).numpy()
+    for key in ("R", "T", "A"):
+        assert np.array_equal(a[key], b[key]), key
+
+
 # ------------------------------------------------------------------------------------------------ edge cases
 def test_two_layer_structure_is_a_bare_interface(eng):
     # N = 2: M = D_0^-1 D_f; 1.0 -> 1.5 gives T = 0.96, R = 0.04 at normal incidence (SURVEY.md a-13)
