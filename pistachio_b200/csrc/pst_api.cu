@@ -87,6 +87,8 @@ struct pst_handle_s {
   DevBuf<int> mat_flags;
   int n_types = 0;                 // layer-type analysis of the current layer list (sync_layers)
   int type_layer[kMaxTypes] = {0};
+  DevBuf<int4> ops_dev;            // run-length ops of the typed path
+  std::vector<int4> ops_host;
   DevBuf<unsigned char> l2buf;
   DevBuf<double> sink;
   // host-buffer pipeline (pst_eval_grid_host)
@@ -127,7 +129,7 @@ extern "C" int pst_destroy(pst_handle_t h) {
   if (!h) return PST_OK;
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
-  h->opt.release(); h->trig.release(); h->layers_dev.release(); h->taboff.release(); h->mat_flags.release(); h->l2buf.release();
+  h->opt.release(); h->trig.release(); h->layers_dev.release(); h->taboff.release(); h->mat_flags.release(); h->ops_dev.release(); h->l2buf.release();
   h->sink.release(); h->hp_in.release(); h->hp_out[0].release(); h->hp_out[1].release();
   for (int i = 0; i < 2; ++i) {
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -177,7 +179,7 @@ template <int P, int C>
 ChainKernel chain_variant(bool so, bool sl, bool seg, bool typed) {
 #define PST_V(O, L, S, T) \
   if (so == O && sl == L && seg == S && typed == T) return tmm_chain_kernel<P, C, O, L, S, T>;
-#define PST_V2(O, L) PST_V(O, L, false, false) PST_V(O, L, false, true) PST_V(O, L, true, false) PST_V(O, L, true, true)
+#define PST_V2(O, L) PST_V(O, L, false, false) PST_V(O, L, false, true) PST_V(O, L, true, false)
   PST_V2(true, true) PST_V2(true, false) PST_V2(false, true) PST_V2(false, false)
 #undef PST_V2
 #undef PST_V
@@ -255,6 +257,32 @@ int sync_layers(pst_handle_t h, const pst_grid_args* a, cudaStream_t st) {
   const bool same = cur.size() == h->layers_host.size() &&
                     std::memcmp(cur.data(), h->layers_host.data(), cur.size() * sizeof(LayerEntry)) == 0;
   if (same) return PST_OK;
+  // run-length ops over the type sequence in application order (last interior layer first):
+  // (A, B, k) = "apply A then B, k times"; (A, -1, k) = "apply A k times"
+  std::vector<int4> ops;
+  if (h->n_types > 0) {
+    std::vector<int> seq;
+    for (int j = a->n_layers - 2; j >= 1; --j) seq.push_back(cur[j].type);
+    const size_t n = seq.size();
+    size_t i = 0;
+    while (i < n) {
+      if (i + 1 < n) {
+        const int ta = seq[i], tb = seq[i + 1];
+        int k = 1;
+        while (i + 2 * (size_t)k + 1 < n && seq[i + 2 * k] == ta && seq[i + 2 * k + 1] == tb) ++k;
+        ops.push_back(make_int4(ta, tb, k, 0));
+        i += 2 * (size_t)k;
+      } else {
+        ops.push_back(make_int4(seq[i], -1, 1, 0));
+        i += 1;
+      }
+    }
+  }
+  if (!ops.empty()) {
+    PST_TRY(h->ops_dev.ensure(ops.size()));
+    PST_CUDA(cudaMemcpyAsync(h->ops_dev.p, ops.data(), ops.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+  }
+  h->ops_host.swap(ops);
   PST_TRY(h->layers_dev.ensure(cur.size()));
   PST_CUDA(cudaMemcpyAsync(h->layers_dev.p, cur.data(), cur.size() * sizeof(LayerEntry), cudaMemcpyHostToDevice, st));
   h->layers_host.swap(cur);
@@ -305,7 +333,8 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
   pl->PB = pl->seg ? 32 : 128;
   const int nthr = pl->PB * W;
   // typed path: worth it when layer matrices repeat (fewer distinct types than interior layers per segment)
-  pl->typed = !(a->flags & PST_FLAG_NO_LAYER_CSE) && h->n_types > 0 && Li / W > h->n_types;
+  // typed path (single-segment kernel only): worth it when layer matrices repeat
+  pl->typed = !pl->seg && !(a->flags & PST_FLAG_NO_LAYER_CSE) && h->n_types > 0 && Li >= 2 * h->n_types;
   pl->type_stride = 0;
   if (pl->typed) {
     int units = h->n_types * (kTypeRecBytes / 16);
@@ -353,6 +382,8 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
   prm.n_types = pl.typed ? h->n_types : 0;
   prm.type_stride = pl.type_stride;
   for (int t = 0; t < kMaxTypes; ++t) prm.type_layer[t] = h->type_layer[t];
+  prm.n_ops = pl.typed ? (int)h->ops_host.size() : 0;
+  prm.ops = h->ops_dev.p;
   prm.flags = a->flags;
   prm.points = (long long)n_wl_launch * a->n_theta;
   prm.opt = h->opt.p;

@@ -123,6 +123,59 @@ PST_HD void apply_cplx_layer(ChainState<NPOL, NC>& st, const CplxLayer<NPOL>& m)
   }
 }
 
+// A cached layer matrix in either form (the typed paths).  Real form: a[0] = c, a[1 + 2p] = al[p], a[2 + 2p] = be[p].
+// Complex form: a[0..1] = cphi, a[2 + 4p .. 5 + 4p] = m10[p], m01[p]; sc = power-of-two exponent.
+template <int NPOL>
+struct TypeRegs {
+  double a[10];
+  int sc;
+  PST_HD void set_real(const RealLayer<NPOL>& m) {
+    a[0] = m.c;
+#pragma unroll
+    for (int p = 0; p < NPOL; ++p) { a[1 + 2 * p] = m.al[p]; a[2 + 2 * p] = m.be[p]; }
+    sc = 0;
+  }
+  PST_HD void set_cplx(const CplxLayer<NPOL>& m) {
+    a[0] = m.cphi.re; a[1] = m.cphi.im;
+#pragma unroll
+    for (int p = 0; p < NPOL; ++p) {
+      a[2 + 4 * p] = m.m10[p].re; a[3 + 4 * p] = m.m10[p].im;
+      a[4 + 4 * p] = m.m01[p].re; a[5 + 4 * p] = m.m01[p].im;
+    }
+    sc = m.sc;
+  }
+};
+
+template <int NPOL, int NC>
+PST_HD void apply_type(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& t, bool lossy) {
+  if (!lossy) {
+    RealLayer<NPOL> m;
+    m.c = t.a[0];
+#pragma unroll
+    for (int p = 0; p < NPOL; ++p) { m.al[p] = t.a[1 + 2 * p]; m.be[p] = t.a[2 + 2 * p]; }
+    apply_real_layer<NPOL, NC>(st, m);
+  } else {
+    CplxLayer<NPOL> m;
+    m.cphi = {t.a[0], t.a[1]};
+#pragma unroll
+    for (int p = 0; p < NPOL; ++p) {
+      m.m10[p] = {t.a[2 + 4 * p], t.a[3 + 4 * p]};
+      m.m01[p] = {t.a[4 + 4 * p], t.a[5 + 4 * p]};
+    }
+    m.sc = t.sc;
+    apply_cplx_layer<NPOL, NC>(st, m);
+  }
+}
+
+// k repetitions of "apply A, then B" with both matrices in registers (the typed path's inner loop)
+template <int NPOL, int NC, bool LA, bool LB>
+PST_HD void pair_loop(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, int k) {
+  for (int i = 0; i < k; ++i) {
+    apply_type<NPOL, NC>(st, A, LA);
+    apply_type<NPOL, NC>(st, B, LB);
+  }
+}
+
 // Build + apply in one go (the untyped path).  `lossless` is the MATERIAL's flag (k = 0 at every wavelength), so
 // the branch is uniform over the block.
 template <int NPOL, int NC>

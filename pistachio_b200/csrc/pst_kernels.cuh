@@ -42,6 +42,8 @@ struct GridParams {
   int n_types;       // typed path: number of cached layer types
   int type_stride;   // typed path: bytes of cache per thread (odd multiple of 16: conflict-free LDS.128)
   int type_layer[kMaxTypes];  // representative layer index of each type
+  int n_ops;         // typed path: number of run-length ops
+  const int4* ops;   // typed path: (type A, type B or -1, repeat count, 0), in application order (exit side first)
   unsigned flags;
   long long points;  // wavelengths of this launch * n_theta
   const double* opt;        // [n_wl][n_mat][6]: OptRow order qr nr inr ni qi ini
@@ -126,9 +128,13 @@ __global__ void prep_trig_kernel(const double* __restrict__ theta, const double*
 // thickness-sweep values; each thread owns one point and both polarisations.
 //   STAGE_OPT / STAGE_LAYERS  optical table window and layer list staged in shared memory once per block
 //   SEG    blockDim.y ordered layer segments per point, combined in order through shared memory (deep stacks)
-//   TYPED  layers with identical (material, thickness) share one layer matrix: every distinct matrix is built once
-//          per thread into a shared-memory cache and the chain loop only applies cached matrices (pure common-
-//          subexpression elimination: the applied matrices are bit-identical to the untyped path's)
+//   TYPED  layers with identical (material, thickness) share one layer matrix (pure common-subexpression
+//          elimination: the applied matrices are bit-identical to the untyped path's).  Every distinct matrix is built
+//          once per thread into a shared-memory record; the host compiles the layer sequence into run-length ops
+//          "apply (A, B) k times" (periodic stacks: quarter-wave mirrors), and the op loop keeps A and B in registers,
+//          so the inner loop is 2 x 16 FP64 instructions per (A, B) pair with no per-layer loads or dispatch.
+//          (v2 read the cached matrix from shared memory per layer and was LSU-bound; a per-layer switch over
+//          register-resident types was latency-bound -- profiles/r01_v2, r01_v3.)
 template <int NPOL, int NCOL, bool STAGE_OPT, bool STAGE_LAYERS, bool SEG, bool TYPED>
 __global__ void __launch_bounds__(SEG ? 512 : 256)
 tmm_chain_kernel(const GridParams prm) {
@@ -202,33 +208,33 @@ tmm_chain_kernel(const GridParams prm) {
   };
   const OptRow exit_row = opt_row(lay[L - 1].mat);
 
-  // ---- typed path: build each distinct layer matrix once into this thread's cache
+  // ---- typed path: build each distinct layer matrix once per thread into its shared-memory record
   unsigned char* my_types = s_types + (size_t)tid * prm.type_stride;
   unsigned lossy_mask = 0;
+  auto load_type = [&](int t, TypeRegs<NPOL>& out) {
+    const double2* rec = reinterpret_cast<const double2*>(my_types + t * kTypeRecBytes);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { const double2 v = rec[k]; out.a[2 * k] = v.x; out.a[2 * k + 1] = v.y; }
+    out.sc = (int)__double_as_longlong(rec[5].x);
+  };
   if constexpr (TYPED) {
     for (int t = 0; t < prm.n_types; ++t) {
       const int j = prm.type_layer[t];
       const LayerEntry le = lay[j];
       const double d = (j == prm.sweep_layer) ? d_sweep : le.d;
-      double2* rec = reinterpret_cast<double2*>(my_types + t * kTypeRecBytes);
+      TypeRegs<NPOL> tmp;
       if (__ldg(prm.mat_flags + le.mat) == 0) {
         double qr, nr, inr;
         opt_row_real(le.mat, qr, nr, inr);
-        const RealLayer<NPOL> m = build_real_layer<NPOL>(qr, nr, inr, d, ct, ict, prm.pol_first);
-        rec[0] = make_double2(m.c, 0.0);
-#pragma unroll
-        for (int pp = 0; pp < NPOL; ++pp) rec[1 + pp] = make_double2(m.al[pp], m.be[pp]);
+        tmp.set_real(build_real_layer<NPOL>(qr, nr, inr, d, ct, ict, prm.pol_first));
       } else {
         lossy_mask |= 1u << t;
-        const CplxLayer<NPOL> m = build_cplx_layer<NPOL>(opt_row(le.mat), d, ct, ict, prm.pol_first);
-        rec[0] = make_double2(m.cphi.re, m.cphi.im);
-#pragma unroll
-        for (int pp = 0; pp < NPOL; ++pp) {
-          rec[1 + 2 * pp] = make_double2(m.m10[pp].re, m.m10[pp].im);
-          rec[2 + 2 * pp] = make_double2(m.m01[pp].re, m.m01[pp].im);
-        }
-        rec[5] = make_double2(__longlong_as_double((long long)m.sc), 0.0);
+        tmp.set_cplx(build_cplx_layer<NPOL>(opt_row(le.mat), d, ct, ict, prm.pol_first));
       }
+      double2* rec = reinterpret_cast<double2*>(my_types + t * kTypeRecBytes);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) rec[k] = make_double2(tmp.a[2 * k], tmp.a[2 * k + 1]);
+      rec[5] = make_double2(__longlong_as_double((long long)tmp.sc), 0.0);
     }
   }
 
@@ -242,33 +248,41 @@ tmm_chain_kernel(const GridParams prm) {
   if constexpr (SEG) init_identity<NPOL>(st);
   else init_exit_columns<NPOL, NC>(st, exit_row.nr, exit_row.ni, ct, prm.pol_first);
 
-  int j = j_hi - 1;
-  while (j >= j_lo) {
-    const int j_stop = max(j - kRenormEvery, j_lo - 1);
-    for (; j > j_stop; --j) {
-      if constexpr (TYPED) {
-        const int t = lay[j].type;
-        const double2* rec = reinterpret_cast<const double2*>(my_types + t * kTypeRecBytes);
-        if (!((lossy_mask >> t) & 1u)) {
-          RealLayer<NPOL> m;
-          m.c = rec[0].x;
-#pragma unroll
-          for (int pp = 0; pp < NPOL; ++pp) { const double2 ab = rec[1 + pp]; m.al[pp] = ab.x; m.be[pp] = ab.y; }
-          apply_real_layer<NPOL, NC>(st, m);
-        } else {
-          CplxLayer<NPOL> m;
-          const double2 c0 = rec[0];
-          m.cphi = {c0.x, c0.y};
-#pragma unroll
-          for (int pp = 0; pp < NPOL; ++pp) {
-            const double2 a = rec[1 + 2 * pp], b = rec[2 + 2 * pp];
-            m.m10[pp] = {a.x, a.y};
-            m.m01[pp] = {b.x, b.y};
-          }
-          m.sc = (int)__double_as_longlong(rec[5].x);
-          apply_cplx_layer<NPOL, NC>(st, m);
+  if constexpr (TYPED) {
+    // run-length ops (host: sync_layers): apply (A, B) k times, or A alone when b < 0
+    int since = 0;
+    for (int op = 0; op < prm.n_ops; ++op) {
+      const int4 o = __ldg(prm.ops + op);
+      TypeRegs<NPOL> A, B;
+      load_type(o.x, A);
+      const bool la = (lossy_mask >> o.x) & 1u;
+      if (o.y < 0) {
+        for (int k = 0; k < o.z; ++k) {
+          apply_type<NPOL, NC>(st, A, la);
+          if (++since >= kRenormEvery) { renormalise<NPOL, NC>(st); since = 0; }
         }
-      } else {
+        continue;
+      }
+      load_type(o.y, B);
+      const bool lb = (lossy_mask >> o.y) & 1u;
+      int k = o.z;
+      while (k > 0) {
+        const int n = min(k, (kRenormEvery - since + 1) / 2 > 0 ? (kRenormEvery - since + 1) / 2 : 1);
+        if (!la && !lb) pair_loop<NPOL, NC, false, false>(st, A, B, n);
+        else if (!la) pair_loop<NPOL, NC, false, true>(st, A, B, n);
+        else if (!lb) pair_loop<NPOL, NC, true, false>(st, A, B, n);
+        else pair_loop<NPOL, NC, true, true>(st, A, B, n);
+        k -= n;
+        since += 2 * n;
+        if (since >= kRenormEvery) { renormalise<NPOL, NC>(st); since = 0; }
+      }
+    }
+    renormalise<NPOL, NC>(st);
+  } else {
+    int j = j_hi - 1;
+    while (j >= j_lo) {
+      const int j_stop = max(j - kRenormEvery, j_lo - 1);
+      for (; j > j_stop; --j) {
         const LayerEntry le = lay[j];
         const double d = (j == prm.sweep_layer) ? d_sweep : le.d;
         const int lossy = STAGE_LAYERS ? le.type : __ldg(prm.mat_flags + le.mat);
@@ -280,8 +294,8 @@ tmm_chain_kernel(const GridParams prm) {
           apply_cplx_layer<NPOL, NC>(st, build_cplx_layer<NPOL>(opt_row(le.mat), d, ct, ict, prm.pol_first));
         }
       }
+      renormalise<NPOL, NC>(st);
     }
-    renormalise<NPOL, NC>(st);
   }
 
   ChainState<NPOL, NCOL> fin;

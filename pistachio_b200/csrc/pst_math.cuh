@@ -44,6 +44,14 @@ PST_HD double from_words(int hi, int lo) {
 }
 #endif
 
+#ifdef __CUDA_ARCH__
+PST_HD double xor_sign(double x, int mask) { return __hiloint2double(__double2hiint(x) ^ mask, __double2loint(x)); }
+#else
+PST_HD double xor_sign(double x, int mask) {
+  long long u; memcpy(&u, &x, 8); u ^= (long long)(unsigned)mask << 32; memcpy(&x, &u, 8); return x;
+}
+#endif
+
 constexpr double kC0 = 299792458.0;                        // scipy.constants.c
 constexpr double kTwoPiC = (2.0 * 3.141592653589793) * kC0;  // (2*np.pi)*c, one rounding, folded on the host
 constexpr double kInvC0 = 1.0 / kC0;                       // numpy's reciprocal-scale in complex/real division
@@ -130,9 +138,14 @@ static const double h_sincos[12] = PST_SINCOS_COEFS;
 // sin and cos of x.  |x| < 2^30: k = rint(x 2/pi) by the magic-number add (no F2I/I2F), three-term Cody-Waite
 // reduction with FMA (pi/2 split into three doubles), two degree-6 polynomials in r^2, quadrant fix-up with integer
 // selects.  Larger |x| (and inf/nan) take the library's Payne-Hanek path.  Accuracy ~1 ulp.
+#ifdef __CUDA_ARCH__
+__device__ __noinline__ void sincos_slow(double x, double* s, double* c) { sincos(x, s, c); }  // cold: keep it out of line
+#else
+inline void sincos_slow(double x, double* s, double* c) { sincos(x, s, c); }
+#endif
 PST_HD void sincos_fast(double x, double& s, double& c) {
   if (!(fabs(x) < 1073741824.0)) {  // also catches nan
-    sincos(x, &s, &c);
+    sincos_slow(x, &s, &c);
     return;
   }
   const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
@@ -168,8 +181,9 @@ PST_HD void sincos_fast(double x, double& s, double& c) {
   // quadrant: q&1 swaps, q&2 negates sin, (q+1)&2 negates cos
   const double ss = (q & 1) ? cr : sr;
   const double cc = (q & 1) ? sr : cr;
-  s = (q & 2) ? -ss : ss;
-  c = ((q + 1) & 2) ? -cc : cc;
+  // sign flips as XOR on the high word (one integer op each instead of an FP64 negate + select)
+  s = xor_sign(ss, (q & 2) << 30);
+  c = xor_sign(cc, ((q + 1) & 2) << 30);
 }
 
 struct cplx {
