@@ -48,6 +48,8 @@ extern "C" {
 #define PST_FLAG_NUMERIC_DET (1u << 2)        /* T = Re(det(M) |t|^2) with det from the computed matrix, as
                                                  tm.py:486 does, instead of the closed form a_last/a_first */
 #define PST_FLAG_NO_SMEM_STAGING (1u << 3)    /* read the optical table from global memory (debug/ablation) */
+#define PST_FLAG_NO_SWEEP_REUSE (1u << 5)     /* thickness sweeps: rebuild the whole chain for every thickness instead
+                                                 of reusing the prefix/suffix products (K3) -- ablation */
 #define PST_FLAG_NO_LAYER_CSE (1u << 4)       /* rebuild the matrix of every layer even when layers repeat (ablation;
                                                  results are bit-identical with and without) */
 

@@ -331,6 +331,20 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
   pl->W = W;
   pl->seg = W > 1;
   pl->PB = pl->seg ? 32 : 128;
+  if (pl->seg) {
+    // deep stacks have few points: pick the points-per-block that balances the blocks over the SMs
+    // (148 SMs; e.g. 16 384 points / 32 = 512 blocks would leave SMs with 4 vs 3 blocks, 86 % efficiency)
+    const long long pts = (long long)n_wl_launch * a->n_theta;
+    double best = -1.0;
+    for (int pb : {32, 16, 8}) {
+      const long long nb = ((pts + pb - 1) / pb) * a->n_sweep;
+      const double eff = (double)nb / ((double)h->sm_count * (double)((nb + h->sm_count - 1) / h->sm_count));
+      if (eff > best + 0.03) {
+        best = eff;
+        pl->PB = pb;
+      }
+    }
+  }
   const int nthr = pl->PB * W;
   // typed path: worth it when layer matrices repeat (fewer distinct types than interior layers per segment)
   // typed path (single-segment kernel only): worth it when layer matrices repeat
@@ -408,6 +422,67 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
   return PST_OK;
 }
 
+using SweepKernel = void (*)(const GridParams, int, int);
+SweepKernel pick_sweep(int npol, bool so, bool sl) {
+#define PST_S(P, O, L) if (npol == P && so == O && sl == L) return tmm_sweep_kernel<P, O, L>;
+  PST_S(1, true, true) PST_S(1, true, false) PST_S(1, false, true) PST_S(1, false, false)
+  PST_S(2, true, true) PST_S(2, true, false) PST_S(2, false, true) PST_S(2, false, false)
+#undef PST_S
+  return nullptr;
+}
+
+bool use_sweep_kernel(const pst_grid_args* a) {
+  return a->sweep_layer >= 0 && !a->M && a->n_sweep >= 4 && !(a->flags & PST_FLAG_NO_SWEEP_REUSE) &&
+         !(a->flags & PST_FLAG_FORCE_DEEP_KERNEL);
+}
+
+// K3 launch for wavelengths [il0, il0 + n_wl_launch): outputs address the window's first element.
+int launch_sweep(pst_handle_t h, const pst_grid_args* a, int il0, int n_wl_launch, const double* sweep_d_dev, double* R,
+                 double* T, double* A, cudaStream_t st) {
+  const int npol = __builtin_popcount(a->pol_mask);
+  const int PB = 128;
+  GridParams prm;
+  std::memset(&prm, 0, sizeof(prm));
+  prm.n_wl = a->n_wl;
+  prm.n_theta = a->n_theta;
+  prm.n_mat = a->n_mat;
+  prm.n_layers = a->n_layers;
+  prm.sweep_layer = a->sweep_layer;
+  prm.pol_first = (a->pol_mask & PST_POL_S) ? 0 : 1;
+  prm.tl_rows = std::min(n_wl_launch, (PB - 1) / a->n_theta + 2);
+  prm.opt_row_bytes = a->n_mat * 48 + ((a->n_mat % 2 == 0) ? 16 : 0);
+  prm.il0 = il0;
+  prm.flags = a->flags;
+  prm.points = (long long)n_wl_launch * a->n_theta;
+  prm.opt = h->opt.p;
+  prm.mat_flags = h->mat_flags.p;
+  prm.trig = h->trig.p;
+  prm.layers = h->layers_dev.p;
+  prm.sweep_d = sweep_d_dev;
+  prm.R = R; prm.T = T; prm.A = A;
+  const size_t budget = std::min<size_t>(h->smem_optin, 200 * 1024);
+  const size_t lay_bytes = (size_t)a->n_layers * sizeof(LayerEntry);
+  const size_t opt_bytes = (size_t)prm.tl_rows * prm.opt_row_bytes;
+  const bool sl = lay_bytes <= 32 * 1024;
+  const bool so = !(a->flags & PST_FLAG_NO_SMEM_STAGING) && opt_bytes + (sl ? lay_bytes : 0) <= 64 * 1024;
+  const size_t smem = (so ? opt_bytes : 0) + (sl ? lay_bytes : 0);
+  SweepKernel fn = pick_sweep(npol, so, sl);
+  if (!fn) return fail(PST_E_INVALID, "pst_eval_grid: no sweep kernel variant");
+  if (smem > 48 * 1024) PST_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+  const long long nblk = (prm.points + PB - 1) / PB;
+  if (nblk > 0x7fffffffLL) return fail(PST_E_INVALID, "pst_eval_grid: too many blocks");
+  // sweeps per block: amortise the prefix/suffix work, but keep at least ~8 blocks per SM in flight
+  int spb = 64;
+  while (spb > 8 && nblk * ((a->n_sweep + spb - 1) / spb) < (long long)h->sm_count * 8) spb /= 2;
+  const long long gy = (a->n_sweep + spb - 1) / spb;
+  if (gy > 65535) spb = (int)((a->n_sweep + 65534) / 65535);
+  dim3 grid((unsigned)nblk, (unsigned)((a->n_sweep + spb - 1) / spb));
+  fn<<<grid, PB, smem, st>>>(prm, a->n_sweep, spb);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PST_OK;
+}
+
 }  // namespace
 
 extern "C" int pst_eval_grid(pst_handle_t h, const pst_grid_args* a, void* stream) {
@@ -418,6 +493,7 @@ extern "C" int pst_eval_grid(pst_handle_t h, const pst_grid_args* a, void* strea
   cudaStream_t st = (cudaStream_t)stream;
   PST_TRY(sync_layers(h, a, st));
   PST_TRY(run_prep(h, a, a->wl, a->theta, a->cos_theta, a->mat_n, a->mat_k, st));
+  if (use_sweep_kernel(a)) return launch_sweep(h, a, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, st);
   ChainPlan pl;
   PST_TRY(plan_chain(h, a, a->n_wl, &pl));
   return launch_chain(h, a, pl, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, a->M, st);
@@ -481,8 +557,12 @@ extern "C" int pst_eval_grid_host(pst_handle_t h, const pst_grid_args* a) {
     ChainPlan pl;
     pst_grid_args loc = *a;
     loc.R = dR; loc.T = dT; loc.A = dA; loc.M = dM;
-    PST_TRY(plan_chain(h, &loc, (int)cw, &pl));
-    PST_TRY(launch_chain(h, &loc, pl, (int)l0, (int)cw, a->sweep_d ? d_sw : nullptr, dR, dT, dA, dM, sc));
+    if (use_sweep_kernel(&loc)) {
+      PST_TRY(launch_sweep(h, &loc, (int)l0, (int)cw, d_sw, dR, dT, dA, sc));
+    } else {
+      PST_TRY(plan_chain(h, &loc, (int)cw, &pl));
+      PST_TRY(launch_chain(h, &loc, pl, (int)l0, (int)cw, a->sweep_d ? d_sw : nullptr, dR, dT, dA, dM, sc));
+    }
     PST_CUDA(cudaEventRecord(h->ev_done[b], sc));
     PST_CUDA(cudaStreamWaitEvent(sd, h->ev_done[b], 0));
     auto copy_back = [&](double* host, const double* dev, size_t width) -> int {

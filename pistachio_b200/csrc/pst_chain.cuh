@@ -253,6 +253,14 @@ PST_HD void apply_segment(ChainState<NPOL, NC>& st, int p, const double (&s)[8],
   st.kexp[p] += s_exp;
 }
 
+// x * 2^e for any int e: two exact power-of-two factors (flushes to 0 / overflows to inf like ldexp, without the
+// library routine's denormal handling -- results below 1e-308 are not part of the path's contract)
+PST_HD double scale2(double x, int e) {
+  e = e > 2000 ? 2000 : (e < -2000 ? -2000 : e);
+  const int h = e / 2;
+  return x * pow2i(h) * pow2i(e - h);
+}
+
 struct PointOut {
   double R, T, A;
   double M[8];  // row-major 2x2 complex, only filled when NCOL == 2
@@ -282,7 +290,7 @@ PST_HD PointOut finish_point(const ChainState<NPOL, NCOL>& fin, int p, double in
   out.R = num * iden;
   // det M = a_last / a_first = n_f / n_0 for both polarisations (the cos factors cancel)
   const double det_re = fma(nfr, in0r, -(nfi * in0i));
-  out.T = ldexp(det_re * iden, -2 * fin.kexp[p]);
+  out.T = scale2(det_re * iden, -2 * fin.kexp[p]);
   if constexpr (NCOL == 2) {
     if (flags & 4u) {
       // numeric determinant like np.linalg.det (tm.py:486); the 2^kexp factors cancel
@@ -290,10 +298,10 @@ PST_HD PointOut finish_point(const ChainState<NPOL, NCOL>& fin, int p, double in
       out.T = det.re * iden;
     }
     const int e = fin.kexp[p];
-    out.M[0] = ldexp(m[0][0].re, e); out.M[1] = ldexp(m[0][0].im, e);
-    out.M[2] = ldexp(m[1][0].re, e); out.M[3] = ldexp(m[1][0].im, e);
-    out.M[4] = ldexp(m[0][1].re, e); out.M[5] = ldexp(m[0][1].im, e);
-    out.M[6] = ldexp(m[1][1].re, e); out.M[7] = ldexp(m[1][1].im, e);
+    out.M[0] = scale2(m[0][0].re, e); out.M[1] = scale2(m[0][0].im, e);
+    out.M[2] = scale2(m[1][0].re, e); out.M[3] = scale2(m[1][0].im, e);
+    out.M[4] = scale2(m[0][1].re, e); out.M[5] = scale2(m[0][1].im, e);
+    out.M[6] = scale2(m[1][1].re, e); out.M[7] = scale2(m[1][1].im, e);
   }
   out.A = (1.0 - out.R) - out.T;
   return out;

@@ -351,6 +351,138 @@ tmm_chain_kernel(const GridParams prm) {
   }
 }
 
+// ------------------------------------------------------------------------------------ K3: thickness sweep
+// One thread per (wavelength, theta) point loops over a chunk of sweep thicknesses.  Everything that does not depend
+// on the swept layer is computed once per thread:
+//   suffix  u0 = (M_{s+1} ... M_{N-2}) D_f[:, 0]                         (state entering the swept layer)
+//   prefix  rows of D_0^-1 (M_1 ... M_{s-1}):  r0, r1  with  M00 = r0 . u, M10 = r1 . u
+// and each thickness costs one layer-matrix build (shared by both polarisations), one layer step and two 2-vector
+// dot products per polarisation.  Results of one chunk iteration are 32 consecutive doubles per warp and array.
+template <int NPOL, bool STAGE_OPT, bool STAGE_LAYERS>
+__global__ void __launch_bounds__(128)
+tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int PB = blockDim.x;
+  const int tid = threadIdx.x;
+  const long long p0 = (long long)blockIdx.x * PB;
+  const long long p_last = min(p0 + PB, prm.points) - 1;
+  const int l_lo = prm.il0 + (int)(p0 / prm.n_theta);
+  const int TL = prm.il0 + (int)(p_last / prm.n_theta) - l_lo + 1;
+  const int L = prm.n_layers;
+  unsigned char* s_opt = smem_raw;
+  const size_t off = STAGE_OPT ? (size_t)prm.tl_rows * prm.opt_row_bytes : 0;
+  LayerEntry* s_layers = reinterpret_cast<LayerEntry*>(smem_raw + off);
+  if constexpr (STAGE_OPT) {
+    const int per_row = prm.n_mat * 3;
+    const int4* src = reinterpret_cast<const int4*>(prm.opt + (size_t)l_lo * prm.n_mat * 6);
+    for (int idx = tid; idx < per_row * TL; idx += PB) {
+      const int r = idx / per_row, c = idx - r * per_row;
+      *reinterpret_cast<int4*>(s_opt + (size_t)r * prm.opt_row_bytes + c * 16) = __ldg(src + idx);
+    }
+  }
+  if constexpr (STAGE_LAYERS) {
+    const int4* src = reinterpret_cast<const int4*>(prm.layers);
+    int4* dst = reinterpret_cast<int4*>(s_layers);
+    for (int idx = tid; idx < L; idx += PB) {
+      int4 e = __ldg(src + idx);
+      e.w = __ldg(prm.mat_flags + e.z);
+      dst[idx] = e;
+    }
+  }
+  if constexpr (STAGE_OPT || STAGE_LAYERS) __syncthreads();
+  if (p0 + tid >= prm.points) return;
+  const long long p = p0 + tid;
+  const int il_loc = (int)(p / prm.n_theta);
+  const int it = (int)(p - (long long)il_loc * prm.n_theta);
+  const int il = prm.il0 + il_loc;
+  const double2 tr = __ldg(prm.trig + it);
+  const double ct = tr.x, ict = tr.y;
+  const unsigned char* optp = STAGE_OPT ? (s_opt + (size_t)(il - l_lo) * prm.opt_row_bytes)
+                                        : reinterpret_cast<const unsigned char*>(prm.opt + (size_t)il * prm.n_mat * 6);
+  const LayerEntry* lay = STAGE_LAYERS ? s_layers : prm.layers;
+  auto opt_row = [&](int mat) {
+    const double2* o = reinterpret_cast<const double2*>(optp + (size_t)mat * 48);
+    const double2 a = o[0], b = o[1], c = o[2];
+    OptRow r;
+    r.qr = a.x; r.nr = a.y; r.inr = b.x; r.ni = b.y; r.qi = c.x; r.ini = c.y;
+    return r;
+  };
+  auto lossy_of = [&](const LayerEntry& le) { return STAGE_LAYERS ? le.type : __ldg(prm.mat_flags + le.mat); };
+  const int js = prm.sweep_layer;
+  const OptRow exit_row = opt_row(lay[L - 1].mat);
+  const OptRow in_row = opt_row(lay[0].mat);
+
+  // ---- suffix: exit column through the layers behind the swept one
+  ChainState<NPOL, 1> suf;
+  init_exit_columns<NPOL, 1>(suf, exit_row.nr, exit_row.ni, ct, prm.pol_first);
+  {
+    int since = 0;
+    for (int j = L - 2; j > js; --j) {
+      const LayerEntry le = lay[j];
+      apply_layer<NPOL, 1>(suf, opt_row(le.mat), lossy_of(le) == 0, le.d, ct, ict, prm.pol_first);
+      if (++since == kRenormEvery) { renormalise<NPOL, 1>(suf); since = 0; }
+    }
+    renormalise<NPOL, 1>(suf);
+  }
+  // ---- prefix: both columns of M_1 ... M_{s-1}, then the rows of D_0^-1 times it
+  ChainState<NPOL, 2> pre;
+  init_identity<NPOL>(pre);
+  {
+    int since = 0;
+    for (int j = js - 1; j >= 1; --j) {
+      const LayerEntry le = lay[j];
+      apply_layer<NPOL, 2>(pre, opt_row(le.mat), lossy_of(le) == 0, le.d, ct, ict, prm.pol_first);
+      if (++since == kRenormEvery) { renormalise<NPOL, 2>(pre); since = 0; }
+    }
+    renormalise<NPOL, 2>(pre);
+  }
+  cplx r0[NPOL][2], r1[NPOL][2];
+#pragma unroll
+  for (int pp = 0; pp < NPOL; ++pp) {
+    const bool is_s = pol_is_s<NPOL>(pp, prm.pol_first);
+    const double w0 = is_s ? 1.0 : ict;
+    const cplx w1 = is_s ? cplx{in_row.inr * ict, in_row.ini * ict} : cplx{in_row.inr, in_row.ini};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const double* v = pre.v[pp][c];
+      const cplx a = {0.5 * w0 * v[0], 0.5 * w0 * v[1]};
+      const cplx b = cscale(cmul(w1, {v[2], v[3]}), 0.5);
+      r0[pp][c] = cadd(a, b);
+      r1[pp][c] = csub(a, b);
+    }
+  }
+  const double det_re = fma(exit_row.nr, in_row.inr, -(exit_row.ni * in_row.ini));
+  const LayerEntry ls = lay[js];
+  const OptRow srow = opt_row(ls.mat);
+  const bool s_lossless = lossy_of(ls) == 0;
+
+  // ---- the sweep loop
+  const int s_begin = blockIdx.y * sweeps_per_block;
+  const int s_end = min(s_begin + sweeps_per_block, n_sweep);
+  const size_t plane = (size_t)prm.points;
+  for (int sw = s_begin; sw < s_end; ++sw) {
+    const double d = __ldg(prm.sweep_d + sw);
+    ChainState<NPOL, 1> u = suf;
+    if (s_lossless) apply_real_layer<NPOL, 1>(u, build_real_layer<NPOL>(srow.qr, srow.nr, srow.inr, d, ct, ict, prm.pol_first));
+    else apply_cplx_layer<NPOL, 1>(u, build_cplx_layer<NPOL>(srow, d, ct, ict, prm.pol_first));
+#pragma unroll
+    for (int pp = 0; pp < NPOL; ++pp) {
+      const cplx u0 = {u.v[pp][0][0], u.v[pp][0][1]}, u1 = {u.v[pp][0][2], u.v[pp][0][3]};
+      const cplx m00 = cadd(cmul(r0[pp][0], u0), cmul(r0[pp][1], u1));
+      const cplx m10 = cadd(cmul(r1[pp][0], u0), cmul(r1[pp][1], u1));
+      const double den = fma(m00.re, m00.re, m00.im * m00.im);
+      const double num = fma(m10.re, m10.re, m10.im * m10.im);
+      const double iden = 1.0 / den;
+      const double R = num * iden;
+      const double T = scale2(det_re * iden, -2 * (u.kexp[pp] + pre.kexp[pp]));
+      const size_t o = ((size_t)sw * NPOL + pp) * plane + (size_t)p;
+      if (prm.R) __stcs(prm.R + o, R);
+      if (prm.T) __stcs(prm.T + o, T);
+      if (prm.A) __stcs(prm.A + o, (1.0 - R) - T);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------- per-layer matrices (API parity)
 // out[i] = [D, P, D^-1, M] (each 2x2 complex128, row major) for wavelength i.  Closed forms of what the
 // reference obtains with np.linalg.inv and multi_dot (tm.py:272-275).

@@ -180,16 +180,44 @@ def test_ragged_grid_shapes(eng, n_wl, n_theta):
 
 
 def test_thickness_sweep_axis(eng, ref_cases):
-    cases = [ref_cases[f"c3_sub_d{k}"] for k in (0, 33333, 66666, 99999)]
+    """K3 (prefix/suffix reuse across the swept thickness) against the reference fixtures, and the plain per-thickness
+    chain (PST_FLAG_NO_SWEEP_REUSE) bit-for-bit against separate single-thickness launches."""
+    from pistachio_b200._cabi import FLAG_NO_SWEEP_REUSE
+
+    ks = (0, 33333, 66666, 99999)
+    cases = [ref_cases[f"c3_sub_d{k}"] for k in ks]
     c = cases[0]
     n = np.asarray(c["n"])
     sweep_d = np.array([cc["d"][2] for cc in cases])
-    res = eng.eval_grid(c["wl"], c["theta"], n.real, n.imag, list(range(n.shape[0])), list(c["d"]), POLS, sweep_layer=2,
-                        sweep_d=sweep_d, cos_theta=np.cos(c["theta"])).numpy()
+    args = (c["wl"], c["theta"], n.real, n.imag, list(range(n.shape[0])), list(c["d"]), POLS)
+    kw = dict(sweep_layer=2, sweep_d=sweep_d, cos_theta=np.cos(c["theta"]))
+    res = eng.eval_grid(*args, **kw).numpy()
+    plain = eng.eval_grid(*args, flags=FLAG_NO_SWEEP_REUSE, **kw).numpy()
     assert res["R"].shape == (4, 2, len(c["wl"]), len(c["theta"]))
     for i, cc in enumerate(cases):
         single = run_case(eng, cc)
-        assert np.array_equal(res["R"][i], single["R"][0]) and np.array_equal(res["T"][i], single["T"][0])
+        assert np.array_equal(plain["R"][i], single["R"][0]) and np.array_equal(plain["T"][i], single["T"][0])
+        rep = parity.compare_grid(f"k3_d{ks[i]}", res["T"][i], res["R"][i], cc["wl"], list(cc["n"]), list(cc["d"]), cc["theta"],
+                                  cc["T"], cc["R"], got_A=res["A"][i])
+        rep.check(max_loose_fraction=0.05)
+    # sweep layer first / last interior layer, single polarisation, ragged sizes
+    rng = np.random.default_rng(5)
+    L, n_wl, n_th = 6, 37, 5
+    wl = np.sort(rng.uniform(0.5, 2.0, n_wl))
+    th = np.sort(rng.uniform(0.0, 1.3, n_th))
+    nn = rng.uniform(1, 3, (L, 1)) * np.ones((1, n_wl)) + 1j * np.array([0, 0.1, 0, 0.02, 0, 0])[:, None]
+    d = rng.uniform(0.05, 1.0, L)
+    sd = np.linspace(0.1, 2.0, 9)
+    for js in (1, L - 2):
+        for pols in (("p-wave",), POLS):
+            out = eng.eval_grid(wl, th, nn.real, nn.imag, list(range(L)), list(d), pols, sweep_layer=js, sweep_d=sd,
+                                cos_theta=np.cos(th)).numpy()
+            for i, dv in enumerate(sd):
+                dd = d.copy()
+                dd[js] = dv
+                T, R = orc.spectrum_closed_form(orc.Stack(wl, list(nn), list(dd)), th, pols)
+                np.testing.assert_allclose(out["T"][i], T, rtol=0, atol=1e-12)
+                np.testing.assert_allclose(out["R"][i], R, rtol=0, atol=1e-12)
 
 
 def test_thick_absorber_and_deep_bragg_stay_finite(eng):
