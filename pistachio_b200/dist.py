@@ -70,16 +70,26 @@ def allgather_result(local: torch.Tensor, axis: str, sizes, group=None) -> torch
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return local
+    if axis == "sweep" and len(set(sizes)) == 1:
+        # slabs along dim 0 concatenate directly: one collective, no staging copies
+        full = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(full, local.contiguous(), group=group)
+        return full
+    if axis == "wl" and len(set(sizes)) == 1:
+        # every (sweep, pol) plane [wl][theta] is contiguous in both the slab and the assembled tensor
+        n_sw, n_pol, n_wl, n_th = local.shape
+        full = torch.empty((n_sw, n_pol, world * n_wl, n_th), dtype=local.dtype, device=local.device)
+        local = local.contiguous()
+        for i in range(n_sw):
+            for j in range(n_pol):
+                dist.all_gather_into_tensor(full[i, j], local[i, j], group=group)
+        return full
     dim = 0 if axis == "sweep" else 2
-    moved = local.movedim(dim, 0).contiguous()  # shard axis first so that the gather is a plain concatenation
-    if len(set(sizes)) == 1:
-        full = torch.empty((world * moved.shape[0],) + tuple(moved.shape[1:]), dtype=moved.dtype, device=moved.device)
-        dist.all_gather_into_tensor(full, moved, group=group)
-    else:
-        cap = max(sizes)
-        pad = torch.zeros((cap,) + tuple(moved.shape[1:]), dtype=moved.dtype, device=moved.device)
-        pad[: moved.shape[0]] = moved
-        bufs = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(bufs, pad, group=group)
-        full = torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+    moved = local.movedim(dim, 0).contiguous()  # ragged slabs: pad to the largest, gather, trim
+    cap = max(sizes)
+    pad = torch.zeros((cap,) + tuple(moved.shape[1:]), dtype=moved.dtype, device=moved.device)
+    pad[: moved.shape[0]] = moved
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    full = torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
     return full.movedim(0, dim).contiguous()
