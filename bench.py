@@ -54,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -363,6 +363,15 @@ def run_ours(args):
                     "note": "algorithmic flops of the formulas the kernel evaluates (FMA = 2), transcendentals, rescaling and "
                             "address arithmetic not counted; see DESIGN.md section 4 and the ncu FP64-pipe utilisation in profiles/"}
     roof["hbm_store"] = {"achieved_gbs": hbm_gbs, "peak_gbs": peaks.get("hbm_gbs"), "frac": hbm_frac}
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
+        with open(os.path.join(ROOT, "profiles", "r01_v4_traffic.json")) as fh:
+            tr = json.load(fh)
+        if tr.get("workload") == args.workload and not args.no_layer_cse:
+            roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roof["traffic_source"] = tr["source"]
+            roof["algorithmic_bytes"] = 24 * points_rank
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -386,7 +395,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
