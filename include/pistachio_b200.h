@@ -156,6 +156,10 @@ int pst_chain_matrices(pst_handle_t h, const double* first_inv /*[dev]*/, const 
 int pst_fresnel(pst_handle_t h, const double* n1 /*[dev] complex n*/, const double* n2, const double* k1x,
                 const double* k2x, int64_t n, double* out_rt /*[dev]*/, double* out_D /*[dev] or NULL*/, void* stream);
 
+/* Replaces transmission_matrix (tm.py:746-751): out complex128 [n][2][2] = (1/t[i]) [[1, r[i]], [r[i], 1]]. */
+int pst_interface_matrices(pst_handle_t h, const double* r /*[dev] complex n*/, const double* t /*[dev] complex n*/,
+                           int64_t n, double* out /*[dev]*/, void* stream);
+
 /* ---- measurement helpers ------------------------------------------------------------------------------ */
 /* Independent-DFMA micro-benchmark: the measured FP64 (non-tensor) peak used as the roofline denominator.
  * Runs `iters` dependent FMAs on 8 independent chains per thread over a full-chip grid, returns TFLOP/s. */

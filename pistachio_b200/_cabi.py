@@ -73,6 +73,7 @@ SYMBOLS = {
                                       C.c_void_p]),
     "pst_fresnel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                C.c_void_p, C.c_void_p]),
+    "pst_interface_matrices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pst_fp64_peak_probe": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_void_p]),
     "pst_flush_l2": (C.c_int, [C.c_void_p, C.c_void_p]),
 }

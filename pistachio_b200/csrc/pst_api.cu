@@ -656,6 +656,17 @@ extern "C" int pst_fresnel(pst_handle_t h, const double* n1, const double* n2, c
   return PST_OK;
 }
 
+extern "C" int pst_interface_matrices(pst_handle_t h, const double* r, const double* t, int64_t n, double* out,
+                                      void* stream) {
+  if (!h) return fail(PST_E_INVALID, "pst_interface_matrices: NULL handle");
+  if (!r || !t || !out || n <= 0) return fail(PST_E_INVALID, "pst_interface_matrices: bad argument");
+  DeviceGuard g(h->device);
+  interface_matrix_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(r, t, n, out);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PST_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ measurement
 extern "C" int pst_fp64_peak_probe(pst_handle_t h, int iters, double* tflops_out, void* stream) {
   if (!h || !tflops_out || iters <= 0) return fail(PST_E_INVALID, "pst_fp64_peak_probe: bad argument");

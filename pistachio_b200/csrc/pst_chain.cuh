@@ -47,13 +47,14 @@ struct CplxLayer {
   int sc;
 };
 
+// Layer-matrix construction is split in two so that callers can batch the transcendental part of several layers:
+//   phase  x = (q.re cos) d, y = (q.im cos) d in the reference's rounding order (tm.py:270, 234)
+//   finish entries of M from sin x, cos x (and cosh y, sinh y)
+PST_HD double layer_phase(double q, double ct, double d) { return mul_rn(mul_rn(q, ct), d); }
+
 template <int NPOL>
-PST_HD RealLayer<NPOL> build_real_layer(double qr, double nr, double inr, double d, double ct, double ict,
-                                        int pol_first) {
-  // phase in the reference's rounding order: kx = q cos(theta) (tm.py:270), argument = kx d (tm.py:234)
-  const double x = mul_rn(mul_rn(qr, ct), d);
-  double sx, cx;
-  sincos_fast(x, sx, cx);
+PST_HD RealLayer<NPOL> finish_real_layer(double sx, double cx, double nr, double inr, double ct, double ict,
+                                         int pol_first) {
   const double sn = sx * nr, si = sx * inr;
   RealLayer<NPOL> m;
   m.c = cx;
@@ -67,11 +68,9 @@ PST_HD RealLayer<NPOL> build_real_layer(double qr, double nr, double inr, double
 }
 
 template <int NPOL>
-PST_HD CplxLayer<NPOL> build_cplx_layer(const OptRow& o, double d, double ct, double ict, int pol_first) {
-  const double x = mul_rn(mul_rn(o.qr, ct), d);
-  const double y = mul_rn(mul_rn(o.qi, ct), d);
-  double sx, cx, ch, sh;
-  sincos_fast(x, sx, cx);
+PST_HD CplxLayer<NPOL> finish_cplx_layer(double sx, double cx, double y, const OptRow& o, double ct, double ict,
+                                         int pol_first) {
+  double ch, sh;
   CplxLayer<NPOL> m;
   m.sc = cosh_sinh_scaled(y, ch, sh);
   // cos(x+iy) = cos x cosh y - i sin x sinh y ; sin(x+iy) = sin x cosh y + i cos x sinh y   (both times 2^sc)
@@ -87,6 +86,21 @@ PST_HD CplxLayer<NPOL> build_cplx_layer(const OptRow& o, double d, double ct, do
     m.m01[p] = {gi * si.im, -(gi * si.re)};  // -i sin(phi) / a
   }
   return m;
+}
+
+template <int NPOL>
+PST_HD RealLayer<NPOL> build_real_layer(double qr, double nr, double inr, double d, double ct, double ict,
+                                        int pol_first) {
+  double sx, cx;
+  sincos_fast(layer_phase(qr, ct, d), sx, cx);
+  return finish_real_layer<NPOL>(sx, cx, nr, inr, ct, ict, pol_first);
+}
+
+template <int NPOL>
+PST_HD CplxLayer<NPOL> build_cplx_layer(const OptRow& o, double d, double ct, double ict, int pol_first) {
+  double sx, cx;
+  sincos_fast(layer_phase(o.qr, ct, d), sx, cx);
+  return finish_cplx_layer<NPOL>(sx, cx, layer_phase(o.qi, ct, d), o, ct, ict, pol_first);
 }
 
 // v <- M v for every polarisation/column held by the thread

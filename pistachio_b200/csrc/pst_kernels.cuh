@@ -112,7 +112,15 @@ __global__ void prep_optical_kernel(const double* __restrict__ wl, const double*
   o[0] = make_double2(r.qr, r.nr);
   o[1] = make_double2(r.inr, r.ni);
   o[2] = make_double2(r.qi, r.ini);
-  if (nk != 0.0) atomicOr(mat_flags + m, 1);  // the material absorbs (or amplifies) somewhere on the grid
+  // the material absorbs (or amplifies) somewhere on the grid: one atomic per warp and material at most
+  const unsigned act = __activemask();
+  const int m0 = __shfl_sync(act, m, __ffs(act) - 1);
+  const bool any_here = __any_sync(act, nk != 0.0 && m == m0);
+  if (m == m0) {
+    if (any_here && (threadIdx.x & 31) == __ffs(act) - 1) atomicOr(mat_flags + m, 1);
+  } else if (nk != 0.0) {
+    atomicOr(mat_flags + m, 1);  // warp straddling two materials
+  }
 }
 
 __global__ void prep_trig_kernel(const double* __restrict__ theta, const double* __restrict__ cos_theta, int n_theta,
@@ -598,6 +606,18 @@ __global__ void chain_matrices_kernel(const double* __restrict__ first_inv, cons
   double4* o = reinterpret_cast<double4*>(out + (size_t)i * 8);
   o[0] = make_double4(m.a.re, m.a.im, m.b.re, m.b.im);
   o[1] = make_double4(m.c.re, m.c.im, m.d.re, m.d.im);
+}
+
+// Interface matrices (1/t) [[1, r], [r, 1]] from given coefficients                 (tm.py:746-751)
+__global__ void interface_matrix_kernel(const double* __restrict__ r, const double* __restrict__ t, long long n,
+                                        double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const cplx it = crecip({t[2 * i], t[2 * i + 1]});
+  const cplx ro = cmul({r[2 * i], r[2 * i + 1]}, it);
+  double* m = out + i * 8;
+  m[0] = it.re; m[1] = it.im; m[2] = ro.re; m[3] = ro.im;
+  m[4] = ro.re; m[5] = ro.im; m[6] = it.re; m[7] = it.im;
 }
 
 // Fresnel coefficients / interface matrices                                         (tm.py:730-751)

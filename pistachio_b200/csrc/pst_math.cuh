@@ -143,11 +143,17 @@ __device__ __noinline__ void sincos_slow(double x, double* s, double* c) { sinco
 #else
 inline void sincos_slow(double x, double* s, double* c) { sincos(x, s, c); }
 #endif
+PST_HD bool sincos_in_fast_range(double x) { return fabs(x) < 1073741824.0; }  // false for nan too
+PST_HD void sincos_core(double x, double& s, double& c);
 PST_HD void sincos_fast(double x, double& s, double& c) {
-  if (!(fabs(x) < 1073741824.0)) {  // also catches nan
+  if (!sincos_in_fast_range(x)) {
     sincos_slow(x, &s, &c);
     return;
   }
+  sincos_core(x, s, c);
+}
+// straight-line part (no branches): several independent calls interleave in one basic block
+PST_HD void sincos_core(double x, double& s, double& c) {
   const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
   const double t = fma(x, 6.36619772367581382433e-01, kMagic);
   const double kd = t - kMagic;

@@ -328,6 +328,18 @@ class TMMEngine:
                                    _ptr(D), self._stream()), "pst_fresnel")
         return rt, D, arrs[0].shape
 
+    def interface_matrices(self, r, t):
+        """(1/t) [[1, r], [r, 1]] per element (pst_interface_matrices; reference transfer_matrix.py:746-751)."""
+        r = np.atleast_1d(np.asarray(r, dtype=np.complex128)).ravel()
+        t = np.atleast_1d(np.asarray(t, dtype=np.complex128)).ravel()
+        if r.shape != t.shape:
+            raise ValueError("r and t differ in length")
+        r_d, t_d = torch.from_numpy(r).to(self.device), torch.from_numpy(t).to(self.device)
+        out = torch.empty((r.size, 2, 2), dtype=torch.complex128, device=self.device)
+        check(self.lib.pst_interface_matrices(self.handle.raw, _ptr(r_d), _ptr(t_d), r.size, _ptr(out), self._stream()),
+              "pst_interface_matrices")
+        return out
+
     # ------------------------------------------------------------------ measurement
     def fp64_peak_tflops(self, iters: int = 4096) -> float:
         out = C.c_double(0.0)

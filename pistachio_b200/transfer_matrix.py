@@ -289,7 +289,9 @@ class Structure:
         index arrays are identical."""
         wl = np.asarray(self.wavelengths, dtype=np.float64).ravel()
         seen, cols_n, cols_k, layer_mat = {}, [], [], []
-        for layer in self.layers:
+        # a one-layer structure is its own incidence and exit medium in the reference (layers[0] is layers[-1])
+        layers = self.layers if len(self.layers) != 1 else [self.layers[0], self.layers[0]]
+        for layer in layers:
             n = np.asarray(layer.complex_refractive, dtype=np.complex128).ravel()
             if n.size != wl.size:
                 raise ValueError(f"layer {layer.material!r} has {n.size} refractive-index points for {wl.size} "
@@ -300,13 +302,15 @@ class Structure:
                 cols_n.append(n.real)
                 cols_k.append(n.imag)
             layer_mat.append(seen[key])
-        layer_d = [float(layer.thickness) for layer in self.layers]
+        layer_d = [float(layer.thickness) for layer in layers]
         return wl, np.array(cols_n), np.array(cols_k), layer_mat, layer_d
 
     def calculate_all_transfer_matrices(self, theta, wave_type):
         """Total matrix M = D_0^-1 (M_1 ... M_{N-2}) D_{N-1} for every wavelength (tm.py:536-572).
         Returns an (n_wl, 2, 2) complex128 array (iterates like the reference's list of 2x2 arrays)."""
-        if len(self.layers) < 2:
+        if len(self.wavelengths) == 0:
+            return np.empty((0, 2, 2), dtype=np.complex128)  # the reference's loop body never runs (tm.py:559)
+        if len(self.layers) < 1:
             raise IndexError("list index out of range")
         if self.strict_reference_cache:
             return self._chain_cached()
@@ -388,6 +392,5 @@ def fresnel(n1, n2, k1x, k2x):
 
 
 def transmission_matrix(r_ij, t_ij):
-    """Interface matrix (1/t)[[1, r], [r, 1]] (tm.py:746-751); pure data assembly of two scalars."""
-    r_ij, t_ij = complex(r_ij), complex(t_ij)
-    return np.array([[1, r_ij], [r_ij, 1]], dtype=np.complex128) / t_ij
+    """Interface matrix (1/t)[[1, r], [r, 1]] (tm.py:746-751)."""
+    return _to_numpy(_eng().interface_matrices(r_ij, t_ij)[0])
