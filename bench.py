@@ -383,6 +383,8 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "identical_to_device_path": same,
+                "d2h_gbs_per_gpu": d2h * e2e_steps / float(t_e2e.item()) / 1e9,
+                "bound": "PCIe device->host copy of R, T, A (24 B/point); kernels overlap the copies",
                 "api": "pst_eval_grid_host via TMMEngine.eval_grid_host, pinned host buffers"},
         "gpu_launches": launches,
         "clocks": clocks,

@@ -78,3 +78,11 @@ extern "C" int emul_eval_grid(int n_wl, int n_theta, int L, const double* wl, co
   }
   return 0;
 }
+
+// ---- elementary functions of the layer loop, exposed for accuracy tests against mpmath
+extern "C" void emul_sincos(int n, const double* x, double* s, double* c) {
+  for (int i = 0; i < n; ++i) sincos_fast(x[i], s[i], c[i]);
+}
+extern "C" void emul_cosh_sinh(int n, const double* y, double* ch, double* sh, int* sc) {
+  for (int i = 0; i < n; ++i) sc[i] = cosh_sinh_scaled(y[i], ch[i], sh[i]);
+}
