@@ -82,6 +82,7 @@ struct pst_handle_s {
   DevBuf<double> opt;
   DevBuf<double2> trig;
   DevBuf<LayerEntry> layers_dev;
+  DevBuf<LayerEntry> layers_flagged;    // same list with `type` = the material's lossy flag (untyped kernels)
   std::vector<LayerEntry> layers_host;  // what layers_dev currently holds
   DevBuf<int> taboff;
   DevBuf<int> mat_flags;
@@ -129,7 +130,7 @@ extern "C" int pst_destroy(pst_handle_t h) {
   if (!h) return PST_OK;
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
-  h->opt.release(); h->trig.release(); h->layers_dev.release(); h->taboff.release(); h->mat_flags.release(); h->ops_dev.release(); h->l2buf.release();
+  h->opt.release(); h->trig.release(); h->layers_dev.release(); h->layers_flagged.release(); h->taboff.release(); h->mat_flags.release(); h->ops_dev.release(); h->l2buf.release();
   h->sink.release(); h->hp_in.release(); h->hp_out[0].release(); h->hp_out[1].release();
   for (int i = 0; i < 2; ++i) {
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -302,7 +303,11 @@ int run_prep(pst_handle_t h, const pst_grid_args* a, const double* wl, const dou
   PST_CUDA(cudaGetLastError());
   prep_trig_kernel<<<(a->n_theta + 255) / 256, 256, 0, st>>>(theta, cos_theta, a->n_theta, h->trig.p);
   PST_CUDA(cudaGetLastError());
-  h->launches += 2;
+  PST_TRY(h->layers_flagged.ensure(a->n_layers));
+  flag_layers_kernel<<<(a->n_layers + 255) / 256, 256, 0, st>>>(h->layers_dev.p, h->mat_flags.p, a->n_layers,
+                                                               h->layers_flagged.p);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 3;
   return PST_OK;
 }
 
@@ -403,7 +408,8 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
   prm.opt = h->opt.p;
   prm.mat_flags = h->mat_flags.p;
   prm.trig = h->trig.p;
-  prm.layers = h->layers_dev.p;
+  prm.layers = pl.typed ? h->layers_dev.p : h->layers_flagged.p;  // typed: type ids; untyped: material flags
+  prm.use_bulk = (a->flags & PST_FLAG_NO_BULK_COPY) ? 0 : 1;
   const long long nblk = (prm.points + pl.PB - 1) / pl.PB;
   if (nblk > 0x7fffffffLL) return fail(PST_E_INVALID, "pst_eval_grid: too many blocks");
   const size_t per_sweep = (size_t)pl.npol * (size_t)prm.points;
@@ -457,7 +463,8 @@ int launch_sweep(pst_handle_t h, const pst_grid_args* a, int il0, int n_wl_launc
   prm.opt = h->opt.p;
   prm.mat_flags = h->mat_flags.p;
   prm.trig = h->trig.p;
-  prm.layers = h->layers_dev.p;
+  prm.layers = h->layers_flagged.p;
+  prm.use_bulk = (a->flags & PST_FLAG_NO_BULK_COPY) ? 0 : 1;
   prm.sweep_d = sweep_d_dev;
   prm.R = R; prm.T = T; prm.A = A;
   const size_t budget = std::min<size_t>(h->smem_optin, 200 * 1024);

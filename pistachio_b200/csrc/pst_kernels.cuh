@@ -18,6 +18,7 @@
 //   M   = D_0^-1 (M_1 ... M_{N-2}) D_{N-1},   t = 1/M00, r = M10/M00, R = |r|^2, T = Re(det M |t|^2).
 // Only the columns of M that are asked for are propagated: v <- M_j v from the exit side.
 #pragma once
+#include "pst_bulk.cuh"
 #include "pst_chain.cuh"
 
 namespace pst {
@@ -45,6 +46,7 @@ struct GridParams {
   int n_ops;         // typed path: number of run-length ops
   const int4* ops;   // typed path: (type A, type B or -1, repeat count, 0), in application order (exit side first)
   unsigned flags;
+  int use_bulk;      // stage the tables with the bulk-copy engine (cp.async.bulk + mbarrier)
   long long points;  // wavelengths of this launch * n_theta
   const double* opt;        // [n_wl][n_mat][6]: OptRow order qr nr inr ni qi ini
   const int* mat_flags;     // [n_mat] bit0: k != 0 at some wavelength
@@ -123,6 +125,17 @@ __global__ void prep_optical_kernel(const double* __restrict__ wl, const double*
   }
 }
 
+// Layer list for the untyped paths: `type` replaced by the material's lossy flag, so the layer loop needs no
+// second lookup and the list can be staged by a plain bulk copy.
+__global__ void flag_layers_kernel(const LayerEntry* __restrict__ layers, const int* __restrict__ mat_flags, int n,
+                                   LayerEntry* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  LayerEntry e = layers[j];
+  e.type = mat_flags[e.mat];
+  out[j] = e;
+}
+
 __global__ void prep_trig_kernel(const double* __restrict__ theta, const double* __restrict__ cos_theta, int n_theta,
                                  double2* __restrict__ trig) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,26 +180,14 @@ tmm_chain_kernel(const GridParams prm) {
   off += TYPED ? (size_t)nthr * prm.type_stride : 0;
   double* s_seg = reinterpret_cast<double*>(smem_raw + off);
 
-  if constexpr (STAGE_OPT) {
-    // the block's wavelength window of the [wl][mat][6] table is one contiguous global range; rows are re-pitched
-    // to opt_row_bytes so that lanes on different wavelengths hit different 16-byte bank groups
-    const int per_row = prm.n_mat * 3;  // 16-byte pieces per wavelength row
-    const int4* src = reinterpret_cast<const int4*>(prm.opt + (size_t)l_lo * prm.n_mat * 6);
-    for (int idx = tid; idx < per_row * TL; idx += nthr) {
-      const int r = idx / per_row, c = idx - r * per_row;
-      *reinterpret_cast<int4*>(s_opt + (size_t)r * prm.opt_row_bytes + c * 16) = __ldg(src + idx);
-    }
-  }
-  if constexpr (STAGE_LAYERS) {
-    const int4* src = reinterpret_cast<const int4*>(prm.layers);
-    int4* dst = reinterpret_cast<int4*>(s_layers);
-    for (int idx = tid; idx < L; idx += nthr) {
-      int4 e = __ldg(src + idx);
-      if constexpr (!TYPED) e.w = __ldg(prm.mat_flags + e.z);  // untyped path: `type` carries the material's flag
-      dst[idx] = e;
-    }
-  }
-  if constexpr (STAGE_OPT || STAGE_LAYERS) __syncthreads();
+  // the block's wavelength window of the [wl][mat][6] table is one contiguous global range; rows are re-pitched
+  // to opt_row_bytes so that lanes on different wavelengths hit different 16-byte bank groups (pst_bulk.cuh)
+  if constexpr (STAGE_OPT || STAGE_LAYERS)
+    stage_block(prm.use_bulk != 0, s_opt,
+                reinterpret_cast<const unsigned char*>(prm.opt + (size_t)l_lo * prm.n_mat * 6), STAGE_OPT ? TL : 0,
+                prm.n_mat * 48, prm.opt_row_bytes, reinterpret_cast<unsigned char*>(s_layers),
+                reinterpret_cast<const unsigned char*>(prm.layers), STAGE_LAYERS ? L * (int)sizeof(LayerEntry) : 0, tid,
+                nthr);
 
   const long long p = min(p0 + threadIdx.x, prm.points - 1);
   const bool valid = (p0 + threadIdx.x) < prm.points;
@@ -293,7 +294,7 @@ tmm_chain_kernel(const GridParams prm) {
       for (; j > j_stop; --j) {
         const LayerEntry le = lay[j];
         const double d = (j == prm.sweep_layer) ? d_sweep : le.d;
-        const int lossy = STAGE_LAYERS ? le.type : __ldg(prm.mat_flags + le.mat);
+        const int lossy = le.type;  // untyped launches get the flagged layer list (flag_layers_kernel)
         if (lossy == 0) {
           double qr, nr, inr;
           opt_row_real(le.mat, qr, nr, inr);
@@ -380,24 +381,12 @@ tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
   unsigned char* s_opt = smem_raw;
   const size_t off = STAGE_OPT ? (size_t)prm.tl_rows * prm.opt_row_bytes : 0;
   LayerEntry* s_layers = reinterpret_cast<LayerEntry*>(smem_raw + off);
-  if constexpr (STAGE_OPT) {
-    const int per_row = prm.n_mat * 3;
-    const int4* src = reinterpret_cast<const int4*>(prm.opt + (size_t)l_lo * prm.n_mat * 6);
-    for (int idx = tid; idx < per_row * TL; idx += PB) {
-      const int r = idx / per_row, c = idx - r * per_row;
-      *reinterpret_cast<int4*>(s_opt + (size_t)r * prm.opt_row_bytes + c * 16) = __ldg(src + idx);
-    }
-  }
-  if constexpr (STAGE_LAYERS) {
-    const int4* src = reinterpret_cast<const int4*>(prm.layers);
-    int4* dst = reinterpret_cast<int4*>(s_layers);
-    for (int idx = tid; idx < L; idx += PB) {
-      int4 e = __ldg(src + idx);
-      e.w = __ldg(prm.mat_flags + e.z);
-      dst[idx] = e;
-    }
-  }
-  if constexpr (STAGE_OPT || STAGE_LAYERS) __syncthreads();
+  if constexpr (STAGE_OPT || STAGE_LAYERS)
+    stage_block(prm.use_bulk != 0, s_opt,
+                reinterpret_cast<const unsigned char*>(prm.opt + (size_t)l_lo * prm.n_mat * 6), STAGE_OPT ? TL : 0,
+                prm.n_mat * 48, prm.opt_row_bytes, reinterpret_cast<unsigned char*>(s_layers),
+                reinterpret_cast<const unsigned char*>(prm.layers), STAGE_LAYERS ? L * (int)sizeof(LayerEntry) : 0, tid,
+                PB);
   if (p0 + tid >= prm.points) return;
   const long long p = p0 + tid;
   const int il_loc = (int)(p / prm.n_theta);
@@ -415,7 +404,7 @@ tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
     r.qr = a.x; r.nr = a.y; r.inr = b.x; r.ni = b.y; r.qi = c.x; r.ini = c.y;
     return r;
   };
-  auto lossy_of = [&](const LayerEntry& le) { return STAGE_LAYERS ? le.type : __ldg(prm.mat_flags + le.mat); };
+  auto lossy_of = [&](const LayerEntry& le) { return le.type; };  // flagged layer list (flag_layers_kernel)
   const int js = prm.sweep_layer;
   const OptRow exit_row = opt_row(lay[L - 1].mat);
   const OptRow in_row = opt_row(lay[0].mat);

@@ -135,6 +135,30 @@ def test_no_smem_staging_variant_is_bit_identical(eng, ref_cases):
     assert np.array_equal(a["R"], b["R"]) and np.array_equal(a["T"], b["T"])
 
 
+def test_bulk_copy_staging_is_bit_identical(eng, ref_cases):
+    """Tables staged by cp.async.bulk + mbarrier vs plain 128-bit loads (PST_FLAG_NO_BULK_COPY): same bits, for
+    single-copy windows (odd material count), per-row copies (even count, padded pitch) and multi-wavelength blocks."""
+    from pistachio_b200 import workloads
+    from pistachio_b200._cabi import FLAG_FORCE_DEEP_KERNEL, FLAG_NO_BULK_COPY, FLAG_NO_LAYER_CSE
+
+    w = workloads.c2_dbr_cavity(n_wl=77, n_theta=5, pairs=6)      # 5 materials, several wavelengths per block
+    prep = eng.prepare_workload(w)
+    for extra in (0, FLAG_NO_LAYER_CSE, FLAG_FORCE_DEEP_KERNEL):
+        a = eng.eval_prepared(prep, flags=extra).numpy()
+        b = eng.eval_prepared(prep, flags=extra | FLAG_NO_BULK_COPY).numpy()
+        assert np.array_equal(a["R"], b["R"]) and np.array_equal(a["T"], b["T"]), extra
+    w = workloads.c4_chirped(n_layers=300, n_wl=200)                # 4 materials: padded row pitch
+    prep = eng.prepare_workload(w)
+    a = eng.eval_prepared(prep, pols=("s-wave",)).numpy()
+    b = eng.eval_prepared(prep, pols=("s-wave",), flags=FLAG_NO_BULK_COPY).numpy()
+    assert np.array_equal(a["R"], b["R"]) and np.array_equal(a["T"], b["T"])
+    w = workloads.c5_box_sweep(n_wl=50, n_theta=3, n_d=6)           # K3
+    prep = eng.prepare_workload(w)
+    a = eng.eval_prepared(prep).numpy()
+    b = eng.eval_prepared(prep, flags=FLAG_NO_BULK_COPY).numpy()
+    assert np.array_equal(a["R"], b["R"]) and np.array_equal(a["T"], b["T"])
+
+
 def test_layer_cse_is_bit_identical(eng):
     """The typed path (identical layers share one cached matrix) is pure common-subexpression elimination."""
     from pistachio_b200 import workloads
