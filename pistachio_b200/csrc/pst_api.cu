@@ -218,7 +218,8 @@ int validate_grid(const pst_grid_args* a, const char* who) {
   if ((a->flags & PST_FLAG_NUMERIC_DET) && !a->M) return fail(PST_E_INVALID, w + ": PST_FLAG_NUMERIC_DET needs the matrix output M");
   for (int j = 0; j < a->n_layers; ++j)
     if (a->layer_mat[j] < 0 || a->layer_mat[j] >= a->n_mat) return fail(PST_E_INVALID, w + ": layer_mat entry out of range");
-  if ((long long)a->n_wl * a->n_theta > (1LL << 40)) return fail(PST_E_INVALID, w + ": grid too large");
+  if ((long long)a->n_wl * a->n_theta > 0x7fffffffLL)
+    return fail(PST_E_INVALID, w + ": n_wl * n_theta must stay below 2^31 per call (kernels index points with 32 bits)");
   return PST_OK;
 }
 

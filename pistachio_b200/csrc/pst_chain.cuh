@@ -158,6 +158,19 @@ struct TypeRegs {
     }
     sc = m.sc;
   }
+  // G with max|M v| <= G max|v| (component-wise max norm), used to space the rescaling
+  PST_HD double growth_bound(bool lossy) const {
+    double g = 0.0;
+    if (!lossy) {
+#pragma unroll
+      for (int p = 0; p < NPOL; ++p) g = fmax(g, fmax(fabs(a[1 + 2 * p]), fabs(a[2 + 2 * p])));
+      return 1.0 + g;  // |cos| <= 1
+    }
+#pragma unroll
+    for (int p = 0; p < NPOL; ++p)
+      g = fmax(g, fmax(fabs(a[2 + 4 * p]) + fabs(a[3 + 4 * p]), fabs(a[4 + 4 * p]) + fabs(a[5 + 4 * p])));
+    return fabs(a[0]) + fabs(a[1]) + g;
+  }
 };
 
 template <int NPOL, int NC>

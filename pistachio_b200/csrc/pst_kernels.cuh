@@ -165,10 +165,12 @@ tmm_chain_kernel(const GridParams prm) {
   const int W = blockDim.y;           // ordered layer segments per point (1 unless SEG)
   const int tid = threadIdx.y * PB + threadIdx.x;
   const int nthr = PB * W;
-  const long long p0 = (long long)blockIdx.x * PB;
-  const long long p_last = min(p0 + PB, prm.points) - 1;
-  const int l_lo = prm.il0 + (int)(p0 / prm.n_theta);
-  const int TL = prm.il0 + (int)(p_last / prm.n_theta) - l_lo + 1;
+  // a launch covers at most 2^31 - 1 points (host-enforced): 32-bit index arithmetic, no 64-bit divisions
+  const unsigned npts = (unsigned)prm.points, nth = (unsigned)prm.n_theta;
+  const unsigned p0 = blockIdx.x * (unsigned)PB;
+  const unsigned p_last = min(p0 + (unsigned)PB, npts) - 1u;
+  const int l_lo = prm.il0 + (int)(p0 / nth);
+  const int TL = prm.il0 + (int)(p_last / nth) - l_lo + 1;
   const int L = prm.n_layers;
 
   // ---- shared-memory carve-up: [optical table][layer list][layer-matrix cache][segment products]
@@ -189,10 +191,10 @@ tmm_chain_kernel(const GridParams prm) {
                 reinterpret_cast<const unsigned char*>(prm.layers), STAGE_LAYERS ? L * (int)sizeof(LayerEntry) : 0, tid,
                 nthr);
 
-  const long long p = min(p0 + threadIdx.x, prm.points - 1);
-  const bool valid = (p0 + threadIdx.x) < prm.points;
-  const int il_loc = (int)(p / prm.n_theta);
-  const int it = (int)(p - (long long)il_loc * prm.n_theta);
+  const unsigned p = min(p0 + threadIdx.x, npts - 1u);
+  const bool valid = (p0 + threadIdx.x) < npts;
+  const int il_loc = (int)(p / nth);
+  const int it = (int)(p - (unsigned)il_loc * nth);
   const int il = prm.il0 + il_loc;
   const double2 tr = __ldg(prm.trig + it);
   const double ct = tr.x, ict = tr.y;
@@ -226,6 +228,7 @@ tmm_chain_kernel(const GridParams prm) {
     for (int k = 0; k < 5; ++k) { const double2 v = rec[k]; out.a[2 * k] = v.x; out.a[2 * k + 1] = v.y; }
     out.sc = (int)__double_as_longlong(rec[5].x);
   };
+  double growth = 1.0;  // bound on max|v| growth per layer over this thread's cached matrices
   if constexpr (TYPED) {
     for (int t = 0; t < prm.n_types; ++t) {
       const int j = prm.type_layer[t];
@@ -240,6 +243,7 @@ tmm_chain_kernel(const GridParams prm) {
         lossy_mask |= 1u << t;
         tmp.set_cplx(build_cplx_layer<NPOL>(opt_row(le.mat), d, ct, ict, prm.pol_first));
       }
+      growth = fmax(growth, tmp.growth_bound((lossy_mask >> t) & 1u));
       double2* rec = reinterpret_cast<double2*>(my_types + t * kTypeRecBytes);
 #pragma unroll
       for (int k = 0; k < 5; ++k) rec[k] = make_double2(tmp.a[2 * k], tmp.a[2 * k + 1]);
@@ -250,8 +254,10 @@ tmm_chain_kernel(const GridParams prm) {
   // ---- the ordered chain over this thread's segment of interior layers
   const int Li = L - 2;
   const int seg = SEG ? threadIdx.y : 0;
-  const int j_lo = 1 + (int)(((long long)Li * seg) / W);
-  const int j_hi = 1 + (int)(((long long)Li * (seg + 1)) / W);  // exclusive
+  // balanced segment bounds without 64-bit division: the first Li % W segments get one extra layer
+  const int seg_q = Li / W, seg_r = Li - seg_q * W;
+  const int j_lo = 1 + seg * seg_q + min(seg, seg_r);
+  const int j_hi = j_lo + seg_q + (seg < seg_r ? 1 : 0);  // exclusive
 
   ChainState<NPOL, NC> st;
   if constexpr (SEG) init_identity<NPOL>(st);
@@ -259,6 +265,11 @@ tmm_chain_kernel(const GridParams prm) {
 
   if constexpr (TYPED) {
     // run-length ops (host: sync_layers): apply (A, B) k times, or A alone when b < 0
+    // Rescaling interval from the growth bound: after a rescale max|v| < 2, and n layers multiply it by at most
+    // growth^n, so n <= 900 / log2(growth) layers cannot overflow.  The interval is made warp-uniform (minimum over
+    // the lanes) because it sets loop trip counts.  Ordinary mirrors need no rescale inside the chain at all.
+    const int lg = exponent_of(growth) + 1;  // >= log2(growth)
+    const int every = max(2, min(1024, (int)__reduce_min_sync(0xffffffffu, (unsigned)(900 / max(lg, 1)))) & ~1);
     int since = 0;
     for (int op = 0; op < prm.n_ops; ++op) {
       const int4 o = __ldg(prm.ops + op);
@@ -268,7 +279,7 @@ tmm_chain_kernel(const GridParams prm) {
       if (o.y < 0) {
         for (int k = 0; k < o.z; ++k) {
           apply_type<NPOL, NC>(st, A, la);
-          if (++since >= kRenormEvery) { renormalise<NPOL, NC>(st); since = 0; }
+          if (++since >= every) { renormalise<NPOL, NC>(st); since = 0; }
         }
         continue;
       }
@@ -276,14 +287,14 @@ tmm_chain_kernel(const GridParams prm) {
       const bool lb = (lossy_mask >> o.y) & 1u;
       int k = o.z;
       while (k > 0) {
-        const int n = min(k, (kRenormEvery - since + 1) / 2 > 0 ? (kRenormEvery - since + 1) / 2 : 1);
+        const int n = min(k, max((every - since) / 2, 1));
         if (!la && !lb) pair_loop<NPOL, NC, false, false>(st, A, B, n);
         else if (!la) pair_loop<NPOL, NC, false, true>(st, A, B, n);
         else if (!lb) pair_loop<NPOL, NC, true, false>(st, A, B, n);
         else pair_loop<NPOL, NC, true, true>(st, A, B, n);
         k -= n;
         since += 2 * n;
-        if (since >= kRenormEvery) { renormalise<NPOL, NC>(st); since = 0; }
+        if (since >= every) { renormalise<NPOL, NC>(st); since = 0; }
       }
     }
     renormalise<NPOL, NC>(st);
@@ -373,10 +384,11 @@ tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int PB = blockDim.x;
   const int tid = threadIdx.x;
-  const long long p0 = (long long)blockIdx.x * PB;
-  const long long p_last = min(p0 + PB, prm.points) - 1;
-  const int l_lo = prm.il0 + (int)(p0 / prm.n_theta);
-  const int TL = prm.il0 + (int)(p_last / prm.n_theta) - l_lo + 1;
+  const unsigned npts = (unsigned)prm.points, nth = (unsigned)prm.n_theta;  // < 2^31 points per launch (host-enforced)
+  const unsigned p0 = blockIdx.x * (unsigned)PB;
+  const unsigned p_last = min(p0 + (unsigned)PB, npts) - 1u;
+  const int l_lo = prm.il0 + (int)(p0 / nth);
+  const int TL = prm.il0 + (int)(p_last / nth) - l_lo + 1;
   const int L = prm.n_layers;
   unsigned char* s_opt = smem_raw;
   const size_t off = STAGE_OPT ? (size_t)prm.tl_rows * prm.opt_row_bytes : 0;
@@ -387,10 +399,10 @@ tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
                 prm.n_mat * 48, prm.opt_row_bytes, reinterpret_cast<unsigned char*>(s_layers),
                 reinterpret_cast<const unsigned char*>(prm.layers), STAGE_LAYERS ? L * (int)sizeof(LayerEntry) : 0, tid,
                 PB);
-  if (p0 + tid >= prm.points) return;
-  const long long p = p0 + tid;
-  const int il_loc = (int)(p / prm.n_theta);
-  const int it = (int)(p - (long long)il_loc * prm.n_theta);
+  if (p0 + tid >= npts) return;
+  const unsigned p = p0 + tid;
+  const int il_loc = (int)(p / nth);
+  const int it = (int)(p - (unsigned)il_loc * nth);
   const int il = prm.il0 + il_loc;
   const double2 tr = __ldg(prm.trig + it);
   const double ct = tr.x, ict = tr.y;

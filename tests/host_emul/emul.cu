@@ -34,7 +34,8 @@ static void run(int n_wl, int n_theta, int L, const double* wl, const double* co
       } else {
         std::vector<ChainState<NPOL, 2>> segs(W);
         for (int w = 0; w < W; ++w) {
-          const int j_lo = 1 + (int)(((long long)Li * w) / W), j_hi = 1 + (int)(((long long)Li * (w + 1)) / W);
+          const int seg_q = Li / W, seg_r = Li - seg_q * W;
+          const int j_lo = 1 + w * seg_q + (w < seg_r ? w : seg_r), j_hi = j_lo + seg_q + (w < seg_r ? 1 : 0);
           init_identity<NPOL>(segs[w]);
           int since = 0;
           for (int j = j_hi - 1; j >= j_lo; --j) {
