@@ -161,6 +161,22 @@ int pst_fresnel(pst_handle_t h, const double* n1 /*[dev] complex n*/, const doub
 int pst_interface_matrices(pst_handle_t h, const double* r /*[dev] complex n*/, const double* t /*[dev] complex n*/,
                            int64_t n, double* out /*[dev]*/, void* stream);
 
+/* ---- fused spectral reduction --------------------------------------------------------
+ * Peak search along the middle axis of y[n_outer][n_pts][n_inner] (a grid result: outer = (sweep, pol), pts =
+ * wavelength, inner = theta) with the semantics of scipy.signal.find_peaks(y, height=, distance=) that the reference's
+ * notebook applies to spectra (notebooks/Cavity Length Determiner.ipynb cell 3), so that only peak lists leave the
+ * device instead of whole spectra.  use_height = 0 ignores `height`; distance <= 1 disables the distance condition.
+ * reverse != 0 scans each spectrum from its last sample to its first (ascending wavenumber on an ascending
+ * wavelength grid); indices then count from the end.  Outputs per spectrum s = outer * n_inner + inner:
+ *   out_idx[s][max_peaks] (first out_count[s] entries valid), out_height[s][max_peaks] (may be NULL),
+ *   out_count[s] (-1: more than max_peaks / 128 candidates), out_spacing[s] = mean difference of axis[] between
+ *   consecutive peaks (NaN below two peaks; may be NULL; axis may be NULL) -- the notebook's `diff().mean()` from which
+ *   the cavity length L = 1e4 / (2 n_eff spacing) follows (cells 5-6). */
+int pst_find_peaks(pst_handle_t h, const double* y /*[dev]*/, int n_outer, int n_pts, int n_inner, double height,
+                   int use_height, int distance, int max_peaks, int reverse, const double* axis /*[dev] n_pts or NULL*/,
+                   int* out_idx /*[dev]*/, double* out_height /*[dev] or NULL*/, int* out_count /*[dev]*/,
+                   double* out_spacing /*[dev] or NULL*/, void* stream);
+
 /* ---- measurement helpers ------------------------------------------------------------------------------ */
 /* Independent-DFMA micro-benchmark: the measured FP64 (non-tensor) peak used as the roofline denominator.
  * Runs `iters` dependent FMAs on 8 independent chains per thread over a full-chip grid, returns TFLOP/s. */

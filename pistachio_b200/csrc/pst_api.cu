@@ -675,6 +675,24 @@ extern "C" int pst_interface_matrices(pst_handle_t h, const double* r, const dou
   return PST_OK;
 }
 
+extern "C" int pst_find_peaks(pst_handle_t h, const double* y, int n_outer, int n_pts, int n_inner, double height,
+                              int use_height, int distance, int max_peaks, int reverse, const double* axis, int* out_idx,
+                              double* out_height, int* out_count, double* out_spacing, void* stream) {
+  if (!h) return fail(PST_E_INVALID, "pst_find_peaks: NULL handle");
+  if (!y || !out_idx || !out_count || n_outer <= 0 || n_pts <= 0 || n_inner <= 0)
+    return fail(PST_E_INVALID, "pst_find_peaks: bad argument");
+  if (max_peaks < 1 || max_peaks > kPeakCap) return fail(PST_E_INVALID, "pst_find_peaks: max_peaks must be in 1..128");
+  if (distance < 0) return fail(PST_E_INVALID, "pst_find_peaks: `distance` must be greater or equal to 1");
+  DeviceGuard g(h->device);
+  const long long n_spec = (long long)n_outer * n_inner;
+  find_peaks_kernel<<<(unsigned)((n_spec + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      y, n_outer, n_pts, n_inner, height, use_height, distance, max_peaks, reverse, axis, out_idx, out_height, out_count,
+      out_spacing);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PST_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ measurement
 extern "C" int pst_fp64_peak_probe(pst_handle_t h, int iters, double* tflops_out, void* stream) {
   if (!h || !tflops_out || iters <= 0) return fail(PST_E_INVALID, "pst_fp64_peak_probe: bad argument");

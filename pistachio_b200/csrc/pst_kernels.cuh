@@ -651,6 +651,89 @@ __global__ void fresnel_kernel(const double* __restrict__ n1, const double* __re
   }
 }
 
+// ------------------------------------------------------------------------------ fused spectral reduction
+// Peak search along the wavelength axis of a result array laid out [outer][point][inner] (the grid layout with
+// outer = (sweep, pol), point = wavelength, inner = theta): one thread per spectrum, lanes on adjacent `inner` so every
+// step of the scan is one coalesced load.  Semantics of scipy.signal.find_peaks(y, height=, distance=) as used by the
+// reference's "Cavity Length Determiner" notebook (cell 3); see oracle/peaks_oracle.py for the restated algorithm.
+// When `reverse` is set the spectrum is scanned from the last sample to the first (ascending wavenumber for an
+// ascending wavelength grid) and indices refer to that reversed order.
+constexpr int kPeakCap = 128;
+__global__ void find_peaks_kernel(const double* __restrict__ y, int n_outer, int n_pts, int n_inner, double height,
+                                  int use_height, int distance, int max_peaks, int reverse,
+                                  const double* __restrict__ axis, int* __restrict__ out_idx,
+                                  double* __restrict__ out_height, int* __restrict__ out_count,
+                                  double* __restrict__ out_spacing) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= (long long)n_outer * n_inner) return;
+  const int outer = (int)(s / n_inner), inner = (int)(s - (long long)outer * n_inner);
+  const double* base = y + ((size_t)outer * n_pts) * n_inner + inner;
+  auto at = [&](int i) { return __ldg(base + (size_t)(reverse ? n_pts - 1 - i : i) * n_inner); };
+  int idx[kPeakCap];
+  double hh[kPeakCap];
+  unsigned char keep[kPeakCap];
+  int n = 0;
+  bool overflow = false;
+  // ---- local maxima with plateau midpoints (streaming state machine), height filter
+  if (n_pts >= 3) {
+    const int i_max = n_pts - 1;
+    int i = 1;
+    double xm1 = at(0), xi = at(1);  // x[i-1], x[i]
+    while (i < i_max) {
+      if (xm1 < xi) {
+        int ahead = i + 1;
+        double xa = at(ahead);
+        while (ahead < i_max && xa == xi) { ++ahead; xa = at(ahead); }
+        if (xa < xi) {  // a peak: plateau [i, ahead-1], reported at its midpoint
+          if (!use_height || xi >= height) {
+            if (n < kPeakCap && n < max_peaks) { idx[n] = (i + ahead - 1) / 2; hh[n] = xi; keep[n] = 1; ++n; }
+            else overflow = true;
+          }
+          i = ahead;  // resume behind the plateau (scipy: i = i_ahead, then i += 1)
+          xi = xa;
+        }
+      }
+      xm1 = xi;
+      ++i;
+      if (i <= i_max) xi = at(i);
+    }
+  }
+  // ---- distance condition: from the highest peak down, a kept peak removes neighbours closer than `distance`
+  if (distance > 1 && n > 1) {
+    unsigned char done[kPeakCap];
+    for (int k = 0; k < n; ++k) done[k] = 0;
+    for (int it = 0; it < n; ++it) {
+      int j = -1;
+      double best = 0.0;
+      for (int k = 0; k < n; ++k)
+        if (!done[k] && keep[k] && (j < 0 || hh[k] >= best)) { j = k; best = hh[k]; }
+      if (j < 0) break;
+      done[j] = 1;
+      for (int k = j - 1; k >= 0 && idx[j] - idx[k] < distance; --k) keep[k] = 0;
+      for (int k = j + 1; k < n && idx[k] - idx[j] < distance; ++k) keep[k] = 0;
+    }
+  }
+  int m = 0, first = -1, last = -1;
+  for (int k = 0; k < n; ++k)
+    if (keep[k]) {
+      out_idx[s * max_peaks + m] = idx[k];
+      if (out_height) out_height[s * max_peaks + m] = hh[k];
+      if (first < 0) first = idx[k];
+      last = idx[k];
+      ++m;
+    }
+  out_count[s] = overflow ? -1 : m;
+  if (out_spacing) {
+    double sp = __longlong_as_double(0x7ff8000000000000LL);  // NaN for fewer than two peaks
+    if (axis && m >= 2) {
+      const double a0 = __ldg(axis + (reverse ? n_pts - 1 - first : first));
+      const double a1 = __ldg(axis + (reverse ? n_pts - 1 - last : last));
+      sp = (a1 - a0) / (double)(m - 1);  // mean of consecutive differences telescopes
+    }
+    out_spacing[s] = sp;
+  }
+}
+
 // ------------------------------------------------------------------------------ measurement helpers
 // 8 independent dependent-FMA chains per thread: the non-tensor FP64 peak of the chip.
 __global__ void dfma_probe_kernel(int iters, double seed, double* __restrict__ sink) {

@@ -340,6 +340,35 @@ class TMMEngine:
               "pst_interface_matrices")
         return out
 
+    # ------------------------------------------------------------------ fused spectral reduction
+    def find_peaks(self, y, height=None, distance=None, max_peaks=64, axis=None, reverse=False):
+        """Peaks along the wavelength axis of a device result y[..., n_wl, n_theta] (e.g. GridResult.T), with the
+        semantics of scipy.signal.find_peaks(spectrum, height=, distance=) (pst_find_peaks).  Returns device tensors
+        (idx [..., n_theta, max_peaks] int32, heights, count [..., n_theta] int32, spacing [..., n_theta]); only these
+        small arrays need to leave the device.  `axis` (n_wl values, e.g. wavenumbers) enables the mean peak spacing."""
+        if not (isinstance(y, torch.Tensor) and y.is_cuda and y.dtype == torch.float64 and y.dim() >= 2):
+            raise ValueError("y must be a float64 CUDA tensor [..., n_wl, n_theta]")
+        y = y.contiguous()
+        n_pts, n_inner = y.shape[-2], y.shape[-1]
+        lead = tuple(y.shape[:-2])
+        n_outer = int(np.prod(lead)) if lead else 1
+        if distance is not None and distance < 1:
+            raise ValueError("`distance` must be greater or equal to 1")
+        dist_i = 0 if distance is None else int(np.ceil(distance))
+        ax_d = _dev_f64(axis, self.device) if axis is not None else None
+        if ax_d is not None and ax_d.numel() != n_pts:
+            raise ValueError("axis must have one value per wavelength")
+        shape = lead + (n_inner,)
+        idx = torch.empty(shape + (max_peaks,), dtype=torch.int32, device=self.device)
+        hts = torch.empty(shape + (max_peaks,), dtype=torch.float64, device=self.device)
+        cnt = torch.empty(shape, dtype=torch.int32, device=self.device)
+        spc = torch.empty(shape, dtype=torch.float64, device=self.device)
+        check(self.lib.pst_find_peaks(self.handle.raw, _ptr(y), n_outer, n_pts, n_inner,
+                                      0.0 if height is None else float(height), 0 if height is None else 1, dist_i,
+                                      int(max_peaks), 1 if reverse else 0, _ptr(ax_d), _ptr(idx), _ptr(hts), _ptr(cnt),
+                                      _ptr(spc), self._stream()), "pst_find_peaks")
+        return idx, hts, cnt, spc
+
     # ------------------------------------------------------------------ measurement
     def fp64_peak_tflops(self, iters: int = 4096) -> float:
         out = C.c_double(0.0)

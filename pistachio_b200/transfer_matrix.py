@@ -363,6 +363,34 @@ class Structure:
             res = {k: (v[0] if v is not None else None) for k, v in res.items()}
         return res
 
+    def cavity_length_from_peaks(self, n_eff=1.0, theta=None, pol=S_WAVE, height=None, distance=None, percent=True,
+                                 sweep_layer=-1, sweep_d=None, max_peaks=64):
+        """Additive API: the reference's "Cavity Length Determiner" notebook fused behind the
+        spectrum.  Transmittance spectra are evaluated on the device, searched for peaks on the ascending-wavenumber
+        axis nu = 1e4/lambda[um] with scipy.signal.find_peaks(T, height=, distance=) semantics (notebook cell 3, where
+        T is in percent), and only the peak lists leave the GPU.  Returns a dict with `peak_wavenumber` (list per
+        spectrum), `count`, `mean_spacing` and `L_cav = 1e4 / (2 n_eff mean_spacing)` (cells 5-6), each shaped
+        (n_theta,) or (n_sweep, n_theta)."""
+        theta = np.atleast_1d(np.asarray(self.theta if theta is None else theta, dtype=np.float64))
+        wl, mat_n, mat_k, layer_mat, layer_d = self._stack_on_grid()
+        eng = _eng()
+        res = eng.eval_grid(wl, theta, mat_n, mat_k, layer_mat, layer_d, (pol,), cos_theta=np.cos(theta),
+                            sweep_layer=sweep_layer, sweep_d=sweep_d, want=("T",))
+        nu = 1.0e4 / wl
+        h = None if height is None else (float(height) / 100.0 if percent else float(height))
+        idx, hts, cnt, spc = eng.find_peaks(res.T[:, 0], height=h, distance=distance, max_peaks=max_peaks, axis=nu,
+                                            reverse=bool(wl.size > 1 and wl[0] < wl[-1]))
+        idx, cnt, spc = _to_numpy(idx), _to_numpy(cnt), _to_numpy(spc)
+        if (cnt < 0).any():
+            raise ValueError("more peaks than max_peaks in at least one spectrum")
+        order = nu[::-1] if (wl.size > 1 and wl[0] < wl[-1]) else nu
+        peaks = [[order[idx[s, t, :cnt[s, t]]] for t in range(idx.shape[1])] for s in range(idx.shape[0])]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out = {"peak_wavenumber": peaks, "count": cnt, "mean_spacing": spc, "L_cav": 1.0e4 / (2.0 * n_eff * spc)}
+        if sweep_d is None:
+            out = {k: v[0] for k, v in out.items()}
+        return out
+
     # ---- misc -----------------------------------------------------------------------------------------------
     def print_structure(self):
         """Print one line per layer, format of tm.py:630-647."""
