@@ -343,6 +343,7 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
     const long long pts = (long long)n_wl_launch * a->n_theta;
     double best = -1.0;
     for (int pb : {32, 16, 8}) {
+      if (W % (32 / pb) != 0) continue;  // a warp holds 32/pb whole segments (shuffle level of the combine)
       const long long nb = ((pts + pb - 1) / pb) * a->n_sweep;
       const double eff = (double)nb / ((double)h->sm_count * (double)((nb + h->sm_count - 1) / h->sm_count));
       if (eff > best + 0.03) {

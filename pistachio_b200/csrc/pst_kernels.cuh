@@ -320,21 +320,51 @@ tmm_chain_kernel(const GridParams prm) {
 
   ChainState<NPOL, NCOL> fin;
   if constexpr (SEG) {
-    // ---- ordered combine: S_0 S_1 ... S_{W-1} applied to the exit columns, by the seg-0 row of threads
-    constexpr int REC = 9;  // 8 doubles + exponent per (segment, polarisation); lanes contiguous
-    double* mine = s_seg + ((size_t)(seg * NPOL) * REC) * PB + threadIdx.x;
+    // ---- ordered combine of the segment products S_0 S_1 ... S_{W-1} (associative, not commutative):
+    // level 1, warp shuffles: a warp holds SW = 32 / PB consecutive segments of the same PB points (lane =
+    // segment-in-warp * PB + point); a log2(SW)-step ordered tree multiplies neighbours, P_seg <- P_seg . P_{seg+s}
+    const int SW = 32 / PB;
+    for (int s = 1; s < SW; s <<= 1) {
+      ChainState<NPOL, 2> other;
 #pragma unroll
-    for (int pp = 0; pp < NPOL; ++pp) {
+      for (int pp = 0; pp < NPOL; ++pp) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) mine[((size_t)pp * REC + c * 4 + k) * PB] = st.v[pp][c][k];
-      mine[((size_t)pp * REC + 8) * PB] = (double)st.kexp[pp];
+          for (int k = 0; k < 4; ++k) other.v[pp][c][k] = __shfl_xor_sync(0xffffffffu, st.v[pp][c][k], s * PB);
+        other.kexp[pp] = __shfl_xor_sync(0xffffffffu, st.kexp[pp], s * PB);
+      }
+      if (((seg % SW) & (2 * s - 1)) == 0) {  // this lane holds the left factor: apply it to the partner's columns
+#pragma unroll
+        for (int pp = 0; pp < NPOL; ++pp) {
+          double left[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) left[k] = st.v[pp][k >> 2][k & 3];
+          apply_segment<NPOL, 2>(other, pp, left, st.kexp[pp]);
+        }
+        st = other;
+        renormalise<NPOL, 2>(st);
+      }
+    }
+    // level 2, block: the first lane group of every warp publishes its product in shared memory and the seg-0 row
+    // applies them, last to first, to the exit columns
+    constexpr int REC = 9;  // 8 doubles + exponent per (warp product, polarisation); lanes contiguous
+    const int WR = W / SW;  // products left after the shuffle level
+    if (seg % SW == 0) {
+      double* mine = s_seg + ((size_t)((seg / SW) * NPOL) * REC) * PB + threadIdx.x;
+#pragma unroll
+      for (int pp = 0; pp < NPOL; ++pp) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mine[((size_t)pp * REC + c * 4 + k) * PB] = st.v[pp][c][k];
+        mine[((size_t)pp * REC + 8) * PB] = (double)st.kexp[pp];
+      }
     }
     __syncthreads();
     if (threadIdx.y != 0) return;
     init_exit_columns<NPOL, NCOL>(fin, exit_row.nr, exit_row.ni, ct, prm.pol_first);
-    for (int w = W - 1; w >= 0; --w) {
+    for (int w = WR - 1; w >= 0; --w) {
       const double* rec = s_seg + ((size_t)(w * NPOL) * REC) * PB + threadIdx.x;
 #pragma unroll
       for (int pp = 0; pp < NPOL; ++pp) {
