@@ -121,7 +121,7 @@ def workload_pols(name):
 
 
 # ------------------------------------------------------------------------------------------------ flop model
-def algorithmic_flops(w, prep, n_pol, cse=True):
+def algorithmic_flops(w, prep, n_pol, cse=True, power=True):
     """Algorithmic FP64 flops per spectral point of the path the kernel takes for this workload.
     Counted: the multiply/add/FMA(=2) of the phase, the layer-matrix entries and the 2-vector layer step, and the
     epilogue.  NOT counted: sincos / exp evaluations, rescaling, address arithmetic.
@@ -147,9 +147,28 @@ def algorithmic_flops(w, prep, n_pol, cse=True):
         if w.interior_layers >= 128 and len(w.wl) * len(w.theta) < 148 * 512:
             cols, typed = 2, False  # K2 segments carry both columns
         builds = {(int(mats[j]), float(ds[j])): build(mats[j]) for j in interior} if typed else None
-        per_thread = (sum(builds.values()) if typed else sum(build(mats[j]) for j in interior)) \
-            + cols * sum(step(mats[j]) for j in interior) + epilogue
+        steps = cols * sum(step(mats[j]) for j in interior)
         kind = "K1 typed (layer CSE)" if typed else ("K2 segmented" if cols == 2 else "K1 untyped")
+        if typed and power:
+            # run-length ops as the host builds them; a lossless pair repeated k >= 3 times costs per polarisation:
+            # period matrix 12 + (k - 2) recurrence FMAs * 2 + closed form 6 + one real-structured step 12
+            seq = [(int(mats[j]), float(ds[j])) for j in reversed(interior)]
+            steps, i = 0, 0
+            while i < len(seq):
+                if i + 1 < len(seq):
+                    k = 1
+                    while i + 2 * k + 1 < len(seq) and seq[i + 2 * k] == seq[i] and seq[i + 2 * k + 1] == seq[i + 1]:
+                        k += 1
+                    if k >= 3 and not lossy[seq[i][0]] and not lossy[seq[i + 1][0]]:
+                        steps += n_pol * (12 + 2 * (k - 2) + 6 + 12)
+                    else:
+                        steps += k * (step(seq[i][0]) + step(seq[i + 1][0]))
+                    i += 2 * k
+                else:
+                    steps += step(seq[i][0])
+                    i += 1
+            kind = "K1 typed (layer CSE + closed-form power of repeated lossless pairs)"
+        per_thread = (sum(builds.values()) if typed else sum(build(mats[j]) for j in interior)) + steps + epilogue
     return {"flop_per_point": per_thread / n_pol, "kernel_path": kind}
 
 
@@ -254,7 +273,7 @@ def run_ours(args):
     out = {k: torch.empty(shape, dtype=torch.float64, device=eng.device) for k in ("R", "T", "A")}
     stream = torch.cuda.current_stream()
 
-    flags = 16 if args.no_layer_cse else 0  # PST_FLAG_NO_LAYER_CSE
+    flags = (16 if args.no_layer_cse else 0) | (128 if args.no_periodic_power else 0)  # PST_FLAG_NO_LAYER_CSE / _NO_PERIODIC_POWER
 
     def step():
         eng.eval_prepared(prep, pols=pols, out=out, flags=flags)
@@ -292,6 +311,29 @@ def run_ours(args):
     sec_total = float(t_dev.item())
     ms_per_step = sec_total / args.steps * 1e3
     value = points_rank * world * args.steps / sec_total
+
+    # ---- ablations of the algorithmic shortcuts (same grid, same outputs; results agree to rounding / bit for bit)
+    ablation = None
+    if args.workload == "c2" and flags == 0:
+        ablation = {}
+        for name, fl in (("layer_by_layer_pairs", 128), ("no_layer_cse", 128 | 16)):
+            for _ in range(3):
+                eng.eval_prepared(prep, pols=pols, out=out, flags=fl)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+            barrier()
+            for a_, b_ in evs:
+                eng.flush_l2()
+                a_.record(stream)
+                eng.eval_prepared(prep, pols=pols, out=out, flags=fl)
+                b_.record(stream)
+            barrier()
+            t_ab = torch.tensor([sum(a_.elapsed_time(b_) for a_, b_ in evs) / 1e3], dtype=torch.float64, device=eng.device)
+            if world > 1:
+                dist.all_reduce(t_ab, op=dist.ReduceOp.MAX)
+            ablation[name] = {"value": points_rank * world * 20 / float(t_ab.item()), "ms_per_step": float(t_ab.item()) / 20 * 1e3}
+        eng.eval_prepared(prep, pols=pols, out=out, flags=flags)  # leave the default path's results in `out`
+        ablation["note"] = ("layer_by_layer_pairs: PST_FLAG_NO_PERIODIC_POWER (every layer applied one by one, cached "
+                            "matrices); no_layer_cse: additionally rebuild every layer matrix (sincos per layer)")
 
     # ---- e2e: the plugin-style call with HOST buffers (pinned), H2D of the inputs and D2H of R, T, A in the timed region
     mat_n_h = prep["mat_n"].cpu().pin_memory()
@@ -382,7 +424,7 @@ def run_ours(args):
     peaks, peaks_src = load_measured_peaks()
     fp64_peak = eng.fp64_peak_tflops(8192)
     layer_steps = points_rank * w.interior_layers
-    flop_model = algorithmic_flops(w, prep, len(pols), cse=not args.no_layer_cse)
+    flop_model = algorithmic_flops(w, prep, len(pols), cse=not args.no_layer_cse, power=not args.no_periodic_power)
     achieved_tf = flop_model["flop_per_point"] * points_rank / (ms_per_step / 1e3) / 1e12
     survey_tf = layer_steps * FLOP_PER_LAYER_STEP / (ms_per_step / 1e3) / 1e12
     hbm_gbs = 24.0 * points_rank / (ms_per_step / 1e3) / 1e9
@@ -403,7 +445,7 @@ def run_ours(args):
     try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
         with open(os.path.join(ROOT, "profiles", "r01_v4_traffic.json")) as fh:
             tr = json.load(fh)
-        if tr.get("workload") == args.workload and not args.no_layer_cse:
+        if tr.get("workload") == args.workload and flags == tr.get("flags", 0):
             roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             roof["traffic_source"] = tr["source"]
             roof["algorithmic_bytes"] = 24 * points_rank
@@ -413,7 +455,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": desc, "layer_cse": not args.no_layer_cse, "points_per_gpu": points_rank, "interior_layers": w.interior_layers,
+        "config": {"workload": desc, "layer_cse": not args.no_layer_cse, "periodic_power": not (args.no_periodic_power or args.no_layer_cse), "points_per_gpu": points_rank, "interior_layers": w.interior_layers,
                    "layer_steps_per_s": value * w.interior_layers, "l2": "flushed between steps (256 MiB memset); outputs 403 MB/step > L2",
                    "timing": "CUDA events per step on the launch stream, max over ranks", "wall_s_incl_flush": t_wall},
         "roofline": roof,
@@ -423,6 +465,7 @@ def run_ours(args):
                 "d2h_gbs_per_gpu": d2h * e2e_steps / float(t_e2e.item()) / 1e9,
                 "bound": "PCIe device->host copy of R, T, A (24 B/point); kernels overlap the copies",
                 "api": "pst_eval_grid_host via TMMEngine.eval_grid_host, pinned host buffers"},
+        "ablation": ablation,
         "e2e_fused_reduction": fused,
         "gpu_launches": launches,
         "clocks": clocks,
@@ -441,6 +484,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-layer-cse", action="store_true", help="ablation: rebuild every layer matrix (PST_FLAG_NO_LAYER_CSE)")
+    ap.add_argument("--no-periodic-power", action="store_true",
+                    help="ablation: apply repeated lossless pairs layer by layer (PST_FLAG_NO_PERIODIC_POWER)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

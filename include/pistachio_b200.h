@@ -50,6 +50,9 @@ extern "C" {
 #define PST_FLAG_NO_SMEM_STAGING (1u << 3)    /* read the optical table from global memory (debug/ablation) */
 #define PST_FLAG_NO_SWEEP_REUSE (1u << 5)     /* thickness sweeps: rebuild the whole chain for every thickness instead
                                                  of reusing the prefix/suffix products (K3) -- ablation */
+#define PST_FLAG_NO_PERIODIC_POWER (1u << 7)  /* apply a k-times repeated lossless layer pair k times instead of through
+                                                 the closed-form power of its period U^k = S_{k-1} U - S_{k-2} I
+                                                 (Chebyshev identity); both agree to rounding -- ablation */
 #define PST_FLAG_NO_BULK_COPY (1u << 6)       /* stage tables with plain 128-bit loads instead of cp.async.bulk (ablation) */
 #define PST_FLAG_NO_LAYER_CSE (1u << 4)       /* rebuild the matrix of every layer even when layers repeat (ablation;
                                                  results are bit-identical with and without) */

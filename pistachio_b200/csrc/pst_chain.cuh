@@ -203,6 +203,54 @@ PST_HD void pair_loop(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const T
   }
 }
 
+// k repetitions of a LOSSLESS pair in closed form.  One period is U = B A (A is applied first) with
+//   U = [[u00, -i u01], [-i u10, u11]],  u00 = cB cA - beB alA,  u11 = cB cA - alB beA,
+//                                         u01 = cB beA + beB cA,  u10 = alB cA + cB alA      (all real, det U = 1)
+// and by Cayley-Hamilton U^2 = 2x U - I, x = (u00 + u11)/2, so U^k = S_{k-1} U - S_{k-2} I with the Chebyshev
+// recurrence S_0 = 1, S_1 = 2x, S_j = 2x S_{j-1} - S_{j-2} (Yeh, Optical Waves in Layered Media, periodic media).
+// k layer-pair steps (32 FP64 instructions each) become k - 2 FMAs per polarisation.  The recurrence is run forward
+// (the growing solution dominates inside a stop band, so it is stable) and rescaled by exact powers of two every 32
+// steps; the exponent goes to the state.  Agreement with the sequential product: rounding level (tests).
+template <int NPOL, int NC>
+PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, int k) {
+  const double cA = A.a[0], cB = B.a[0];
+  const double cc = cB * cA;
+#pragma unroll
+  for (int p = 0; p < NPOL; ++p) {
+    const double alA = A.a[1 + 2 * p], beA = A.a[2 + 2 * p], alB = B.a[1 + 2 * p], beB = B.a[2 + 2 * p];
+    const double u00 = fma(-beB, alA, cc), u11 = fma(-alB, beA, cc);
+    const double u01 = fma(cB, beA, beB * cA), u10 = fma(alB, cA, cB * alA);
+    const double x2 = u00 + u11;  // 2x
+    double s1 = 1.0, s2 = 0.0;    // S_{j-1}, S_{j-2} at j = 1:  S_0 = 1, S_{-1} = 0
+    int ks = 0;
+    for (int j = 1; j < k; ++j) {  // after the loop: s1 = S_{k-1}, s2 = S_{k-2}
+      const double s = fma(x2, s1, -s2);
+      s2 = s1;
+      s1 = s;
+      if ((j & 31) == 0) {
+        int e = exponent_of(fmax(fabs(s1), fabs(s2)));
+        e = e > 1000 ? 1000 : (e < -1000 ? 0 : e);
+        const double f = pow2i(-e);
+        s1 *= f;
+        s2 *= f;
+        ks += e;
+      }
+    }
+    // U^k = S_{k-1} U - S_{k-2} I
+    const double p00 = fma(s1, u00, -s2), p11 = fma(s1, u11, -s2), p01 = s1 * u01, p10 = s1 * u10;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      double* v = st.v[p][c];
+      const double v0r = v[0], v0i = v[1], v1r = v[2], v1i = v[3];
+      v[0] = fma(p00, v0r, p01 * v1i);
+      v[1] = fma(p00, v0i, -(p01 * v1r));
+      v[2] = fma(p11, v1r, p10 * v0i);
+      v[3] = fma(p11, v1i, -(p10 * v0r));
+    }
+    st.kexp[p] += ks;
+  }
+}
+
 // Build + apply in one go (the untyped path).  `lossless` is the MATERIAL's flag (k = 0 at every wavelength), so
 // the branch is uniform over the block.
 template <int NPOL, int NC>

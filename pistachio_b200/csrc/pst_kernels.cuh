@@ -285,6 +285,14 @@ tmm_chain_kernel(const GridParams prm) {
       }
       load_type(o.y, B);
       const bool lb = (lossy_mask >> o.y) & 1u;
+      if (!la && !lb && o.z >= 3 && !(prm.flags & 128u)) {
+        // a lossless pair repeated k times: closed-form power of the period (Chebyshev identity, pst_chain.cuh)
+        if (since > 0) renormalise<NPOL, NC>(st);
+        apply_pair_power<NPOL, NC>(st, A, B, o.z);
+        renormalise<NPOL, NC>(st);
+        since = 0;
+        continue;
+      }
       int k = o.z;
       while (k > 0) {
         const int n = min(k, max((every - since) / 2, 1));

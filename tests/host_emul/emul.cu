@@ -23,7 +23,50 @@ static void run(int n_wl, int n_theta, int L, const double* wl, const double* co
     for (int it = 0; it < n_theta; ++it) {
       const double ct = cos_theta[it], ict = 1.0 / ct;
       ChainState<NPOL, NCOL> fin;
-      if (W <= 1) {
+      if (W <= 1 && (flags & 256u)) {
+        // typed path with run-length ops and the closed-form power of repeated lossless pairs (what the kernel does
+        // by default for periodic stacks): layer types by (n at this wavelength, thickness)
+        std::vector<int> seq;
+        for (int j = L - 2; j >= 1; --j) {
+          int t = j;
+          for (int u = L - 2; u > j; --u)
+            if (rows[u].nr == rows[j].nr && rows[u].ni == rows[j].ni && d[u] == d[j]) { t = u; break; }
+          seq.push_back(t);
+        }
+        init_exit_columns<NPOL, NCOL>(fin, rows[L - 1].nr, rows[L - 1].ni, ct, pol_first);
+        auto build = [&](int j) {
+          TypeRegs<NPOL> t;
+          if (lossless[j]) t.set_real(build_real_layer<NPOL>(rows[j].qr, rows[j].nr, rows[j].inr, d[j], ct, ict, pol_first));
+          else t.set_cplx(build_cplx_layer<NPOL>(rows[j], d[j], ct, ict, pol_first));
+          return t;
+        };
+        size_t i = 0;
+        const size_t n = seq.size();
+        while (i < n) {
+          if (i + 1 < n) {
+            const int ta = seq[i], tb = seq[i + 1];
+            int k = 1;
+            while (i + 2 * (size_t)k + 1 < n && seq[i + 2 * k] == ta && seq[i + 2 * k + 1] == tb) ++k;
+            const TypeRegs<NPOL> A = build(ta), B = build(tb);
+            if (lossless[ta] && lossless[tb] && k >= 3) {
+              renormalise<NPOL, NCOL>(fin);
+              apply_pair_power<NPOL, NCOL>(fin, A, B, k);
+            } else {
+              for (int r = 0; r < k; ++r) {
+                apply_type<NPOL, NCOL>(fin, A, !lossless[ta]);
+                apply_type<NPOL, NCOL>(fin, B, !lossless[tb]);
+                renormalise<NPOL, NCOL>(fin);
+              }
+            }
+            renormalise<NPOL, NCOL>(fin);
+            i += 2 * (size_t)k;
+          } else {
+            apply_type<NPOL, NCOL>(fin, build(seq[i]), !lossless[seq[i]]);
+            i += 1;
+          }
+        }
+        renormalise<NPOL, NCOL>(fin);
+      } else if (W <= 1) {
         init_exit_columns<NPOL, NCOL>(fin, rows[L - 1].nr, rows[L - 1].ni, ct, pol_first);
         int since = 0;
         for (int j = L - 2; j >= 1; --j) {

@@ -162,11 +162,11 @@ def test_bulk_copy_staging_is_bit_identical(eng, ref_cases):
 def test_layer_cse_is_bit_identical(eng):
     """The typed path (identical layers share one cached matrix) is pure common-subexpression elimination."""
     from pistachio_b200 import workloads
-    from pistachio_b200._cabi import FLAG_FORCE_DEEP_KERNEL, FLAG_NO_LAYER_CSE
+    from pistachio_b200._cabi import FLAG_FORCE_DEEP_KERNEL, FLAG_NO_LAYER_CSE, FLAG_NO_PERIODIC_POWER
 
     w = workloads.c2_dbr_cavity(n_wl=96, n_theta=70, pairs=20)
     prep = eng.prepare_workload(w)
-    for extra in (0, FLAG_FORCE_DEEP_KERNEL):
+    for extra in (FLAG_NO_PERIODIC_POWER, FLAG_FORCE_DEEP_KERNEL):
         a = eng.eval_prepared(prep, flags=extra, want_matrix=True).numpy()
         b = eng.eval_prepared(prep, flags=extra | FLAG_NO_LAYER_CSE, want_matrix=True).numpy()
         for key in ("R", "T", "A", "M"):
@@ -177,6 +177,55 @@ def test_layer_cse_is_bit_identical(eng):
     b = eng.eval_prepared(prep, flags=FLAG_NO_LAYER_CSE).numpy()
     for key in ("R", "T", "A"):
         assert np.array_equal(a[key], b[key]), key
+
+
+def test_periodic_power_path(eng, ref_cases):
+    """A k-times repeated lossless pair goes through the closed-form power of its period (Chebyshev identity).  It must
+    hold the same parity against the reference as the layer-by-layer product and agree with it to rounding, also for
+    the full matrix, for a single polarisation, and for a 1000-pair stop band where the recurrence must be rescaled."""
+    from pistachio_b200 import workloads
+    from pistachio_b200._cabi import FLAG_NO_PERIODIC_POWER
+
+    c = ref_cases["c2_sub"]
+    n = np.asarray(c["n"])
+    # material columns shared between identical layers, as a user of the engine would pass them
+    cols, layer_mat = [], []
+    for row in n:
+        for i, col in enumerate(cols):
+            if np.array_equal(col, row):
+                layer_mat.append(i)
+                break
+        else:
+            layer_mat.append(len(cols))
+            cols.append(row)
+    cols = np.array(cols)
+    kw = dict(cos_theta=np.cos(c["theta"]), want_matrix=True)
+    pw = eng.eval_grid(c["wl"], c["theta"], cols.real, cols.imag, layer_mat, list(c["d"]), **kw).numpy()
+    sq = eng.eval_grid(c["wl"], c["theta"], cols.real, cols.imag, layer_mat, list(c["d"]), flags=FLAG_NO_PERIODIC_POWER, **kw).numpy()
+    assert not np.array_equal(pw["R"], sq["R"])  # the closed form is really taken
+    rep = parity.compare_grid("c2_sub_power", pw["T"][0], pw["R"][0], c["wl"], list(c["n"]), list(c["d"]), c["theta"], c["T"],
+                              c["R"], got_A=pw["A"][0])
+    rep.check(max_loose_fraction=0.05)
+    assert np.abs(pw["R"] - sq["R"]).max() < 2e-13 and np.abs(pw["T"] - sq["T"]).max() < 2e-13
+    scale = np.abs(sq["M"]).max(axis=(-1, -2), keepdims=True)
+    assert np.all(np.abs(pw["M"] - sq["M"]) <= 1e-12 * scale)
+    one = eng.eval_grid(c["wl"], c["theta"], cols.real, cols.imag, layer_mat, list(c["d"]), ("p-wave",),
+                        cos_theta=np.cos(c["theta"])).numpy()
+    assert np.array_equal(one["R"][0, 0], pw["R"][0, 1])
+    # 1000 pairs of a high-contrast mirror: growth 1.7^1000 inside the stop band
+    wl = np.linspace(0.8, 1.25, 48)
+    mat_n = np.array([np.full(48, 1.0), np.full(48, 2.32), np.full(48, 1.36), np.full(48, 1.5)])
+    lm = [0] + [1, 2] * 1000 + [3]
+    d = [0.0] + [1.0 / (4 * 2.32), 1.0 / (4 * 1.36)] * 1000 + [0.0]
+    th = np.array([0.0, 0.6])
+    from pistachio_b200._cabi import FLAG_FORCE_POINT_KERNEL  # few points: the planner would pick the segmented kernel
+
+    a = eng.eval_grid(wl, th, mat_n, np.zeros_like(mat_n), lm, d, flags=FLAG_FORCE_POINT_KERNEL).numpy()
+    b = eng.eval_grid(wl, th, mat_n, np.zeros_like(mat_n), lm, d, flags=FLAG_FORCE_POINT_KERNEL | FLAG_NO_PERIODIC_POWER).numpy()
+    assert not np.array_equal(a["R"], b["R"])
+    assert np.isfinite(a["R"]).all() and np.isfinite(a["T"]).all()
+    np.testing.assert_allclose(a["R"], b["R"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(a["R"] + a["T"], 1.0, atol=1e-9)
 
 
 def test_resonant_cavity_against_50_digit_truth(eng):

@@ -113,3 +113,27 @@ def test_emul_thick_absorber_and_deep_bragg_stay_finite(emul):
         assert np.isfinite(R).all() and np.isfinite(T).all()
         assert (R >= 0).all() and (R <= 1 + 1e-12).all() and (T >= 0).all()
         np.testing.assert_allclose(R + T, 1.0, atol=1e-9)
+
+
+def test_emul_periodic_power_matches_reference_and_sequential(emul, ref_cases):
+    """Closed-form power of a repeated lossless pair (Chebyshev identity, apply_pair_power) vs the reference fixture
+    and vs the layer-by-layer product, on the 2 x 20-pair DBR cavity and on a 1000-pair stop band (rescaled recurrence)."""
+    c = ref_cases["c2_sub"]
+    Rs, Ts, _, Ms = run_emul(emul, c["wl"], list(c["n"]), list(c["d"]), c["theta"], ncol=2)
+    Rp, Tp, Ap, Mp = run_emul(emul, c["wl"], list(c["n"]), list(c["d"]), c["theta"], ncol=2, flags=256)
+    rep = parity.compare_grid("c2_sub_power", Tp, Rp, c["wl"], list(c["n"]), list(c["d"]), c["theta"], c["T"], c["R"], got_A=Ap)
+    rep.check(max_loose_fraction=0.05)
+    assert np.abs(Rp - Rs).max() < 2e-13 and np.abs(Tp - Ts).max() < 2e-13
+    scale = np.abs(Ms).max(axis=(-1, -2), keepdims=True)
+    assert np.all(np.abs(Mp - Ms) <= 1e-12 * scale)
+    # deep Bragg stack: the recurrence grows like 1.7^1000 and must be rescaled, the result stays finite and agrees
+    wl = np.linspace(0.8, 1.25, 12)
+    pairs = 1000
+    n_list = [np.full(12, 1.0 + 0j)] + [np.full(12, v + 0j) for v in (2.32, 1.36)] * pairs + [np.full(12, 1.5 + 0j)]
+    d = [0.0] + [1.0 / (4 * 2.32), 1.0 / (4 * 1.36)] * pairs + [0.0]
+    Rs, Ts, _, _ = run_emul(emul, wl, n_list, d, [0.0, 0.6])
+    Rp, Tp, _, _ = run_emul(emul, wl, n_list, d, [0.0, 0.6], flags=256)
+    assert np.isfinite(Rp).all() and np.isfinite(Tp).all()
+    np.testing.assert_allclose(Rp, Rs, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(Tp, Ts, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(Rp + Tp, 1.0, atol=1e-9)
