@@ -215,29 +215,56 @@ template <int NPOL, int NC>
 PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, int k) {
   const double cA = A.a[0], cB = B.a[0];
   const double cc = cB * cA;
+  double u00[NPOL], u11[NPOL], u01[NPOL], u10[NPOL], x2[NPOL];
+  double sa[NPOL], sb[NPOL];  // (S_{j-1}, S_{j-2}); a step pair updates them in place, no register shuffling
+  int ks[NPOL];
 #pragma unroll
   for (int p = 0; p < NPOL; ++p) {
     const double alA = A.a[1 + 2 * p], beA = A.a[2 + 2 * p], alB = B.a[1 + 2 * p], beB = B.a[2 + 2 * p];
-    const double u00 = fma(-beB, alA, cc), u11 = fma(-alB, beA, cc);
-    const double u01 = fma(cB, beA, beB * cA), u10 = fma(alB, cA, cB * alA);
-    const double x2 = u00 + u11;  // 2x
-    double s1 = 1.0, s2 = 0.0;    // S_{j-1}, S_{j-2} at j = 1:  S_0 = 1, S_{-1} = 0
-    int ks = 0;
-    for (int j = 1; j < k; ++j) {  // after the loop: s1 = S_{k-1}, s2 = S_{k-2}
-      const double s = fma(x2, s1, -s2);
-      s2 = s1;
-      s1 = s;
-      if ((j & 31) == 0) {
-        int e = exponent_of(fmax(fabs(s1), fabs(s2)));
-        e = e > 1000 ? 1000 : (e < -1000 ? 0 : e);
-        const double f = pow2i(-e);
-        s1 *= f;
-        s2 *= f;
-        ks += e;
+    u00[p] = fma(-beB, alA, cc);
+    u11[p] = fma(-alB, beA, cc);
+    u01[p] = fma(cB, beA, beB * cA);
+    u10[p] = fma(alB, cA, cB * alA);
+    x2[p] = u00[p] + u11[p];  // 2x
+    sa[p] = 1.0;              // S_0
+    sb[p] = 0.0;              // S_{-1}
+    ks[p] = 0;
+  }
+  // k - 1 recurrence steps for both polarisations together (two independent chains), two steps per iteration:
+  //   sb <- 2x sa - sb  (= S_j),  sa <- 2x sb - sa  (= S_{j+1});  rescaled by an exact power of two every 32 steps
+  int left = k - 1;
+  while (left >= 2) {
+    const int n2 = (left >> 1) < 16 ? (left >> 1) : 16;
+    for (int i = 0; i < n2; ++i) {
+#pragma unroll
+      for (int p = 0; p < NPOL; ++p) {
+        sb[p] = fma(x2[p], sa[p], -sb[p]);
+        sa[p] = fma(x2[p], sb[p], -sa[p]);
       }
     }
+    left -= 2 * n2;
+    if (left >= 2) {
+#pragma unroll
+      for (int p = 0; p < NPOL; ++p) {
+        int e = exponent_of(fmax(fabs(sa[p]), fabs(sb[p])));
+        e = e > 1000 ? 1000 : (e < -1000 ? 0 : e);
+        const double f = pow2i(-e);
+        sa[p] *= f;
+        sb[p] *= f;
+        ks[p] += e;
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NPOL; ++p) {
+    if (left == 1) {  // odd number of steps: one more, then restore the (S_{k-1}, S_{k-2}) roles
+      const double s = fma(x2[p], sa[p], -sb[p]);
+      sb[p] = sa[p];
+      sa[p] = s;
+    }
     // U^k = S_{k-1} U - S_{k-2} I
-    const double p00 = fma(s1, u00, -s2), p11 = fma(s1, u11, -s2), p01 = s1 * u01, p10 = s1 * u10;
+    const double p00 = fma(sa[p], u00[p], -sb[p]), p11 = fma(sa[p], u11[p], -sb[p]);
+    const double p01 = sa[p] * u01[p], p10 = sa[p] * u10[p];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       double* v = st.v[p][c];
@@ -247,7 +274,7 @@ PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, 
       v[2] = fma(p11, v1r, p10 * v0i);
       v[3] = fma(p11, v1i, -(p10 * v0r));
     }
-    st.kexp[p] += ks;
+    st.kexp[p] += ks[p];
   }
 }
 
