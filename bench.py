@@ -443,9 +443,18 @@ def run_ours(args):
                             "address arithmetic not counted; see DESIGN.md section 4 and the ncu FP64-pipe utilisation in profiles/"}
     roof["hbm_store"] = {"achieved_gbs": hbm_gbs, "peak_gbs": peaks.get("hbm_gbs"), "frac": hbm_frac}
     try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
-        with open(os.path.join(ROOT, "profiles", "r01_v4_traffic.json")) as fh:
-            tr = json.load(fh)
-        if tr.get("workload") == args.workload and flags == tr.get("flags", 0):
+        import glob
+
+        cands = []
+        for path in glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")):
+            with open(path) as fh:
+                t = json.load(fh)
+            if t.get("workload") == args.workload and flags == t.get("flags", 0):
+                import re
+
+                cands.append((tuple(int(x) for x in re.findall(r"\d+", os.path.basename(path))), os.path.basename(path), t))
+        tr = max(cands, key=lambda c: c[:2])[2] if cands else {}  # newest capture of this workload (files are named rNN_vMM_traffic.json)
+        if tr:
             roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             roof["traffic_source"] = tr["source"]
             roof["algorithmic_bytes"] = 24 * points_rank
