@@ -88,8 +88,8 @@ struct pst_handle_s {
   DevBuf<int> mat_flags;
   int n_types = 0;                 // layer-type analysis of the current layer list (sync_layers)
   int type_layer[kMaxTypes] = {0};
-  DevBuf<int4> ops_dev;            // run-length ops of the typed path
-  std::vector<int4> ops_host;
+  std::vector<int4> ops_host;      // run-length ops of the typed path (passed by value: TypedPlan)
+  DevBuf<unsigned> lossy_types;    // bit t: the material of layer type t absorbs (flag_layers_kernel)
   DevBuf<unsigned char> l2buf;
   DevBuf<double> sink;
   // host-buffer pipeline (pst_eval_grid_host)
@@ -130,7 +130,7 @@ extern "C" int pst_destroy(pst_handle_t h) {
   if (!h) return PST_OK;
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
-  h->opt.release(); h->trig.release(); h->layers_dev.release(); h->layers_flagged.release(); h->taboff.release(); h->mat_flags.release(); h->ops_dev.release(); h->l2buf.release();
+  h->opt.release(); h->trig.release(); h->layers_dev.release(); h->layers_flagged.release(); h->taboff.release(); h->mat_flags.release(); h->lossy_types.release(); h->l2buf.release();
   h->sink.release(); h->hp_in.release(); h->hp_out[0].release(); h->hp_out[1].release();
   for (int i = 0; i < 2; ++i) {
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -177,21 +177,30 @@ namespace {
 using ChainKernel = void (*)(const GridParams);
 
 template <int P, int C>
-ChainKernel chain_variant(bool so, bool sl, bool seg, bool typed) {
-#define PST_V(O, L, S, T) \
-  if (so == O && sl == L && seg == S && typed == T) return tmm_chain_kernel<P, C, O, L, S, T>;
-#define PST_V2(O, L) PST_V(O, L, false, false) PST_V(O, L, false, true) PST_V(O, L, true, false)
+ChainKernel chain_variant(bool so, bool sl, bool seg) {
+#define PST_V(O, L, S) \
+  if (so == O && sl == L && seg == S) return tmm_chain_kernel<P, C, O, L, S>;
+#define PST_V2(O, L) PST_V(O, L, false) PST_V(O, L, true)
   PST_V2(true, true) PST_V2(true, false) PST_V2(false, true) PST_V2(false, false)
 #undef PST_V2
 #undef PST_V
   return nullptr;
 }
 
-ChainKernel pick_chain(int npol, int ncol, bool so, bool sl, bool seg, bool typed) {
-  if (npol == 1 && ncol == 1) return chain_variant<1, 1>(so, sl, seg, typed);
-  if (npol == 1 && ncol == 2) return chain_variant<1, 2>(so, sl, seg, typed);
-  if (npol == 2 && ncol == 1) return chain_variant<2, 1>(so, sl, seg, typed);
-  if (npol == 2 && ncol == 2) return chain_variant<2, 2>(so, sl, seg, typed);
+ChainKernel pick_chain(int npol, int ncol, bool so, bool sl, bool seg) {
+  if (npol == 1 && ncol == 1) return chain_variant<1, 1>(so, sl, seg);
+  if (npol == 1 && ncol == 2) return chain_variant<1, 2>(so, sl, seg);
+  if (npol == 2 && ncol == 1) return chain_variant<2, 1>(so, sl, seg);
+  if (npol == 2 && ncol == 2) return chain_variant<2, 2>(so, sl, seg);
+  return nullptr;
+}
+
+using TypedKernel = void (*)(const GridParams, const TypedPlan);
+TypedKernel pick_typed(int npol, int ncol) {
+  if (npol == 1 && ncol == 1) return tmm_typed_kernel<1, 1>;
+  if (npol == 1 && ncol == 2) return tmm_typed_kernel<1, 2>;
+  if (npol == 2 && ncol == 1) return tmm_typed_kernel<2, 1>;
+  if (npol == 2 && ncol == 2) return tmm_typed_kernel<2, 2>;
   return nullptr;
 }
 
@@ -280,10 +289,6 @@ int sync_layers(pst_handle_t h, const pst_grid_args* a, cudaStream_t st) {
       }
     }
   }
-  if (!ops.empty()) {
-    PST_TRY(h->ops_dev.ensure(ops.size()));
-    PST_CUDA(cudaMemcpyAsync(h->ops_dev.p, ops.data(), ops.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
-  }
   h->ops_host.swap(ops);
   PST_TRY(h->layers_dev.ensure(cur.size()));
   PST_CUDA(cudaMemcpyAsync(h->layers_dev.p, cur.data(), cur.size() * sizeof(LayerEntry), cudaMemcpyHostToDevice, st));
@@ -305,8 +310,12 @@ int run_prep(pst_handle_t h, const pst_grid_args* a, const double* wl, const dou
   prep_trig_kernel<<<(a->n_theta + 255) / 256, 256, 0, st>>>(theta, cos_theta, a->n_theta, h->trig.p);
   PST_CUDA(cudaGetLastError());
   PST_TRY(h->layers_flagged.ensure(a->n_layers));
+  PST_TRY(h->lossy_types.ensure(1));
+  TypeMats tm;
+  tm.n = h->n_types;
+  for (int t = 0; t < kMaxTypes; ++t) tm.mat[t] = t < h->n_types ? a->layer_mat[h->type_layer[t]] : 0;
   flag_layers_kernel<<<(a->n_layers + 255) / 256, 256, 0, st>>>(h->layers_dev.p, h->mat_flags.p, a->n_layers,
-                                                               h->layers_flagged.p);
+                                                               h->layers_flagged.p, tm, h->lossy_types.p);
   PST_CUDA(cudaGetLastError());
   h->launches += 3;
   return PST_OK;
@@ -317,6 +326,7 @@ struct ChainPlan {
   bool so, sl, seg, typed;
   size_t smem;
   ChainKernel fn;
+  TypedKernel fn_typed;
 };
 
 int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPlan* pl) {
@@ -353,24 +363,31 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
     }
   }
   const int nthr = pl->PB * W;
-  // typed path: worth it when layer matrices repeat (fewer distinct types than interior layers per segment)
   // typed path (single-segment kernel only): worth it when layer matrices repeat
-  pl->typed = !pl->seg && !(a->flags & PST_FLAG_NO_LAYER_CSE) && h->n_types > 0 && Li >= 2 * h->n_types;
+  pl->typed = !pl->seg && !(a->flags & PST_FLAG_NO_LAYER_CSE) && h->n_types > 0 && Li >= 2 * h->n_types &&
+              (int)h->ops_host.size() <= kMaxOps;
   pl->type_stride = 0;
+  pl->fn_typed = nullptr;
   if (pl->typed) {
     int units = h->n_types * (kTypeRecBytes / 16);
     if (units % 2 == 0) units += 1;
     pl->type_stride = units * 16;
+    pl->so = pl->sl = false;
+    pl->smem = (size_t)pl->PB * pl->type_stride;
+    pl->tl_rows = pl->opt_row_bytes = 0;
+    pl->fn_typed = pick_typed(pl->npol, pl->ncol);
+    pl->fn = nullptr;
+    if (!pl->fn_typed) return fail(PST_E_INVALID, "pst_eval_grid: no typed kernel variant for this configuration");
+    if (pl->smem > 48 * 1024)
+      PST_CUDA(cudaFuncSetAttribute((const void*)pl->fn_typed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    return PST_OK;
   }
   pl->tl_rows = std::min(n_wl_launch, (pl->PB - 1) / a->n_theta + 2);
   pl->opt_row_bytes = a->n_mat * 48 + ((a->n_mat % 2 == 0) ? 16 : 0);
   const size_t budget = std::min<size_t>(h->smem_optin, 200 * 1024);
   const size_t seg_bytes = pl->seg ? (size_t)W * pl->npol * 9 * pl->PB * sizeof(double) : 0;
-  size_t type_bytes = pl->typed ? (size_t)nthr * pl->type_stride : 0;
-  if (seg_bytes + type_bytes > budget * 3 / 4) {
-    pl->typed = false;
-    type_bytes = 0;
-  }
+  const size_t type_bytes = 0;
+  (void)nthr;
   const size_t lay_bytes = (size_t)a->n_layers * sizeof(LayerEntry);
   const size_t opt_bytes = (size_t)pl->tl_rows * pl->opt_row_bytes;
   pl->sl = lay_bytes <= 64 * 1024 && seg_bytes + type_bytes + lay_bytes <= budget;
@@ -379,7 +396,7 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
   used += pl->so ? opt_bytes : 0;
   if (used > budget) return fail(PST_E_INVALID, "pst_eval_grid: shared-memory plan exceeds the device limit");
   pl->smem = used;
-  pl->fn = pick_chain(pl->npol, pl->ncol, pl->so, pl->sl, pl->seg, pl->typed);
+  pl->fn = pick_chain(pl->npol, pl->ncol, pl->so, pl->sl, pl->seg);
   if (!pl->fn) return fail(PST_E_INVALID, "pst_eval_grid: no kernel variant for this configuration");
   if (used > 48 * 1024) PST_CUDA(cudaFuncSetAttribute((const void*)pl->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
   return PST_OK;
@@ -400,17 +417,30 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
   prm.tl_rows = pl.tl_rows;
   prm.opt_row_bytes = pl.opt_row_bytes;
   prm.il0 = il0;
-  prm.n_types = pl.typed ? h->n_types : 0;
-  prm.type_stride = pl.type_stride;
-  for (int t = 0; t < kMaxTypes; ++t) prm.type_layer[t] = h->type_layer[t];
-  prm.n_ops = pl.typed ? (int)h->ops_host.size() : 0;
-  prm.ops = h->ops_dev.p;
   prm.flags = a->flags;
   prm.points = (long long)n_wl_launch * a->n_theta;
   prm.opt = h->opt.p;
   prm.mat_flags = h->mat_flags.p;
   prm.trig = h->trig.p;
-  prm.layers = pl.typed ? h->layers_dev.p : h->layers_flagged.p;  // typed: type ids; untyped: material flags
+  prm.layers = h->layers_flagged.p;  // `type` field = the material's lossy flag
+  TypedPlan tp;
+  std::memset(&tp, 0, sizeof(tp));
+  if (pl.typed) {
+    tp.n_types = h->n_types;
+    tp.n_ops = (int)h->ops_host.size();
+    tp.sweep_type = -1;
+    tp.mat_first = a->layer_mat[0];
+    tp.mat_last = a->layer_mat[a->n_layers - 1];
+    tp.type_stride = pl.type_stride;
+    for (int t = 0; t < h->n_types; ++t) {
+      const int j = h->type_layer[t];
+      tp.type_mat[t] = a->layer_mat[j];
+      tp.type_d[t] = a->layer_d[j];
+      if (j == a->sweep_layer) tp.sweep_type = t;
+    }
+    for (int i = 0; i < tp.n_ops; ++i) tp.ops[i] = h->ops_host[i];
+    tp.lossy_types = h->lossy_types.p;
+  }
   prm.use_bulk = (a->flags & PST_FLAG_NO_BULK_COPY) ? 0 : 1;
   const long long nblk = (prm.points + pl.PB - 1) / pl.PB;
   if (nblk > 0x7fffffffLL) return fail(PST_E_INVALID, "pst_eval_grid: too many blocks");
@@ -423,7 +453,8 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
     prm.A = A ? A + (size_t)s0 * per_sweep : nullptr;
     prm.M = M ? M + (size_t)s0 * per_sweep * 8 : nullptr;
     dim3 grid((unsigned)nblk, (unsigned)ns), block(pl.PB, pl.W);
-    pl.fn<<<grid, block, pl.smem, st>>>(prm);
+    if (pl.typed) pl.fn_typed<<<grid, block, pl.smem, st>>>(prm, tp);
+    else pl.fn<<<grid, block, pl.smem, st>>>(prm);
     PST_CUDA(cudaGetLastError());
     h->launches += 1;
   }

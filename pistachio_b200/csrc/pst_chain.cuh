@@ -158,18 +158,18 @@ struct TypeRegs {
     }
     sc = m.sc;
   }
-  // G with max|M v| <= G max|v| (component-wise max norm), used to space the rescaling
-  PST_HD double growth_bound(bool lossy) const {
-    double g = 0.0;
-    if (!lossy) {
+  // Largest high word (sign cleared) over the entries: an integer stand-in for max|entry| (monotone in magnitude).
+  PST_HD unsigned max_hi(bool lossy) const {
+    unsigned m = 0;
+    const int n = lossy ? 2 + 4 * NPOL : 1 + 2 * NPOL;
 #pragma unroll
-      for (int p = 0; p < NPOL; ++p) g = fmax(g, fmax(fabs(a[1 + 2 * p]), fabs(a[2 + 2 * p])));
-      return 1.0 + g;  // |cos| <= 1
+    for (int k = 0; k < 10; ++k) {
+      if (k < n) {
+        const unsigned h = (unsigned)hi_word(a[k]) & 0x7fffffffu;
+        m = h > m ? h : m;
+      }
     }
-#pragma unroll
-    for (int p = 0; p < NPOL; ++p)
-      g = fmax(g, fmax(fabs(a[2 + 4 * p]) + fabs(a[3 + 4 * p]), fabs(a[4 + 4 * p]) + fabs(a[5 + 4 * p])));
-    return fabs(a[0]) + fabs(a[1]) + g;
+    return m;
   }
 };
 
@@ -211,24 +211,26 @@ PST_HD void pair_loop(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const T
 // k layer-pair steps (32 FP64 instructions each) become k - 2 FMAs per polarisation.  The recurrence is run forward
 // (the growing solution dominates inside a stop band, so it is stable) and rescaled by exact powers of two every 32
 // steps; the exponent goes to the state.  Agreement with the sequential product: rounding level (tests).
-template <int NPOL, int NC>
-PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, int k) {
-  const double cA = A.a[0], cB = B.a[0];
-  const double cc = cB * cA;
-  double u00[NPOL], u11[NPOL], u01[NPOL], u10[NPOL], x2[NPOL];
-  double sa[NPOL], sb[NPOL];  // (S_{j-1}, S_{j-2}); a step pair updates them in place, no register shuffling
+// Chebyshev coefficients of a period's k-th power: (S_{k-1}, S_{k-2}) 2^ks.  They depend on the period only through
+// its trace, which is the same for U = B A and its mirror image A B (bit for bit: the two products commute term by
+// term), so a cavity between two mirrored Bragg stacks runs the recurrence once.
+template <int NPOL>
+struct PairPower {
+  double sa[NPOL], sb[NPOL];
   int ks[NPOL];
+};
+
+template <int NPOL>
+PST_HD void pair_power_coeffs(const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, int k, PairPower<NPOL>& S) {
+  const double cc = B.a[0] * A.a[0];
+  double x2[NPOL];
 #pragma unroll
   for (int p = 0; p < NPOL; ++p) {
     const double alA = A.a[1 + 2 * p], beA = A.a[2 + 2 * p], alB = B.a[1 + 2 * p], beB = B.a[2 + 2 * p];
-    u00[p] = fma(-beB, alA, cc);
-    u11[p] = fma(-alB, beA, cc);
-    u01[p] = fma(cB, beA, beB * cA);
-    u10[p] = fma(alB, cA, cB * alA);
-    x2[p] = u00[p] + u11[p];  // 2x
-    sa[p] = 1.0;              // S_0
-    sb[p] = 0.0;              // S_{-1}
-    ks[p] = 0;
+    x2[p] = fma(-beB, alA, cc) + fma(-alB, beA, cc);  // u00 + u11 = 2x
+    S.sa[p] = 1.0;                                     // S_0
+    S.sb[p] = 0.0;                                     // S_{-1}
+    S.ks[p] = 0;
   }
   // k - 1 recurrence steps for both polarisations together (two independent chains), two steps per iteration:
   //   sb <- 2x sa - sb  (= S_j),  sa <- 2x sb - sa  (= S_{j+1});  rescaled by an exact power of two every 32 steps
@@ -238,33 +240,46 @@ PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, 
     for (int i = 0; i < n2; ++i) {
 #pragma unroll
       for (int p = 0; p < NPOL; ++p) {
-        sb[p] = fma(x2[p], sa[p], -sb[p]);
-        sa[p] = fma(x2[p], sb[p], -sa[p]);
+        S.sb[p] = fma(x2[p], S.sa[p], -S.sb[p]);
+        S.sa[p] = fma(x2[p], S.sb[p], -S.sa[p]);
       }
     }
     left -= 2 * n2;
     if (left >= 2) {
 #pragma unroll
       for (int p = 0; p < NPOL; ++p) {
-        int e = exponent_of(fmax(fabs(sa[p]), fabs(sb[p])));
+        int e = exponent_of(fmax(fabs(S.sa[p]), fabs(S.sb[p])));
         e = e > 1000 ? 1000 : (e < -1000 ? 0 : e);
         const double f = pow2i(-e);
-        sa[p] *= f;
-        sb[p] *= f;
-        ks[p] += e;
+        S.sa[p] *= f;
+        S.sb[p] *= f;
+        S.ks[p] += e;
       }
     }
   }
+  if (left == 1) {  // odd number of steps: one more, then restore the (S_{k-1}, S_{k-2}) roles
+#pragma unroll
+    for (int p = 0; p < NPOL; ++p) {
+      const double s = fma(x2[p], S.sa[p], -S.sb[p]);
+      S.sb[p] = S.sa[p];
+      S.sa[p] = s;
+    }
+  }
+}
+
+// v <- U^k v with U = B A (A applied first) and U^k = S_{k-1} U - S_{k-2} I
+template <int NPOL, int NC>
+PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B,
+                             const PairPower<NPOL>& S) {
+  const double cA = A.a[0], cB = B.a[0];
+  const double cc = cB * cA;
 #pragma unroll
   for (int p = 0; p < NPOL; ++p) {
-    if (left == 1) {  // odd number of steps: one more, then restore the (S_{k-1}, S_{k-2}) roles
-      const double s = fma(x2[p], sa[p], -sb[p]);
-      sb[p] = sa[p];
-      sa[p] = s;
-    }
-    // U^k = S_{k-1} U - S_{k-2} I
-    const double p00 = fma(sa[p], u00[p], -sb[p]), p11 = fma(sa[p], u11[p], -sb[p]);
-    const double p01 = sa[p] * u01[p], p10 = sa[p] * u10[p];
+    const double alA = A.a[1 + 2 * p], beA = A.a[2 + 2 * p], alB = B.a[1 + 2 * p], beB = B.a[2 + 2 * p];
+    const double u00 = fma(-beB, alA, cc), u11 = fma(-alB, beA, cc);
+    const double u01 = fma(cB, beA, beB * cA), u10 = fma(alB, cA, cB * alA);
+    const double p00 = fma(S.sa[p], u00, -S.sb[p]), p11 = fma(S.sa[p], u11, -S.sb[p]);
+    const double p01 = S.sa[p] * u01, p10 = S.sa[p] * u10;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       double* v = st.v[p][c];
@@ -274,8 +289,15 @@ PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, 
       v[2] = fma(p11, v1r, p10 * v0i);
       v[3] = fma(p11, v1i, -(p10 * v0r));
     }
-    st.kexp[p] += ks[p];
+    st.kexp[p] += S.ks[p];
   }
+}
+
+template <int NPOL, int NC>
+PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, int k) {
+  PairPower<NPOL> S;
+  pair_power_coeffs<NPOL>(A, B, k, S);
+  apply_pair_power<NPOL, NC>(st, A, B, S);
 }
 
 // Build + apply in one go (the untyped path).  `lossless` is the MATERIAL's flag (k = 0 at every wavelength), so
@@ -310,6 +332,15 @@ PST_HD void renormalise(ChainState<NPOL, NC>& st) {
       for (int k = 0; k < 4; ++k) st.v[p][c][k] *= s;
     st.kexp[p] += e;
   }
+}
+
+// lg >= log2 G with max|M v| <= G max|v| over a set of cached layer matrices, from the largest high word m_hi of
+// their entries (e = floor(log2 max|entry|)):
+//   lossless   G = 1 + max(|al|, |be|)                       <= 2 max(1, m)  ->  1 + max(e + 1, 0)
+//   absorbing  G = |c.re| + |c.im| + max(|m.re| + |m.im|)    <= 4 max(1, m)  ->  2 + max(e + 1, 0)
+PST_HD int growth_log2(unsigned m_hi, bool any_lossy) {
+  const int e = (int)(m_hi >> 20) - 1023;
+  return (e + 1 > 0 ? e + 1 : 0) + (any_lossy ? 2 : 1);
 }
 
 // Exit-medium columns D_f[:, c]:  s: (1, +-n_f cos)   p: (cos, +-n_f)                       (tm.py:209,212)
@@ -362,6 +393,12 @@ PST_HD double scale2(double x, int e) {
   const int h = e / 2;
   return x * pow2i(h) * pow2i(e - h);
 }
+// x * 2^(2h): one power of two applied twice (same result as scale2(x, 2h), fewer integer instructions)
+PST_HD double scale_sq(double x, int h) {
+  h = h > 1023 ? 1023 : (h < -1023 ? -1023 : h);
+  const double f = from_words((h + 1023) << 20, 0);  // h = -1023 gives 0.0
+  return x * f * f;
+}
 
 struct PointOut {
   double R, T, A;
@@ -392,7 +429,7 @@ PST_HD PointOut finish_point(const ChainState<NPOL, NCOL>& fin, int p, double in
   out.R = num * iden;
   // det M = a_last / a_first = n_f / n_0 for both polarisations (the cos factors cancel)
   const double det_re = fma(nfr, in0r, -(nfi * in0i));
-  out.T = scale2(det_re * iden, -2 * fin.kexp[p]);
+  out.T = scale_sq(det_re * iden, -fin.kexp[p]);
   if constexpr (NCOL == 2) {
     if (flags & 4u) {
       // numeric determinant like np.linalg.det (tm.py:486); the 2^kexp factors cancel

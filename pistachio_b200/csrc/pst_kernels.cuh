@@ -32,6 +32,7 @@ struct LayerEntry {  // 16 bytes: one LDS.128 / LDG.128 per layer
 constexpr int kMaxTypes = 8;        // distinct (material, thickness) pairs the typed path caches per thread
 constexpr int kTypeRecBytes = 96;   // one cached layer matrix: 12 doubles (complex form) or 6 (real form)
 constexpr int kRenormEvery = 16;
+constexpr int kMaxOps = 24;         // run-length ops the typed kernel takes by value (longer programs use K1 untyped)
 
 struct GridParams {
   int n_wl, n_theta, n_mat, n_layers;
@@ -40,11 +41,6 @@ struct GridParams {
   int tl_rows;       // wavelength rows of the shared-memory optical table (>= max wavelengths per block)
   int opt_row_bytes; // bytes per wavelength row in shared memory: n_mat*48 (+16 pad when n_mat is even)
   int il0;           // first wavelength index of this launch (host pipeline launches wavelength windows)
-  int n_types;       // typed path: number of cached layer types
-  int type_stride;   // typed path: bytes of cache per thread (odd multiple of 16: conflict-free LDS.128)
-  int type_layer[kMaxTypes];  // representative layer index of each type
-  int n_ops;         // typed path: number of run-length ops
-  const int4* ops;   // typed path: (type A, type B or -1, repeat count, 0), in application order (exit side first)
   unsigned flags;
   int use_bulk;      // stage the tables with the bulk-copy engine (cp.async.bulk + mbarrier)
   long long points;  // wavelengths of this launch * n_theta
@@ -57,6 +53,18 @@ struct GridParams {
   double* T;
   double* A;
   double* M;
+};
+
+// The typed kernel's program, passed BY VALUE (constant bank): nothing on its dependent path is a global load.
+struct TypedPlan {
+  int n_types, n_ops;
+  int sweep_type;           // type whose thickness is sweep_d[blockIdx.y]; -1: none
+  int mat_first, mat_last;  // materials of the incidence and the exit medium
+  int type_stride;          // bytes of layer-matrix cache per thread (odd multiple of 16: conflict-free LDS.128)
+  int type_mat[kMaxTypes];
+  double type_d[kMaxTypes];
+  int4 ops[kMaxOps];        // (type A, type B or -1, repeat count, 0), in application order (exit side first)
+  const unsigned* lossy_types;  // device word, bit t: the material of type t absorbs somewhere on the grid (flag kernel)
 };
 
 // ---------------------------------------------------------------------------------------------- K0
@@ -127,9 +135,18 @@ __global__ void prep_optical_kernel(const double* __restrict__ wl, const double*
 
 // Layer list for the untyped paths: `type` replaced by the material's lossy flag, so the layer loop needs no
 // second lookup and the list can be staged by a plain bulk copy.
+struct TypeMats {
+  int n;
+  int mat[kMaxTypes];
+};
 __global__ void flag_layers_kernel(const LayerEntry* __restrict__ layers, const int* __restrict__ mat_flags, int n,
-                                   LayerEntry* __restrict__ out) {
+                                   LayerEntry* __restrict__ out, const TypeMats tm, unsigned* __restrict__ lossy_types) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) {  // bit t: the material of layer type t absorbs (typed kernel)
+    unsigned m = 0;
+    for (int t = 0; t < tm.n; ++t) m |= (mat_flags[tm.mat[t]] != 0 ? 1u : 0u) << t;
+    *lossy_types = m;
+  }
   if (j >= n) return;
   LayerEntry e = layers[j];
   e.type = mat_flags[e.mat];
@@ -149,14 +166,7 @@ __global__ void prep_trig_kernel(const double* __restrict__ theta, const double*
 // thickness-sweep values; each thread owns one point and both polarisations.
 //   STAGE_OPT / STAGE_LAYERS  optical table window and layer list staged in shared memory once per block
 //   SEG    blockDim.y ordered layer segments per point, combined in order through shared memory (deep stacks)
-//   TYPED  layers with identical (material, thickness) share one layer matrix (pure common-subexpression
-//          elimination: the applied matrices are bit-identical to the untyped path's).  Every distinct matrix is built
-//          once per thread into a shared-memory record; the host compiles the layer sequence into run-length ops
-//          "apply (A, B) k times" (periodic stacks: quarter-wave mirrors), and the op loop keeps A and B in registers,
-//          so the inner loop is 2 x 16 FP64 instructions per (A, B) pair with no per-layer loads or dispatch.
-//          (v2 read the cached matrix from shared memory per layer and was LSU-bound; a per-layer switch over
-//          register-resident types was latency-bound -- profiles/r01_v2, r01_v3.)
-template <int NPOL, int NCOL, bool STAGE_OPT, bool STAGE_LAYERS, bool SEG, bool TYPED>
+template <int NPOL, int NCOL, bool STAGE_OPT, bool STAGE_LAYERS, bool SEG>
 __global__ void __launch_bounds__(SEG ? 512 : 256)
 tmm_chain_kernel(const GridParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -173,13 +183,11 @@ tmm_chain_kernel(const GridParams prm) {
   const int TL = prm.il0 + (int)(p_last / nth) - l_lo + 1;
   const int L = prm.n_layers;
 
-  // ---- shared-memory carve-up: [optical table][layer list][layer-matrix cache][segment products]
+  // ---- shared-memory carve-up: [optical table][layer list][segment products]
   unsigned char* s_opt = smem_raw;
   size_t off = STAGE_OPT ? (size_t)prm.tl_rows * prm.opt_row_bytes : 0;
   LayerEntry* s_layers = reinterpret_cast<LayerEntry*>(smem_raw + off);
   off += STAGE_LAYERS ? (size_t)L * sizeof(LayerEntry) : 0;
-  unsigned char* s_types = smem_raw + off;
-  off += TYPED ? (size_t)nthr * prm.type_stride : 0;
   double* s_seg = reinterpret_cast<double*>(smem_raw + off);
 
   // the block's wavelength window of the [wl][mat][6] table is one contiguous global range; rows are re-pitched
@@ -219,38 +227,6 @@ tmm_chain_kernel(const GridParams prm) {
   };
   const OptRow exit_row = opt_row(lay[L - 1].mat);
 
-  // ---- typed path: build each distinct layer matrix once per thread into its shared-memory record
-  unsigned char* my_types = s_types + (size_t)tid * prm.type_stride;
-  unsigned lossy_mask = 0;
-  auto load_type = [&](int t, TypeRegs<NPOL>& out) {
-    const double2* rec = reinterpret_cast<const double2*>(my_types + t * kTypeRecBytes);
-#pragma unroll
-    for (int k = 0; k < 5; ++k) { const double2 v = rec[k]; out.a[2 * k] = v.x; out.a[2 * k + 1] = v.y; }
-    out.sc = (int)__double_as_longlong(rec[5].x);
-  };
-  double growth = 1.0;  // bound on max|v| growth per layer over this thread's cached matrices
-  if constexpr (TYPED) {
-    for (int t = 0; t < prm.n_types; ++t) {
-      const int j = prm.type_layer[t];
-      const LayerEntry le = lay[j];
-      const double d = (j == prm.sweep_layer) ? d_sweep : le.d;
-      TypeRegs<NPOL> tmp;
-      if (__ldg(prm.mat_flags + le.mat) == 0) {
-        double qr, nr, inr;
-        opt_row_real(le.mat, qr, nr, inr);
-        tmp.set_real(build_real_layer<NPOL>(qr, nr, inr, d, ct, ict, prm.pol_first));
-      } else {
-        lossy_mask |= 1u << t;
-        tmp.set_cplx(build_cplx_layer<NPOL>(opt_row(le.mat), d, ct, ict, prm.pol_first));
-      }
-      growth = fmax(growth, tmp.growth_bound((lossy_mask >> t) & 1u));
-      double2* rec = reinterpret_cast<double2*>(my_types + t * kTypeRecBytes);
-#pragma unroll
-      for (int k = 0; k < 5; ++k) rec[k] = make_double2(tmp.a[2 * k], tmp.a[2 * k + 1]);
-      rec[5] = make_double2(__longlong_as_double((long long)tmp.sc), 0.0);
-    }
-  }
-
   // ---- the ordered chain over this thread's segment of interior layers
   const int Li = L - 2;
   const int seg = SEG ? threadIdx.y : 0;
@@ -263,50 +239,7 @@ tmm_chain_kernel(const GridParams prm) {
   if constexpr (SEG) init_identity<NPOL>(st);
   else init_exit_columns<NPOL, NC>(st, exit_row.nr, exit_row.ni, ct, prm.pol_first);
 
-  if constexpr (TYPED) {
-    // run-length ops (host: sync_layers): apply (A, B) k times, or A alone when b < 0
-    // Rescaling interval from the growth bound: after a rescale max|v| < 2, and n layers multiply it by at most
-    // growth^n, so n <= 900 / log2(growth) layers cannot overflow.  The interval is made warp-uniform (minimum over
-    // the lanes) because it sets loop trip counts.  Ordinary mirrors need no rescale inside the chain at all.
-    const int lg = exponent_of(growth) + 1;  // >= log2(growth)
-    const int every = max(2, min(1024, (int)__reduce_min_sync(0xffffffffu, (unsigned)(900 / max(lg, 1)))) & ~1);
-    int since = 0;
-    for (int op = 0; op < prm.n_ops; ++op) {
-      const int4 o = __ldg(prm.ops + op);
-      TypeRegs<NPOL> A, B;
-      load_type(o.x, A);
-      const bool la = (lossy_mask >> o.x) & 1u;
-      if (o.y < 0) {
-        for (int k = 0; k < o.z; ++k) {
-          apply_type<NPOL, NC>(st, A, la);
-          if (++since >= every) { renormalise<NPOL, NC>(st); since = 0; }
-        }
-        continue;
-      }
-      load_type(o.y, B);
-      const bool lb = (lossy_mask >> o.y) & 1u;
-      if (!la && !lb && o.z >= 3 && !(prm.flags & 128u)) {
-        // a lossless pair repeated k times: closed-form power of the period (Chebyshev identity, pst_chain.cuh)
-        if (since > 0) renormalise<NPOL, NC>(st);
-        apply_pair_power<NPOL, NC>(st, A, B, o.z);
-        renormalise<NPOL, NC>(st);
-        since = 0;
-        continue;
-      }
-      int k = o.z;
-      while (k > 0) {
-        const int n = min(k, max((every - since) / 2, 1));
-        if (!la && !lb) pair_loop<NPOL, NC, false, false>(st, A, B, n);
-        else if (!la) pair_loop<NPOL, NC, false, true>(st, A, B, n);
-        else if (!lb) pair_loop<NPOL, NC, true, false>(st, A, B, n);
-        else pair_loop<NPOL, NC, true, true>(st, A, B, n);
-        k -= n;
-        since += 2 * n;
-        if (since >= every) { renormalise<NPOL, NC>(st); since = 0; }
-      }
-    }
-    renormalise<NPOL, NC>(st);
-  } else {
+  {
     int j = j_hi - 1;
     while (j >= j_lo) {
       const int j_stop = max(j - kRenormEvery, j_lo - 1);
@@ -396,6 +329,151 @@ tmm_chain_kernel(const GridParams prm) {
     const PointOut r = finish_point<NPOL, NCOL>(fin, pp, in_row.inr, in_row.ini, exit_row.nr, exit_row.ni, ict,
                                                 prm.pol_first, prm.flags);
     const size_t o = ((size_t)sweep * NPOL + pp) * plane + (size_t)p;
+    if (prm.R) prm.R[o] = r.R;
+    if (prm.T) prm.T[o] = r.T;
+    if (prm.A) prm.A[o] = r.A;
+    if constexpr (NCOL == 2) {
+      if (prm.M) {
+        double4* mo = reinterpret_cast<double4*>(prm.M + o * 8);
+        mo[0] = make_double4(r.M[0], r.M[1], r.M[2], r.M[3]);
+        mo[1] = make_double4(r.M[4], r.M[5], r.M[6], r.M[7]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ K1 typed (layer CSE)
+// Layers with identical (material, thickness) share one layer matrix -- pure common-subexpression elimination: the
+// applied matrices are bit-identical to the untyped path's.  Every distinct matrix is built once per thread into a
+// thread-private shared-memory record; the host compiles the layer sequence into run-length ops "apply (A, B) k
+// times" (periodic stacks: quarter-wave mirrors); the op loop keeps A and B in registers, and a lossless pair
+// repeated k >= 3 times is applied as the closed-form power of its period (pst_chain.cuh).
+// The whole program (types, ops) arrives by value in the constant bank and the 48-byte optical rows are read straight
+// through the read-only path (a warp shares its wavelength, so they are broadcast loads, prefetched one type ahead):
+// no staging, no barrier, no global load on the dependent path.  (History in profiles/: v2 read the cached matrix
+// from shared memory per layer and was LSU-bound; a per-layer switch over register-resident types was latency-bound;
+// v7 staged tables with a bulk copy and fetched ops/flags from global memory -- 18 % of its stall samples.)
+template <int NPOL, int NCOL>
+__global__ void __launch_bounds__(128)
+tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NC = NCOL;
+  const unsigned npts = (unsigned)prm.points, nth = (unsigned)prm.n_theta;
+  const unsigned praw = blockIdx.x * 128u + threadIdx.x;
+  const bool valid = praw < npts;
+  const unsigned p = valid ? praw : npts - 1u;  // tail lanes shadow the last point (warp-wide reductions below)
+  const int il_loc = (int)(p / nth);
+  const int it = (int)(p - (unsigned)il_loc * nth);
+  const int il = prm.il0 + il_loc;
+  const double2 tr = __ldg(prm.trig + it);
+  const unsigned lossy_mask = __ldg(tp.lossy_types);
+  const double d_sweep = prm.sweep_d ? __ldg(prm.sweep_d + blockIdx.y) : 0.0;
+  const double ct = tr.x, ict = tr.y;
+  const double2* optp = reinterpret_cast<const double2*>(prm.opt + (size_t)il * prm.n_mat * 6);  // rows of 3 double2
+  const double2 ex0 = __ldg(optp + tp.mat_last * 3), ex1 = __ldg(optp + tp.mat_last * 3 + 1);
+  const double nfr = ex0.y, nfi = ex1.y;
+
+  // ---- build each distinct layer matrix once
+  unsigned char* my_types = smem_raw + (size_t)threadIdx.x * tp.type_stride;
+  unsigned m_hi = 0;
+  {
+    const double2* row = optp + tp.type_mat[0] * 3;
+    double2 ra = __ldg(row), rb = __ldg(row + 1), rc = __ldg(row + 2);
+    for (int t = 0; t < tp.n_types; ++t) {
+      const double2 a = ra, b = rb, c = rc;
+      if (t + 1 < tp.n_types) {  // next type's row is in flight while this one is built
+        row = optp + tp.type_mat[t + 1] * 3;
+        ra = __ldg(row); rb = __ldg(row + 1); rc = __ldg(row + 2);
+      }
+      const double d = (t == tp.sweep_type) ? d_sweep : tp.type_d[t];
+      const bool lossy = (lossy_mask >> t) & 1u;
+      TypeRegs<NPOL> tmp;
+      if (!lossy) {
+        tmp.set_real(build_real_layer<NPOL>(a.x, a.y, b.x, d, ct, ict, prm.pol_first));
+      } else {
+        OptRow o;
+        o.qr = a.x; o.nr = a.y; o.inr = b.x; o.ni = b.y; o.qi = c.x; o.ini = c.y;
+        tmp.set_cplx(build_cplx_layer<NPOL>(o, d, ct, ict, prm.pol_first));
+      }
+      const unsigned h = tmp.max_hi(lossy);
+      m_hi = h > m_hi ? h : m_hi;
+      double2* rec = reinterpret_cast<double2*>(my_types + t * kTypeRecBytes);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) rec[k] = make_double2(tmp.a[2 * k], tmp.a[2 * k + 1]);
+      rec[5] = make_double2(__longlong_as_double((long long)tmp.sc), 0.0);
+    }
+  }
+  auto load_type = [&](int t, TypeRegs<NPOL>& out) {
+    const double2* rec = reinterpret_cast<const double2*>(my_types + t * kTypeRecBytes);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { const double2 v = rec[k]; out.a[2 * k] = v.x; out.a[2 * k + 1] = v.y; }
+    out.sc = (int)__double_as_longlong(rec[5].x);
+  };
+
+  // Rescaling interval from the growth bound: after a rescale max|v| < 2 and n layers multiply it by at most G^n,
+  // so n <= 900 / log2 G layers cannot overflow.  Warp-uniform (maximum over the lanes): it sets loop trip counts.
+  // Ordinary mirrors need no rescale inside the chain at all.
+  const int lg = growth_log2(__reduce_max_sync(0xffffffffu, m_hi), lossy_mask != 0);
+  const int every = max(2, min(1024, 900 / lg)) & ~1;
+
+  ChainState<NPOL, NC> st;
+  init_exit_columns<NPOL, NC>(st, nfr, nfi, ct, prm.pol_first);
+  PairPower<NPOL> S;
+#pragma unroll
+  for (int pp = 0; pp < NPOL; ++pp) { S.sa[pp] = 1.0; S.sb[pp] = 0.0; S.ks[pp] = 0; }
+  int s_lo = -1, s_hi = -1, s_k = -1;  // the period S belongs to
+  int since = 0;                      // layers applied since the last rescale
+  for (int op = 0; op < tp.n_ops; ++op) {
+    const int4 o = tp.ops[op];
+    TypeRegs<NPOL> A, B;
+    load_type(o.x, A);
+    const bool la = (lossy_mask >> o.x) & 1u;
+    if (o.y < 0) {
+      for (int k = 0; k < o.z; ++k) {
+        apply_type<NPOL, NC>(st, A, la);
+        if (++since >= every) { renormalise<NPOL, NC>(st); since = 0; }
+      }
+      continue;
+    }
+    load_type(o.y, B);
+    const bool lb = (lossy_mask >> o.y) & 1u;
+    if (!la && !lb && o.z >= 3 && !(prm.flags & 128u)) {
+      // a lossless pair repeated k times: closed-form power of the period (Chebyshev identity, pst_chain.cuh).
+      // |U^k entries| <= 2 (2 G^2)^32 G^2 after the recurrence's own rescaling; rescale first only if that times the
+      // current bound 2 G^since could leave the fp64 range
+      if (since * lg + 66 * lg + 40 > 1000) renormalise<NPOL, NC>(st);
+      const int t_lo = min(o.x, o.y), t_hi = max(o.x, o.y);
+      if (t_lo != s_lo || t_hi != s_hi || o.z != s_k) {  // else: same or mirrored period, same trace, same S
+        pair_power_coeffs<NPOL>(A, B, o.z, S);
+        s_lo = t_lo; s_hi = t_hi; s_k = o.z;
+      }
+      apply_pair_power<NPOL, NC>(st, A, B, S);
+      renormalise<NPOL, NC>(st);
+      since = 0;
+      continue;
+    }
+    int k = o.z;
+    while (k > 0) {
+      const int n = min(k, max((every - since) / 2, 1));
+      if (!la && !lb) pair_loop<NPOL, NC, false, false>(st, A, B, n);
+      else if (!la) pair_loop<NPOL, NC, false, true>(st, A, B, n);
+      else if (!lb) pair_loop<NPOL, NC, true, false>(st, A, B, n);
+      else pair_loop<NPOL, NC, true, true>(st, A, B, n);
+      k -= n;
+      since += 2 * n;
+      if (since >= every) { renormalise<NPOL, NC>(st); since = 0; }
+    }
+  }
+  if (since > 0) renormalise<NPOL, NC>(st);
+  if (!valid) return;
+
+  // ---- epilogue
+  const double2 in1 = __ldg(optp + tp.mat_first * 3 + 1), in2 = __ldg(optp + tp.mat_first * 3 + 2);
+  const size_t plane = (size_t)prm.points;
+#pragma unroll
+  for (int pp = 0; pp < NPOL; ++pp) {
+    const PointOut r = finish_point<NPOL, NCOL>(st, pp, in1.x, in2.y, nfr, nfi, ict, prm.pol_first, prm.flags);
+    const size_t o = ((size_t)blockIdx.y * NPOL + pp) * plane + (size_t)p;
     if (prm.R) prm.R[o] = r.R;
     if (prm.T) prm.T[o] = r.T;
     if (prm.A) prm.A[o] = r.A;
@@ -521,7 +599,7 @@ tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
       const double num = fma(m10.re, m10.re, m10.im * m10.im);
       const double iden = 1.0 / den;
       const double R = num * iden;
-      const double T = scale2(det_re * iden, -2 * (u.kexp[pp] + pre.kexp[pp]));
+      const double T = scale_sq(det_re * iden, -(u.kexp[pp] + pre.kexp[pp]));
       const size_t o = ((size_t)sw * NPOL + pp) * plane + (size_t)p;
       if (prm.R) __stcs(prm.R + o, R);
       if (prm.T) __stcs(prm.T + o, T);
