@@ -197,10 +197,10 @@ ChainKernel pick_chain(int npol, int ncol, bool so, bool sl, bool seg) {
 
 using TypedKernel = void (*)(const GridParams, const TypedPlan);
 TypedKernel pick_typed(int npol, int ncol) {
-  if (npol == 1 && ncol == 1) return tmm_typed_kernel<1, 1>;
-  if (npol == 1 && ncol == 2) return tmm_typed_kernel<1, 2>;
-  if (npol == 2 && ncol == 1) return tmm_typed_kernel<2, 1>;
-  if (npol == 2 && ncol == 2) return tmm_typed_kernel<2, 2>;
+  if (npol == 1 && ncol == 1) return tmm_typed_kernel<1, 1, 5>;
+  if (npol == 1 && ncol == 2) return tmm_typed_kernel<1, 2, 4>;
+  if (npol == 2 && ncol == 1) return tmm_typed_kernel<2, 1, 5>;  // 96 registers; 6 blocks/SM (80) spills and gains < 1 %
+  if (npol == 2 && ncol == 2) return tmm_typed_kernel<2, 2, 3>;
   return nullptr;
 }
 
@@ -369,7 +369,7 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
   pl->type_stride = 0;
   pl->fn_typed = nullptr;
   if (pl->typed) {
-    int units = h->n_types * (kTypeRecBytes / 16);
+    int units = (h->n_types * (kTypeRecBytes + 4) + 15) / 16;  // records + one exponent int per type
     if (units % 2 == 0) units += 1;
     pl->type_stride = units * 16;
     pl->so = pl->sl = false;

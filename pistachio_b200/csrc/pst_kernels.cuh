@@ -30,7 +30,8 @@ struct LayerEntry {  // 16 bytes: one LDS.128 / LDG.128 per layer
 };
 
 constexpr int kMaxTypes = 8;        // distinct (material, thickness) pairs the typed path caches per thread
-constexpr int kTypeRecBytes = 96;   // one cached layer matrix: 12 doubles (complex form) or 6 (real form)
+constexpr int kTypeRecBytes = 80;   // one cached layer matrix: 10 doubles (complex form) or 5 (real form); the
+                                    // power-of-two exponents of all types follow the records as ints
 constexpr int kRenormEvery = 16;
 constexpr int kMaxOps = 24;         // run-length ops the typed kernel takes by value (longer programs use K1 untyped)
 
@@ -353,8 +354,8 @@ tmm_chain_kernel(const GridParams prm) {
 // no staging, no barrier, no global load on the dependent path.  (History in profiles/: v2 read the cached matrix
 // from shared memory per layer and was LSU-bound; a per-layer switch over register-resident types was latency-bound;
 // v7 staged tables with a bulk copy and fetched ops/flags from global memory -- 18 % of its stall samples.)
-template <int NPOL, int NCOL>
-__global__ void __launch_bounds__(128)
+template <int NPOL, int NCOL, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NC = NCOL;
@@ -375,22 +376,21 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
 
   // ---- build each distinct layer matrix once
   unsigned char* my_types = smem_raw + (size_t)threadIdx.x * tp.type_stride;
+  int* my_sc = reinterpret_cast<int*>(my_types + tp.n_types * kTypeRecBytes);
   unsigned m_hi = 0;
   {
-    const double2* row = optp + tp.type_mat[0] * 3;
-    double2 ra = __ldg(row), rb = __ldg(row + 1), rc = __ldg(row + 2);
+    double2 ra = __ldg(optp + tp.type_mat[0] * 3);
     for (int t = 0; t < tp.n_types; ++t) {
-      const double2 a = ra, b = rb, c = rc;
-      if (t + 1 < tp.n_types) {  // next type's row is in flight while this one is built
-        row = optp + tp.type_mat[t + 1] * 3;
-        ra = __ldg(row); rb = __ldg(row + 1); rc = __ldg(row + 2);
-      }
+      const double2* row = optp + tp.type_mat[t] * 3;
+      const double2 a = ra, b = __ldg(row + 1);  // (q.re, n.re), (1/n).re, n.im): same cache line as a
+      if (t + 1 < tp.n_types) ra = __ldg(optp + tp.type_mat[t + 1] * 3);  // next type's line is in flight during the build
       const double d = (t == tp.sweep_type) ? d_sweep : tp.type_d[t];
       const bool lossy = (lossy_mask >> t) & 1u;
       TypeRegs<NPOL> tmp;
       if (!lossy) {
         tmp.set_real(build_real_layer<NPOL>(a.x, a.y, b.x, d, ct, ict, prm.pol_first));
       } else {
+        const double2 c = __ldg(row + 2);
         OptRow o;
         o.qr = a.x; o.nr = a.y; o.inr = b.x; o.ni = b.y; o.qi = c.x; o.ini = c.y;
         tmp.set_cplx(build_cplx_layer<NPOL>(o, d, ct, ict, prm.pol_first));
@@ -398,23 +398,35 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
       const unsigned h = tmp.max_hi(lossy);
       m_hi = h > m_hi ? h : m_hi;
       double2* rec = reinterpret_cast<double2*>(my_types + t * kTypeRecBytes);
+      if (!lossy) {
+        rec[0] = make_double2(tmp.a[0], tmp.a[1]);
+        rec[1] = make_double2(tmp.a[2], tmp.a[3]);
+        rec[2] = make_double2(tmp.a[4], 0.0);
+      } else {
 #pragma unroll
-      for (int k = 0; k < 5; ++k) rec[k] = make_double2(tmp.a[2 * k], tmp.a[2 * k + 1]);
-      rec[5] = make_double2(__longlong_as_double((long long)tmp.sc), 0.0);
+        for (int k = 0; k < 5; ++k) rec[k] = make_double2(tmp.a[2 * k], tmp.a[2 * k + 1]);
+        my_sc[t] = tmp.sc;
+      }
     }
   }
-  auto load_type = [&](int t, TypeRegs<NPOL>& out) {
+  auto load_type = [&](int t, bool lossy, TypeRegs<NPOL>& out) {
     const double2* rec = reinterpret_cast<const double2*>(my_types + t * kTypeRecBytes);
+    if (!lossy) {
 #pragma unroll
-    for (int k = 0; k < 5; ++k) { const double2 v = rec[k]; out.a[2 * k] = v.x; out.a[2 * k + 1] = v.y; }
-    out.sc = (int)__double_as_longlong(rec[5].x);
+      for (int k = 0; k < 3; ++k) { const double2 v = rec[k]; out.a[2 * k] = v.x; out.a[2 * k + 1] = v.y; }
+      out.sc = 0;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) { const double2 v = rec[k]; out.a[2 * k] = v.x; out.a[2 * k + 1] = v.y; }
+      out.sc = my_sc[t];
+    }
   };
 
   // Rescaling interval from the growth bound: after a rescale max|v| < 2 and n layers multiply it by at most G^n,
   // so n <= 900 / log2 G layers cannot overflow.  Warp-uniform (maximum over the lanes): it sets loop trip counts.
   // Ordinary mirrors need no rescale inside the chain at all.
   const int lg = growth_log2(__reduce_max_sync(0xffffffffu, m_hi), lossy_mask != 0);
-  const int every = max(2, min(1024, 900 / lg)) & ~1;
+  const int every = max(2, min(1024, __float2int_rz(899.5f * __frcp_rn((float)lg)))) & ~1;  // <= 900 / lg, no division
 
   ChainState<NPOL, NC> st;
   init_exit_columns<NPOL, NC>(st, nfr, nfi, ct, prm.pol_first);
@@ -426,8 +438,8 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   for (int op = 0; op < tp.n_ops; ++op) {
     const int4 o = tp.ops[op];
     TypeRegs<NPOL> A, B;
-    load_type(o.x, A);
     const bool la = (lossy_mask >> o.x) & 1u;
+    load_type(o.x, la, A);
     if (o.y < 0) {
       for (int k = 0; k < o.z; ++k) {
         apply_type<NPOL, NC>(st, A, la);
@@ -435,8 +447,8 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
       }
       continue;
     }
-    load_type(o.y, B);
     const bool lb = (lossy_mask >> o.y) & 1u;
+    load_type(o.y, lb, B);
     if (!la && !lb && o.z >= 3 && !(prm.flags & 128u)) {
       // a lossless pair repeated k times: closed-form power of the period (Chebyshev identity, pst_chain.cuh).
       // |U^k entries| <= 2 (2 G^2)^32 G^2 after the recurrence's own rescaling; rescale first only if that times the

@@ -72,29 +72,40 @@ PST_HD int exponent_of(double x) {
 
 // y = k*ln2 + r, |r| <= ln2/2:  e^{+-r} = E(r^2) +- r*O(r^2) with one shared even/odd Taylor
 // split (degree 13, truncation < 4e-18).  Returns even = E, odd = r*O; k is returned, not applied.
+#define PST_EXP_COEFS                                                                                          \
+  {1.4426950408889634, -6.93147180369123816490e-01, -1.90821492927058770002e-10, 1.0 / 479001600.0,            \
+   1.0 / 3628800.0, 1.0 / 40320.0, 1.0 / 720.0, 1.0 / 24.0, 1.0 / 6227020800.0, 1.0 / 39916800.0,             \
+   1.0 / 362880.0, 1.0 / 5040.0, 1.0 / 120.0, 1.0 / 6.0}
+// 0: log2(e); 1, 2: -ln2 split (low 21 bits of the high part are zero); 3..7: 1/12! .. 1/4!; 8..13: 1/13! .. 1/3!
+#ifdef __CUDACC__
+__constant__ double c_exp[14] = PST_EXP_COEFS;
+#endif
+static const double h_exp[14] = PST_EXP_COEFS;
+#ifdef __CUDA_ARCH__
+#define PST_EC(i) c_exp[i]
+#else
+#define PST_EC(i) h_exp[i]
+#endif
 PST_HD void exp_split(double y, double& even, double& odd, int& k) {
-  const double kLog2e = 1.4426950408889634;
-  const double kLn2Hi = 6.93147180369123816490e-01;  // split of ln2, low 21 bits of Hi are zero
-  const double kLn2Lo = 1.90821492927058770002e-10;
-  double kd = rint(y * kLog2e);
+  double kd = rint(y * PST_EC(0));
   kd = fmin(fmax(kd, -1.0e9), 1.0e9);
-  double r = fma(-kd, kLn2Hi, y);
-  r = fma(-kd, kLn2Lo, r);
+  double r = fma(kd, PST_EC(1), y);
+  r = fma(kd, PST_EC(2), r);
   k = (int)kd;
   double r2 = r * r;
-  double e = 1.0 / 479001600.0;            // 1/12!
-  e = fma(e, r2, 1.0 / 3628800.0);         // 1/10!
-  e = fma(e, r2, 1.0 / 40320.0);           // 1/8!
-  e = fma(e, r2, 1.0 / 720.0);             // 1/6!
-  e = fma(e, r2, 1.0 / 24.0);              // 1/4!
+  double e = PST_EC(3);                    // 1/12!
+  e = fma(e, r2, PST_EC(4));               // 1/10!
+  e = fma(e, r2, PST_EC(5));               // 1/8!
+  e = fma(e, r2, PST_EC(6));               // 1/6!
+  e = fma(e, r2, PST_EC(7));               // 1/4!
   e = fma(e, r2, 0.5);                     // 1/2!
   e = fma(e, r2, 1.0);
-  double o = 1.0 / 6227020800.0;           // 1/13!
-  o = fma(o, r2, 1.0 / 39916800.0);        // 1/11!
-  o = fma(o, r2, 1.0 / 362880.0);          // 1/9!
-  o = fma(o, r2, 1.0 / 5040.0);            // 1/7!
-  o = fma(o, r2, 1.0 / 120.0);             // 1/5!
-  o = fma(o, r2, 1.0 / 6.0);               // 1/3!
+  double o = PST_EC(8);                    // 1/13!
+  o = fma(o, r2, PST_EC(9));               // 1/11!
+  o = fma(o, r2, PST_EC(10));              // 1/9!
+  o = fma(o, r2, PST_EC(11));              // 1/7!
+  o = fma(o, r2, PST_EC(12));              // 1/5!
+  o = fma(o, r2, PST_EC(13));              // 1/3!
   o = fma(o, r2, 1.0);
   even = e;
   odd = r * o;
@@ -124,11 +135,14 @@ PST_HD int cosh_sinh_scaled(double y, double& ch, double& sh) {
   {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,                       \
    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,                        \
    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,                        \
-   -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11}
+   -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11,                       \
+   6.36619772367581382433e-01, -1.5707963267948966, -6.123233995736757e-17, -8.478427660368898e-32}
+// 12: 2/pi; 13..15: -(pi/2) split into three doubles (0x3ff921fb54442d18, 0x3c91a62633145c00, 0x397b839a252049c0);
+// the middle one is truncated (trailing zero bits) so that kd*mid stays exact for |kd| < 2^30
 #ifdef __CUDACC__
-__constant__ double c_sincos[12] = PST_SINCOS_COEFS;
+__constant__ double c_sincos[16] = PST_SINCOS_COEFS;
 #endif
-static const double h_sincos[12] = PST_SINCOS_COEFS;
+static const double h_sincos[16] = PST_SINCOS_COEFS;
 #ifdef __CUDA_ARCH__
 #define PST_SC(i) c_sincos[i]
 #else
@@ -155,7 +169,7 @@ PST_HD void sincos_fast(double x, double& s, double& c) {
 // straight-line part (no branches): several independent calls interleave in one basic block
 PST_HD void sincos_core(double x, double& s, double& c) {
   const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
-  const double t = fma(x, 6.36619772367581382433e-01, kMagic);
+  const double t = fma(x, PST_SC(12), kMagic);
   const double kd = t - kMagic;
   int q;
   {
@@ -167,10 +181,9 @@ PST_HD void sincos_core(double x, double& s, double& c) {
 #endif
     q = (int)u;  // low word of the magic sum = k mod 2^32
   }
-  // pi/2 = hi + mid + lo; mid is truncated (trailing zero bits) so that kd*mid stays exact for |kd| < 2^30
-  double r = fma(kd, -1.5707963267948966, x);       // 0x3ff921fb54442d18
-  r = fma(kd, -6.123233995736757e-17, r);           // 0x3c91a62633145c00
-  r = fma(kd, -8.478427660368898e-32, r);           // 0x397b839a252049c0
+  double r = fma(kd, PST_SC(13), x);  // three-term Cody-Waite
+  r = fma(kd, PST_SC(14), r);
+  r = fma(kd, PST_SC(15), r);
   const double z = r * r;
   double ps = fma(PST_SC(5), z, PST_SC(4));
   double pc = fma(PST_SC(11), z, PST_SC(10));
