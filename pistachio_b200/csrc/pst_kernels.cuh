@@ -168,7 +168,7 @@ __global__ void prep_trig_kernel(const double* __restrict__ theta, const double*
 //   STAGE_OPT / STAGE_LAYERS  optical table window and layer list staged in shared memory once per block
 //   SEG    blockDim.y ordered layer segments per point, combined in order through shared memory (deep stacks)
 template <int NPOL, int NCOL, bool STAGE_OPT, bool STAGE_LAYERS, bool SEG>
-__global__ void __launch_bounds__(SEG ? 512 : 256)
+__global__ void __launch_bounds__(SEG ? 512 : 256, (SEG && NPOL == 1) ? 2 : 1)  // deep-stack kernel: 64 registers, 8 x 128-thread blocks per SM
 tmm_chain_kernel(const GridParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NC = SEG ? 2 : NCOL;  // a segment product needs both columns
@@ -507,7 +507,7 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
 // and each thickness costs one layer-matrix build (shared by both polarisations), one layer step and two 2-vector
 // dot products per polarisation.  Results of one chunk iteration are 32 consecutive doubles per warp and array.
 template <int NPOL, bool STAGE_OPT, bool STAGE_LAYERS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int PB = blockDim.x;
@@ -593,25 +593,60 @@ tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
   const OptRow srow = opt_row(ls.mat);
   const bool s_lossless = lossy_of(ls) == 0;
 
+  // The swept layer is M_s = cos(phi) I + sin(phi) J with J = [[0, -i/a], [-i a, 0]], and a = n g does not depend on
+  // the thickness.  With u the suffix vector and r0, r1 the prefix rows,
+  //   M00 = r0 . (M_s u) = cos(phi) al0 + sin(phi) be0,   al0 = r0 . u,  be0 = r0 . (J u)      (M10 likewise with r1)
+  // so one thickness costs one complex sincos (shared by both polarisations) and two 2-term complex sums per
+  // polarisation; al, be are per-thread constants of the sweep.
+  cplx al0[NPOL], be0[NPOL], al1[NPOL], be1[NPOL];
+  int kfix[NPOL];
+#pragma unroll
+  for (int pp = 0; pp < NPOL; ++pp) {
+    const bool is_s = pol_is_s<NPOL>(pp, prm.pol_first);
+    const double g = is_s ? ct : ict, gi = is_s ? ict : ct;
+    const cplx u0 = {suf.v[pp][0][0], suf.v[pp][0][1]}, u1 = {suf.v[pp][0][2], suf.v[pp][0][3]};
+    const cplx a = {srow.nr * g, srow.ni * g}, ia = {srow.inr * gi, srow.ini * gi};
+    const cplx t0 = cmul(ia, u1), t1 = cmul(a, u0);
+    const cplx w0 = {t0.im, -t0.re}, w1 = {t1.im, -t1.re};  // J u = (-i u1 / a, -i a u0)
+    al0[pp] = cadd(cmul(r0[pp][0], u0), cmul(r0[pp][1], u1));
+    al1[pp] = cadd(cmul(r1[pp][0], u0), cmul(r1[pp][1], u1));
+    be0[pp] = cadd(cmul(r0[pp][0], w0), cmul(r0[pp][1], w1));
+    be1[pp] = cadd(cmul(r1[pp][0], w0), cmul(r1[pp][1], w1));
+    kfix[pp] = suf.kexp[pp] + pre.kexp[pp];
+  }
+  const double qcr = mul_rn(srow.qr, ct), qci = mul_rn(srow.qi, ct);  // first rounding of layer_phase()
+
   // ---- the sweep loop
   const int s_begin = blockIdx.y * sweeps_per_block;
   const int s_end = min(s_begin + sweeps_per_block, n_sweep);
   const size_t plane = (size_t)prm.points;
   for (int sw = s_begin; sw < s_end; ++sw) {
     const double d = __ldg(prm.sweep_d + sw);
-    ChainState<NPOL, 1> u = suf;
-    if (s_lossless) apply_real_layer<NPOL, 1>(u, build_real_layer<NPOL>(srow.qr, srow.nr, srow.inr, d, ct, ict, prm.pol_first));
-    else apply_cplx_layer<NPOL, 1>(u, build_cplx_layer<NPOL>(srow, d, ct, ict, prm.pol_first));
+    double sx, cx;
+    sincos_fast(mul_rn(qcr, d), sx, cx);
+    cplx cphi = {cx, 0.0}, sphi = {sx, 0.0};
+    int sc = 0;
+    if (!s_lossless) {
+      double ch, sh;
+      sc = cosh_sinh_scaled(mul_rn(qci, d), ch, sh);  // cos, sin of (x + i y), both times 2^sc
+      cphi = {cx * ch, -(sx * sh)};
+      sphi = {sx * ch, cx * sh};
+    }
 #pragma unroll
     for (int pp = 0; pp < NPOL; ++pp) {
-      const cplx u0 = {u.v[pp][0][0], u.v[pp][0][1]}, u1 = {u.v[pp][0][2], u.v[pp][0][3]};
-      const cplx m00 = cadd(cmul(r0[pp][0], u0), cmul(r0[pp][1], u1));
-      const cplx m10 = cadd(cmul(r1[pp][0], u0), cmul(r1[pp][1], u1));
+      cplx m00, m10;
+      if (s_lossless) {
+        m00 = {fma(cx, al0[pp].re, sx * be0[pp].re), fma(cx, al0[pp].im, sx * be0[pp].im)};
+        m10 = {fma(cx, al1[pp].re, sx * be1[pp].re), fma(cx, al1[pp].im, sx * be1[pp].im)};
+      } else {
+        m00 = cadd(cmul(cphi, al0[pp]), cmul(sphi, be0[pp]));
+        m10 = cadd(cmul(cphi, al1[pp]), cmul(sphi, be1[pp]));
+      }
       const double den = fma(m00.re, m00.re, m00.im * m00.im);
       const double num = fma(m10.re, m10.re, m10.im * m10.im);
       const double iden = 1.0 / den;
       const double R = num * iden;
-      const double T = scale_sq(det_re * iden, -(u.kexp[pp] + pre.kexp[pp]));
+      const double T = scale_sq(det_re * iden, -(kfix[pp] + sc));
       const size_t o = ((size_t)sw * NPOL + pp) * plane + (size_t)p;
       if (prm.R) __stcs(prm.R + o, R);
       if (prm.T) __stcs(prm.T + o, T);
