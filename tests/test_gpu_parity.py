@@ -115,6 +115,44 @@ def test_fuzz_stacks(eng, ref_cases):
     assert loose <= 0.05 * total
 
 
+def test_fuzz_1000_random_stacks_against_live_oracle(eng):
+    """SURVEY.md section 8d fuzz recipe at full count: 1000 seeded random stacks (L in [2, 64], n in U[1, 4], kappa = 0
+    w.p. 1/2 else 10^U[-4, 1], d/lambda in U[0, 5], theta in U[0, 1.5], both polarisations, 16 wavelengths each) against
+    the oracle evaluated on the same box.  The conditioning clause is only computed for stacks that need it."""
+    rng = np.random.default_rng(1)
+    total = loose = 0
+    worst = 0.0
+    for i in range(1000):
+        L = int(rng.integers(2, 65))
+        wl = np.sort(rng.uniform(0.4, 2.0, 16))
+        nr = rng.uniform(1.0, 4.0, (L, 1)) * np.ones((1, 16))
+        kap = np.where(rng.random(L) < 0.5, 10.0 ** rng.uniform(-4, 1, L), 0.0)[:, None] * np.ones((1, 16))
+        n = nr + 1j * kap
+        n[0] = n[0].real
+        d = rng.uniform(0.0, 5.0, L) * wl.mean() / nr[:, 0]
+        att = 2 * np.pi * kap[:, 0] * d / wl.min()  # keep the reference finite: bound the attenuation exponent
+        d = np.where(att > 30.0, d * 30.0 / np.maximum(att, 1e-300), d)
+        th = rng.uniform(0.0, 1.5, 1)
+        res = eng.eval_grid(wl, th, n.real, n.imag, list(range(L)), list(d), POLS, cos_theta=np.cos(th))
+        out = res.numpy()
+        with np.errstate(all="ignore"):
+            T0, R0, M0 = parity.oracle_grid(wl, list(n), list(d), th, want_m=True)
+        fin = np.isfinite(T0) & np.isfinite(R0)
+        tol_R = 1e-12 * np.maximum(np.abs(R0), 1e-3)
+        tol_T = 1e-12 * np.maximum(np.abs(T0), 1e-3)
+        dR, dT = np.abs(out["R"][0] - R0), np.abs(out["T"][0] - T0)
+        total += 2 * int(fin.sum())
+        if np.all(dR[fin] <= tol_R[fin]) and np.all(dT[fin] <= tol_T[fin]):
+            worst = max(worst, float((dR[fin] / tol_R[fin]).max(initial=0)), float((dT[fin] / tol_T[fin]).max(initial=0)))
+            assert np.isfinite(out["R"][0][fin]).all() and np.isfinite(out["T"][0][fin]).all()
+            continue
+        rep = parity.compare_grid(f"fuzz1000/{i}", out["T"][0], out["R"][0], wl, list(n), list(d), th, got_A=out["A"][0])
+        assert rep.n_fail == 0, (rep.summary(), rep.worst)
+        loose += rep.n_loose
+    print(f"fuzz1000: {total} values, {loose} needed the conditioning clause, worst tight ratio elsewhere {worst:.3f}")
+    assert loose <= 0.02 * total
+
+
 def test_single_polarisation_and_device_cos(eng, ref_cases):
     c = ref_cases["c2_sub"]
     both = run_case(eng, c)
