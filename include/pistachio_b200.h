@@ -54,6 +54,12 @@ extern "C" {
                                                  the closed-form power of its period U^k = S_{k-1} U - S_{k-2} I
                                                  (Chebyshev identity); both agree to rounding -- ablation */
 #define PST_FLAG_NO_BULK_COPY (1u << 6)       /* stage tables with plain 128-bit loads instead of cp.async.bulk (ablation) */
+#define PST_FLAG_MULTICAST_OUT (1u << 8)       /* R, T, A are addresses inside an NVLink multicast mapping (CUDA multicast
+                                                 object, e.g. torch symmetric memory's multicast_ptr, offset to this
+                                                 rank's slab): results are written with multimem.st and land on every
+                                                 GPU of the mapping -- a sharded sweep is assembled on all devices
+                                                 without an all-gather.  The caller synchronises the devices afterwards.
+                                                 Not valid with M or with pst_eval_grid_host */
 #define PST_FLAG_NO_LAYER_CSE (1u << 4)       /* rebuild the matrix of every layer even when layers repeat (ablation;
                                                  results are bit-identical with and without) */
 

@@ -224,6 +224,7 @@ int validate_grid(const pst_grid_args* a, const char* who) {
   }
   if ((a->flags & PST_FLAG_FORCE_POINT_KERNEL) && (a->flags & PST_FLAG_FORCE_DEEP_KERNEL))
     return fail(PST_E_INVALID, w + ": contradictory kernel flags");
+  if ((a->flags & PST_FLAG_MULTICAST_OUT) && a->M) return fail(PST_E_INVALID, w + ": PST_FLAG_MULTICAST_OUT does not cover the matrix output M");
   if ((a->flags & PST_FLAG_NUMERIC_DET) && !a->M) return fail(PST_E_INVALID, w + ": PST_FLAG_NUMERIC_DET needs the matrix output M");
   for (int j = 0; j < a->n_layers; ++j)
     if (a->layer_mat[j] < 0 || a->layer_mat[j] >= a->n_mat) return fail(PST_E_INVALID, w + ": layer_mat entry out of range");
@@ -542,6 +543,7 @@ extern "C" int pst_eval_grid(pst_handle_t h, const pst_grid_args* a, void* strea
 extern "C" int pst_eval_grid_host(pst_handle_t h, const pst_grid_args* a) {
   if (!h) return fail(PST_E_INVALID, "pst_eval_grid_host: NULL handle");
   PST_TRY(validate_grid(a, "pst_eval_grid_host"));
+  if (a->flags & PST_FLAG_MULTICAST_OUT) return fail(PST_E_INVALID, "pst_eval_grid_host: PST_FLAG_MULTICAST_OUT needs device (multicast) output pointers");
   DeviceGuard g(h->device);
   if (!g.ok) return fail(PST_E_CUDA, "pst_eval_grid_host: cudaSetDevice failed");
   if (!h->s_compute) {

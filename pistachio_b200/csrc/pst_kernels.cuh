@@ -56,6 +56,22 @@ struct GridParams {
   double* M;
 };
 
+// Result stores.  PST_FLAG_MULTICAST_OUT (bit 8): R, T, A are addresses in an NVLink multicast mapping (CUDA multicast
+// object; torch symmetric memory's multicast_ptr) and every value is written once with multimem.st -- the NVSwitch
+// replicates it into the same offset of every GPU bound to the mapping, so a sharded sweep leaves the ASSEMBLED
+// arrays on all devices without a separate all-gather pass (pistachio_b200/dist.py: AssembledResult).
+constexpr unsigned kFlagMulticastOut = 1u << 8;
+template <bool STREAMING>
+__device__ __forceinline__ void store_result(double* p, double v, bool multicast) {
+  if (multicast) {
+    asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+  } else if (STREAMING) {
+    __stcs(p, v);
+  } else {
+    *p = v;
+  }
+}
+
 // The typed kernel's program, passed BY VALUE (constant bank): nothing on its dependent path is a global load.
 struct TypedPlan {
   int n_types, n_ops;
@@ -330,9 +346,10 @@ tmm_chain_kernel(const GridParams prm) {
     const PointOut r = finish_point<NPOL, NCOL>(fin, pp, in_row.inr, in_row.ini, exit_row.nr, exit_row.ni, ict,
                                                 prm.pol_first, prm.flags);
     const size_t o = ((size_t)sweep * NPOL + pp) * plane + (size_t)p;
-    if (prm.R) prm.R[o] = r.R;
-    if (prm.T) prm.T[o] = r.T;
-    if (prm.A) prm.A[o] = r.A;
+    const bool mc = prm.flags & kFlagMulticastOut;
+    if (prm.R) store_result<false>(prm.R + o, r.R, mc);
+    if (prm.T) store_result<false>(prm.T + o, r.T, mc);
+    if (prm.A) store_result<false>(prm.A + o, r.A, mc);
     if constexpr (NCOL == 2) {
       if (prm.M) {
         double4* mo = reinterpret_cast<double4*>(prm.M + o * 8);
@@ -486,9 +503,10 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   for (int pp = 0; pp < NPOL; ++pp) {
     const PointOut r = finish_point<NPOL, NCOL>(st, pp, in1.x, in2.y, nfr, nfi, ict, prm.pol_first, prm.flags);
     const size_t o = ((size_t)blockIdx.y * NPOL + pp) * plane + (size_t)p;
-    if (prm.R) prm.R[o] = r.R;
-    if (prm.T) prm.T[o] = r.T;
-    if (prm.A) prm.A[o] = r.A;
+    const bool mc = prm.flags & kFlagMulticastOut;
+    if (prm.R) store_result<false>(prm.R + o, r.R, mc);
+    if (prm.T) store_result<false>(prm.T + o, r.T, mc);
+    if (prm.A) store_result<false>(prm.A + o, r.A, mc);
     if constexpr (NCOL == 2) {
       if (prm.M) {
         double4* mo = reinterpret_cast<double4*>(prm.M + o * 8);
@@ -620,6 +638,7 @@ tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
   const int s_begin = blockIdx.y * sweeps_per_block;
   const int s_end = min(s_begin + sweeps_per_block, n_sweep);
   const size_t plane = (size_t)prm.points;
+  const bool mc = prm.flags & kFlagMulticastOut;
   for (int sw = s_begin; sw < s_end; ++sw) {
     const double d = __ldg(prm.sweep_d + sw);
     double sx, cx;
@@ -648,9 +667,9 @@ tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
       const double R = num * iden;
       const double T = scale_sq(det_re * iden, -(kfix[pp] + sc));
       const size_t o = ((size_t)sw * NPOL + pp) * plane + (size_t)p;
-      if (prm.R) __stcs(prm.R + o, R);
-      if (prm.T) __stcs(prm.T + o, T);
-      if (prm.A) __stcs(prm.A + o, (1.0 - R) - T);
+      if (prm.R) store_result<true>(prm.R + o, R, mc);
+      if (prm.T) store_result<true>(prm.T + o, T, mc);
+      if (prm.A) store_result<true>(prm.A + o, (1.0 - R) - T, mc);
     }
   }
 }
@@ -837,28 +856,39 @@ __global__ void find_peaks_kernel(const double* __restrict__ y, int n_outer, int
   unsigned char keep[kPeakCap];
   int n = 0;
   bool overflow = false;
-  // ---- local maxima with plateau midpoints (streaming state machine), height filter
+  // ---- local maxima with plateau midpoints, height filter.  One-sample-at-a-time state machine (a rise opens a
+  // candidate plateau, a strict descent closes it as a peak at the plateau's midpoint; plateaus touching either end
+  // never close, as in scipy's _local_maxima_1d), fed from batches of independent loads so that the scan is
+  // bandwidth- rather than latency-bound.
   if (n_pts >= 3) {
-    const int i_max = n_pts - 1;
-    int i = 1;
-    double xm1 = at(0), xi = at(1);  // x[i-1], x[i]
-    while (i < i_max) {
-      if (xm1 < xi) {
-        int ahead = i + 1;
-        double xa = at(ahead);
-        while (ahead < i_max && xa == xi) { ++ahead; xa = at(ahead); }
-        if (xa < xi) {  // a peak: plateau [i, ahead-1], reported at its midpoint
-          if (!use_height || xi >= height) {
-            if (n < kPeakCap && n < max_peaks) { idx[n] = (i + ahead - 1) / 2; hh[n] = xi; keep[n] = 1; ++n; }
-            else overflow = true;
+    constexpr int kBatch = 16;
+    double prev = at(0);
+    bool rising = false;
+    int start = 0;
+    for (int i0 = 1; i0 < n_pts; i0 += kBatch) {
+      double buf[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) buf[k] = (i0 + k < n_pts) ? at(i0 + k) : 0.0;
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const int i = i0 + k;
+        if (i < n_pts) {
+          const double x = buf[k];
+          if (x > prev) {
+            rising = true;
+            start = i;
+          } else if (x < prev) {
+            if (rising && (!use_height || prev >= height)) {
+              if (n < kPeakCap && n < max_peaks) { idx[n] = (start + i - 1) / 2; hh[n] = prev; keep[n] = 1; ++n; }
+              else overflow = true;
+            }
+            rising = false;
+          } else if (x != prev) {
+            rising = false;  // NaN: scipy's comparisons are all false, no plateau runs through it
           }
-          i = ahead;  // resume behind the plateau (scipy: i = i_ahead, then i += 1)
-          xi = xa;
+          prev = x;
         }
       }
-      xm1 = xi;
-      ++i;
-      if (i <= i_max) xi = at(i);
     }
   }
   // ---- distance condition: from the highest peak down, a kept peak removes neighbours closer than `distance`

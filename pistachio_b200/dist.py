@@ -93,3 +93,60 @@ def allgather_result(local: torch.Tensor, axis: str, sizes, group=None) -> torch
     dist.all_gather(bufs, pad, group=group)
     full = torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
     return full.movedim(0, dim).contiguous()
+
+
+class AssembledResult:
+    """R, T, A of a sweep sharded along its slowest axis, ASSEMBLED ON EVERY GPU by the compute kernel itself.
+
+    Each array is a symmetric-memory allocation (torch.distributed._symmetric_memory: same virtual layout on every
+    rank, bound to one NVLink multicast object).  A rank passes the multicast address of its own slab to
+    `TMMEngine.eval_grid(..., out_ptrs=res.slab_ptrs(), flags=FLAG_MULTICAST_OUT)`: the kernel writes each result once
+    with multimem.st and the NVSwitch replicates it into the same offset of every GPU's copy, so the transfer overlaps
+    the arithmetic store by store and no all-gather pass follows.  `finish()` orders the devices (stream sync +
+    symmetric-memory barrier) before anyone reads `full[...]`.
+
+    Falls back (`multicast = False`) when the fabric has no multicast support: `eval_into` then computes into the local
+    slab and `finish()` runs the in-place NCCL all-gather -- same result, two passes.
+    """
+
+    def __init__(self, n_slow: int, plane_shape, rank: int, world: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        if n_slow % world:
+            raise ValueError("AssembledResult needs equal slabs (slow axis divisible by the world size)")
+        self.rank, self.world, self.per = rank, world, n_slow // world
+        self.group = group if group is not None else dist.group.WORLD
+        self.shape = (n_slow,) + tuple(plane_shape)
+        self.plane_elems = 1
+        for s in plane_shape:
+            self.plane_elems *= int(s)
+        self.full, self.handles = {}, {}
+        for k in ("R", "T", "A"):
+            t = symm.empty(self.shape, dtype=torch.float64, device=device)
+            self.full[k] = t
+            self.handles[k] = symm.rendezvous(t, self.group)
+        self.multicast = all(int(h.multicast_ptr) != 0 for h in self.handles.values())
+
+    def local_slab(self, key: str) -> torch.Tensor:
+        lo = self.rank * self.per
+        return self.full[key][lo:lo + self.per]
+
+    def slab_ptrs(self) -> dict:
+        off = self.rank * self.per * self.plane_elems * 8
+        return {k: int(h.multicast_ptr) + off for k, h in self.handles.items()}
+
+    def eval_into(self, eng, prep_slab: dict, pols, flags: int = 0):
+        """Evaluate this rank's slab (a `shard_prepared`-style dict whose sweep_d holds `per` thicknesses)."""
+        from ._cabi import FLAG_MULTICAST_OUT
+
+        if self.multicast:
+            return eng.eval_prepared(prep_slab, pols=pols, out_ptrs=self.slab_ptrs(), flags=flags | FLAG_MULTICAST_OUT)
+        return eng.eval_prepared(prep_slab, pols=pols, out={k: self.local_slab(k) for k in ("R", "T", "A")}, flags=flags)
+
+    def finish(self):
+        if self.multicast:
+            torch.cuda.current_stream().synchronize()
+            self.handles["R"].barrier()
+        else:
+            for k in ("R", "T", "A"):
+                dist.all_gather_into_tensor(self.full[k], self.local_slab(k), group=self.group)

@@ -142,7 +142,8 @@ class TMMEngine:
         return a, keep
 
     def eval_grid(self, wl, theta, mat_n, mat_k, layer_mat, layer_d, pols=(S_WAVE, P_WAVE), *, sweep_layer=-1,
-                  sweep_d=None, cos_theta=None, want=("R", "T", "A"), want_matrix=False, flags=0, out=None) -> GridResult:
+                  sweep_d=None, cos_theta=None, want=("R", "T", "A"), want_matrix=False, flags=0, out=None,
+                  out_ptrs=None) -> GridResult:
         """Fused build + chain + R/T/A for every (sweep, pol, wavelength, theta) point (pst_eval_grid).
 
         wl, theta[, cos_theta], sweep_d: 1-D float64 (host arrays are uploaded; CUDA tensors are used in place).
@@ -161,6 +162,17 @@ class TMMEngine:
         n_pol = bin(mask).count("1")
         n_sw = 1 if sw_d is None else sw_d.numel()
         shape = (n_sw, n_pol, n_wl, n_theta)
+        if out_ptrs is not None:
+            # raw device addresses for R, T, A (e.g. a slab inside an NVLink multicast mapping with
+            # PST_FLAG_MULTICAST_OUT, see dist.AssembledResult); the caller owns the memory and its extent
+            if want_matrix:
+                raise ValueError("out_ptrs does not cover the matrix output")
+            raw = tuple(C.c_void_p(int(out_ptrs[k])) if out_ptrs.get(k) else None for k in ("R", "T", "A")) + (None,)
+            a, keep = self._grid_args(_ptr(wl_d), _ptr(th_d), _ptr(n_d), _ptr(k_d), layer_mat, layer_d, pols, sweep_layer,
+                                      _ptr(sw_d), n_sw, _ptr(ct_d), flags, n_wl, n_theta, n_mat, raw)
+            check(self.lib.pst_eval_grid(self.handle.raw, C.byref(a), self._stream()), "pst_eval_grid")
+            del keep
+            return GridResult(None, None, None, None, pols_of_mask(mask))
         res = {}
         for key in ("R", "T", "A"):
             if key in want:
@@ -177,9 +189,9 @@ class TMMEngine:
             M = None if out is None else out.get("M")
             if M is None:
                 M = torch.empty(shape + (2, 2), dtype=torch.complex128, device=self.device)
+        outs = (_ptr(res["R"]), _ptr(res["T"]), _ptr(res["A"]), _ptr(M))
         a, keep = self._grid_args(_ptr(wl_d), _ptr(th_d), _ptr(n_d), _ptr(k_d), layer_mat, layer_d, pols, sweep_layer,
-                                  _ptr(sw_d), n_sw, _ptr(ct_d), flags, n_wl, n_theta, n_mat,
-                                  (_ptr(res["R"]), _ptr(res["T"]), _ptr(res["A"]), _ptr(M)))
+                                  _ptr(sw_d), n_sw, _ptr(ct_d), flags, n_wl, n_theta, n_mat, outs)
         check(self.lib.pst_eval_grid(self.handle.raw, C.byref(a), self._stream()), "pst_eval_grid")
         del keep
         return GridResult(res["R"], res["T"], res["A"], M, pols_of_mask(mask))

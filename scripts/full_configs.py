@@ -159,9 +159,31 @@ def main() -> None:
         viol = int(((full["A"][lo:lo + per] != (1.0 - full["R"][lo:lo + per]) - full["T"][lo:lo + per]).sum()).item())
         pts = n_d * 2 * 8192 * 256
         recv = 24.0 * pts * (world - 1) / world
+        # ---- the same job with the all-gather fused into the compute kernel: multicast stores into symmetric memory
+        fused = None
+        if world > 1:
+            try:
+                asm = pdist.AssembledResult(n_d, (2, 8192, 256), rank, world, eng.device)
+
+                def fused_step():
+                    asm.eval_into(eng, p, pols)
+                    asm.finish()
+
+                fused_step()
+                ms_f = timed(fused_step)
+                ident = torch.tensor([int(all(bool(torch.equal(asm.full[k], full[k])) for k in ("R", "T", "A")))], device=eng.device)
+                dist.all_reduce(ident, op=dist.ReduceOp.MIN)
+                fused = {"ms": ms_f, "points_per_s_assembled": pts / (ms_f / 1e3), "multicast": bool(asm.multicast),
+                         "recv_GBps_per_rank": recv / 1e9 / (ms_f / 1e3),
+                         "bit_identical_to_nccl_assembly_on_all_ranks": bool(ident.item()),
+                         "how": "K3 writes R, T, A with multimem.st into symmetric-memory buffers (NVSwitch multicast): no all-gather pass"}
+                del asm
+            except Exception as e:  # fabric without multicast / symmetric memory unavailable: report, keep the NCCL numbers
+                fused = {"unavailable": repr(e)[:300]}
         if rank == 0:
             print(json.dumps({
                 "config": "configs[4] box sweep, full size: 256 d x 8192 wl x 256 theta x s/p = 2^30 points", "n_gpus": world,
+                "fused_multicast_assembly": fused,
                 "points": pts, "compute_ms": ms_c, "points_per_s_compute": pts / (ms_c / 1e3),
                 "allgather_ms": ms_g, "allgather_recv_GB_per_rank": recv / 1e9,
                 "allgather_GBps_per_rank": (recv / 1e9 / (ms_g / 1e3)) if world > 1 else None,
