@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PST_ABI_VERSION 1
+#define PST_ABI_VERSION 2
 
 #define PST_OK 0
 #define PST_E_INVALID (-1)  /* bad argument */
@@ -95,6 +95,18 @@ int pst_resample_tables(pst_handle_t h, int n_tab, const int* tab_off /*[host] n
  *   Structure.calculate_all_t_r(M)                      tm.py:490-514  (t = 1/M00, r = M10/M00, R, T)
  * and the fan-out over angles Structure.angle_resolved_spectra (tm.py:597-628).
  * The reference model is kept: the same theta in every layer (no Snell refraction, tm.py:209,212,270). */
+/* Optional fan-out of the results to several GPUs by the compute kernel itself (unicast stores over NVLink into
+ * peer-mapped memory, e.g. the per-rank buffer_ptrs of a torch symmetric-memory allocation).  Entry i addresses the
+ * first element of THIS call's output block inside GPU i's array; every result is stored once per entry (the caller's
+ * own GPU is normally one of them).  See also PST_FLAG_MULTICAST_OUT for the NVSwitch-multicast variant. */
+#define PST_MAX_PEERS 8
+typedef struct pst_peer_outputs {
+  int n_peers;
+  double* R[PST_MAX_PEERS]; /* [dev, peer-mapped]; an array may be left out by setting all its entries to NULL */
+  double* T[PST_MAX_PEERS];
+  double* A[PST_MAX_PEERS];
+} pst_peer_outputs;
+
 typedef struct pst_grid_args {
   size_t struct_size; /* = sizeof(pst_grid_args) */
   int n_wl;           /* wavelengths */
@@ -118,6 +130,8 @@ typedef struct pst_grid_args {
   double* T;
   double* A;               /* A = 1 - R - T (not computed by the reference; north_star) */
   double* M;               /* [dev] or NULL: total 2x2 matrices, complex128 [n_sweep][n_pol][n_wl][n_theta][2][2] */
+  const pst_peer_outputs* peers; /* [host] or NULL.  When given, R, T, A above must be NULL: the results go to the
+                                    listed peer buffers instead (pst_eval_grid only) */
 } pst_grid_args;
 
 int pst_eval_grid(pst_handle_t h, const pst_grid_args* args, void* stream);

@@ -11,7 +11,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libpistachio_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 POL_S, POL_P = 1, 2
 FLAG_FORCE_POINT_KERNEL = 1 << 0
 FLAG_FORCE_DEEP_KERNEL = 1 << 1
@@ -25,6 +25,15 @@ FLAG_MULTICAST_OUT = 1 << 8
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
+
+
+MAX_PEERS = 8
+
+
+class PeerOutputs(C.Structure):
+    """Mirror of `pst_peer_outputs`."""
+
+    _fields_ = [("n_peers", C.c_int), ("R", C.c_void_p * MAX_PEERS), ("T", C.c_void_p * MAX_PEERS), ("A", C.c_void_p * MAX_PEERS)]
 
 
 class GridArgs(C.Structure):
@@ -52,6 +61,7 @@ class GridArgs(C.Structure):
         ("T", C.c_void_p),
         ("A", C.c_void_p),
         ("M", C.c_void_p),
+        ("peers", C.POINTER(PeerOutputs)),
     ]
 
 

@@ -214,7 +214,17 @@ int validate_grid(const pst_grid_args* a, const char* who) {
   if (a->pol_mask == 0 || (a->pol_mask & ~3u)) return fail(PST_E_INVALID, w + ": pol_mask must be PST_POL_S, PST_POL_P or both");
   if (!a->wl || !a->mat_n || !a->mat_k || !a->layer_mat || !a->layer_d) return fail(PST_E_INVALID, w + ": NULL input pointer");
   if (!a->theta && !a->cos_theta) return fail(PST_E_INVALID, w + ": theta and cos_theta are both NULL");
-  if (!a->R && !a->T && !a->A && !a->M) return fail(PST_E_INVALID, w + ": no output requested");
+  if (a->peers) {
+    const pst_peer_outputs* po = a->peers;
+    if (po->n_peers < 1 || po->n_peers > PST_MAX_PEERS) return fail(PST_E_INVALID, w + ": peers->n_peers must be 1..PST_MAX_PEERS");
+    if (a->R || a->T || a->A || a->M) return fail(PST_E_INVALID, w + ": with peers, R, T, A and M must be NULL (results go to the peer buffers)");
+    if (a->flags & PST_FLAG_MULTICAST_OUT) return fail(PST_E_INVALID, w + ": peers and PST_FLAG_MULTICAST_OUT exclude each other");
+    bool any = false;
+    for (int i = 0; i < po->n_peers; ++i) any = any || po->R[i] || po->T[i] || po->A[i];
+    if (!any) return fail(PST_E_INVALID, w + ": no output requested");
+  } else if (!a->R && !a->T && !a->A && !a->M) {
+    return fail(PST_E_INVALID, w + ": no output requested");
+  }
   if (a->sweep_layer >= 0) {
     if (a->sweep_layer < 1 || a->sweep_layer > a->n_layers - 2)
       return fail(PST_E_INVALID, w + ": sweep_layer must be an interior layer");
@@ -453,6 +463,12 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
     prm.T = T ? T + (size_t)s0 * per_sweep : nullptr;
     prm.A = A ? A + (size_t)s0 * per_sweep : nullptr;
     prm.M = M ? M + (size_t)s0 * per_sweep * 8 : nullptr;
+    prm.n_peers = a->peers ? a->peers->n_peers : 0;
+    for (int i = 0; i < prm.n_peers; ++i) {
+      prm.peer_R[i] = a->peers->R[i] ? a->peers->R[i] + (size_t)s0 * per_sweep : nullptr;
+      prm.peer_T[i] = a->peers->T[i] ? a->peers->T[i] + (size_t)s0 * per_sweep : nullptr;
+      prm.peer_A[i] = a->peers->A[i] ? a->peers->A[i] + (size_t)s0 * per_sweep : nullptr;
+    }
     dim3 grid((unsigned)nblk, (unsigned)ns), block(pl.PB, pl.W);
     if (pl.typed) pl.fn_typed<<<grid, block, pl.smem, st>>>(prm, tp);
     else pl.fn<<<grid, block, pl.smem, st>>>(prm);
@@ -501,6 +517,12 @@ int launch_sweep(pst_handle_t h, const pst_grid_args* a, int il0, int n_wl_launc
   prm.use_bulk = (a->flags & PST_FLAG_NO_BULK_COPY) ? 0 : 1;
   prm.sweep_d = sweep_d_dev;
   prm.R = R; prm.T = T; prm.A = A;
+  prm.n_peers = a->peers ? a->peers->n_peers : 0;
+  for (int i = 0; i < prm.n_peers; ++i) {
+    prm.peer_R[i] = a->peers->R[i];
+    prm.peer_T[i] = a->peers->T[i];
+    prm.peer_A[i] = a->peers->A[i];
+  }
   const size_t budget = std::min<size_t>(h->smem_optin, 200 * 1024);
   const size_t lay_bytes = (size_t)a->n_layers * sizeof(LayerEntry);
   const size_t opt_bytes = (size_t)prm.tl_rows * prm.opt_row_bytes;
@@ -544,6 +566,7 @@ extern "C" int pst_eval_grid_host(pst_handle_t h, const pst_grid_args* a) {
   if (!h) return fail(PST_E_INVALID, "pst_eval_grid_host: NULL handle");
   PST_TRY(validate_grid(a, "pst_eval_grid_host"));
   if (a->flags & PST_FLAG_MULTICAST_OUT) return fail(PST_E_INVALID, "pst_eval_grid_host: PST_FLAG_MULTICAST_OUT needs device (multicast) output pointers");
+  if (a->peers) return fail(PST_E_INVALID, "pst_eval_grid_host: peer outputs are device pointers (pst_eval_grid only)");
   DeviceGuard g(h->device);
   if (!g.ok) return fail(PST_E_CUDA, "pst_eval_grid_host: cudaSetDevice failed");
   if (!h->s_compute) {

@@ -54,6 +54,10 @@ struct GridParams {
   double* T;
   double* A;
   double* M;
+  int n_peers;              // > 0: results go to these peer-mapped buffers instead of R, T, A (pst_peer_outputs)
+  double* peer_R[8];
+  double* peer_T[8];
+  double* peer_A[8];
 };
 
 // Result stores.  PST_FLAG_MULTICAST_OUT (bit 8): R, T, A are addresses in an NVLink multicast mapping (CUDA multicast
@@ -70,6 +74,24 @@ __device__ __forceinline__ void store_result(double* p, double v, bool multicast
   } else {
     *p = v;
   }
+}
+
+// One spectral point's R, T, A to wherever the call wants them: the local arrays (plain or multicast stores) or, with
+// pst_peer_outputs, one unicast copy per listed GPU over NVLink (the pointer lists sit in the constant bank).
+template <bool STREAMING>
+__device__ __forceinline__ void store_point(const GridParams& prm, size_t o, double R, double T, double A) {
+  if (prm.n_peers > 0) {
+    for (int i = 0; i < prm.n_peers; ++i) {
+      if (prm.peer_R[i]) __stcs(prm.peer_R[i] + o, R);
+      if (prm.peer_T[i]) __stcs(prm.peer_T[i] + o, T);
+      if (prm.peer_A[i]) __stcs(prm.peer_A[i] + o, A);
+    }
+    return;
+  }
+  const bool mc = prm.flags & kFlagMulticastOut;
+  if (prm.R) store_result<STREAMING>(prm.R + o, R, mc);
+  if (prm.T) store_result<STREAMING>(prm.T + o, T, mc);
+  if (prm.A) store_result<STREAMING>(prm.A + o, A, mc);
 }
 
 // The typed kernel's program, passed BY VALUE (constant bank): nothing on its dependent path is a global load.
@@ -346,10 +368,7 @@ tmm_chain_kernel(const GridParams prm) {
     const PointOut r = finish_point<NPOL, NCOL>(fin, pp, in_row.inr, in_row.ini, exit_row.nr, exit_row.ni, ict,
                                                 prm.pol_first, prm.flags);
     const size_t o = ((size_t)sweep * NPOL + pp) * plane + (size_t)p;
-    const bool mc = prm.flags & kFlagMulticastOut;
-    if (prm.R) store_result<false>(prm.R + o, r.R, mc);
-    if (prm.T) store_result<false>(prm.T + o, r.T, mc);
-    if (prm.A) store_result<false>(prm.A + o, r.A, mc);
+    store_point<false>(prm, o, r.R, r.T, r.A);
     if constexpr (NCOL == 2) {
       if (prm.M) {
         double4* mo = reinterpret_cast<double4*>(prm.M + o * 8);
@@ -503,10 +522,7 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   for (int pp = 0; pp < NPOL; ++pp) {
     const PointOut r = finish_point<NPOL, NCOL>(st, pp, in1.x, in2.y, nfr, nfi, ict, prm.pol_first, prm.flags);
     const size_t o = ((size_t)blockIdx.y * NPOL + pp) * plane + (size_t)p;
-    const bool mc = prm.flags & kFlagMulticastOut;
-    if (prm.R) store_result<false>(prm.R + o, r.R, mc);
-    if (prm.T) store_result<false>(prm.T + o, r.T, mc);
-    if (prm.A) store_result<false>(prm.A + o, r.A, mc);
+    store_point<false>(prm, o, r.R, r.T, r.A);
     if constexpr (NCOL == 2) {
       if (prm.M) {
         double4* mo = reinterpret_cast<double4*>(prm.M + o * 8);
@@ -638,7 +654,6 @@ tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
   const int s_begin = blockIdx.y * sweeps_per_block;
   const int s_end = min(s_begin + sweeps_per_block, n_sweep);
   const size_t plane = (size_t)prm.points;
-  const bool mc = prm.flags & kFlagMulticastOut;
   for (int sw = s_begin; sw < s_end; ++sw) {
     const double d = __ldg(prm.sweep_d + sw);
     double sx, cx;
@@ -667,9 +682,7 @@ tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
       const double R = num * iden;
       const double T = scale_sq(det_re * iden, -(kfix[pp] + sc));
       const size_t o = ((size_t)sw * NPOL + pp) * plane + (size_t)p;
-      if (prm.R) store_result<true>(prm.R + o, R, mc);
-      if (prm.T) store_result<true>(prm.T + o, T, mc);
-      if (prm.A) store_result<true>(prm.A + o, (1.0 - R) - T, mc);
+      store_point<true>(prm, o, R, T, (1.0 - R) - T);
     }
   }
 }

@@ -98,22 +98,26 @@ def allgather_result(local: torch.Tensor, axis: str, sizes, group=None) -> torch
 class AssembledResult:
     """R, T, A of a sweep sharded along its slowest axis, ASSEMBLED ON EVERY GPU by the compute kernel itself.
 
-    Each array is a symmetric-memory allocation (torch.distributed._symmetric_memory: same virtual layout on every
-    rank, bound to one NVLink multicast object).  A rank passes the multicast address of its own slab to
-    `TMMEngine.eval_grid(..., out_ptrs=res.slab_ptrs(), flags=FLAG_MULTICAST_OUT)`: the kernel writes each result once
-    with multimem.st and the NVSwitch replicates it into the same offset of every GPU's copy, so the transfer overlaps
-    the arithmetic store by store and no all-gather pass follows.  `finish()` orders the devices (stream sync +
-    symmetric-memory barrier) before anyone reads `full[...]`.
+    Each array is a symmetric-memory allocation (torch.distributed._symmetric_memory: same layout on every rank,
+    peer-mapped, bound to one NVLink multicast object).  The compute kernel writes every result straight into all
+    GPUs' copies, so the transfer overlaps the arithmetic store by store and no all-gather pass follows:
 
-    Falls back (`multicast = False`) when the fabric has no multicast support: `eval_into` then computes into the local
-    slab and `finish()` runs the in-place NCCL all-gather -- same result, two passes.
+      mode "unicast"    one store per receiving GPU through the peer-mapped addresses (pst_peer_outputs);
+                        per-GPU link traffic (N-1)/N of the array in each direction
+      mode "multicast"  one multimem.st per result (PST_FLAG_MULTICAST_OUT); the NVSwitch replicates it -- the sender's own
+                        copy comes back through the switch as well, so every GPU receives the WHOLE array
+      mode "nccl"       compute into the local slab, then the in-place NCCL all-gather (two passes; the baseline)
+
+    `finish()` orders the devices (stream sync + symmetric-memory barrier) before anyone reads `full[...]`.
     """
 
-    def __init__(self, n_slow: int, plane_shape, rank: int, world: int, device, group=None):
+    def __init__(self, n_slow: int, plane_shape, rank: int, world: int, device, group=None, mode: str = "unicast"):
         import torch.distributed._symmetric_memory as symm
 
         if n_slow % world:
             raise ValueError("AssembledResult needs equal slabs (slow axis divisible by the world size)")
+        if mode not in ("unicast", "multicast", "nccl"):
+            raise ValueError("mode must be 'unicast', 'multicast' or 'nccl'")
         self.rank, self.world, self.per = rank, world, n_slow // world
         self.group = group if group is not None else dist.group.WORLD
         self.shape = (n_slow,) + tuple(plane_shape)
@@ -125,28 +129,41 @@ class AssembledResult:
             t = symm.empty(self.shape, dtype=torch.float64, device=device)
             self.full[k] = t
             self.handles[k] = symm.rendezvous(t, self.group)
-        self.multicast = all(int(h.multicast_ptr) != 0 for h in self.handles.values())
+        if mode == "multicast" and not all(int(h.multicast_ptr) != 0 for h in self.handles.values()):
+            mode = "unicast"  # fabric without multicast support
+        self.mode = mode
+
+    @property
+    def _slab_offset(self) -> int:
+        return self.rank * self.per * self.plane_elems * 8
 
     def local_slab(self, key: str) -> torch.Tensor:
         lo = self.rank * self.per
         return self.full[key][lo:lo + self.per]
 
-    def slab_ptrs(self) -> dict:
-        off = self.rank * self.per * self.plane_elems * 8
-        return {k: int(h.multicast_ptr) + off for k, h in self.handles.items()}
+    def multicast_ptrs(self) -> dict:
+        return {k: int(h.multicast_ptr) + self._slab_offset for k, h in self.handles.items()}
+
+    def peer_ptrs(self) -> dict:
+        """This rank's slab inside every GPU's copy, rotated so that each rank starts with its right-hand neighbour
+        (at any instant the ranks then target different destinations)."""
+        order = [(self.rank + 1 + i) % self.world for i in range(self.world)]
+        return {k: [int(h.buffer_ptrs[i]) + self._slab_offset for i in order] for k, h in self.handles.items()}
 
     def eval_into(self, eng, prep_slab: dict, pols, flags: int = 0):
-        """Evaluate this rank's slab (a `shard_prepared`-style dict whose sweep_d holds `per` thicknesses)."""
+        """Evaluate this rank's slab (a prepared dict whose sweep_d holds this rank's `per` thicknesses)."""
         from ._cabi import FLAG_MULTICAST_OUT
 
-        if self.multicast:
-            return eng.eval_prepared(prep_slab, pols=pols, out_ptrs=self.slab_ptrs(), flags=flags | FLAG_MULTICAST_OUT)
+        if self.mode == "multicast":
+            return eng.eval_prepared(prep_slab, pols=pols, out_ptrs=self.multicast_ptrs(), flags=flags | FLAG_MULTICAST_OUT)
+        if self.mode == "unicast":
+            return eng.eval_prepared(prep_slab, pols=pols, out_ptrs=self.peer_ptrs(), flags=flags)
         return eng.eval_prepared(prep_slab, pols=pols, out={k: self.local_slab(k) for k in ("R", "T", "A")}, flags=flags)
 
     def finish(self):
-        if self.multicast:
-            torch.cuda.current_stream().synchronize()
-            self.handles["R"].barrier()
-        else:
+        if self.mode == "nccl":
             for k in ("R", "T", "A"):
                 dist.all_gather_into_tensor(self.full[k], self.local_slab(k), group=self.group)
+            return
+        torch.cuda.current_stream().synchronize()
+        self.handles["R"].barrier()

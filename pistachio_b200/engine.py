@@ -167,9 +167,25 @@ class TMMEngine:
             # PST_FLAG_MULTICAST_OUT, see dist.AssembledResult); the caller owns the memory and its extent
             if want_matrix:
                 raise ValueError("out_ptrs does not cover the matrix output")
-            raw = tuple(C.c_void_p(int(out_ptrs[k])) if out_ptrs.get(k) else None for k in ("R", "T", "A")) + (None,)
+            peers = None
+            if any(isinstance(out_ptrs.get(k), (list, tuple)) for k in ("R", "T", "A")):
+                # one address per receiving GPU: unicast fan-out by the kernel (pst_peer_outputs)
+                peers = _cabi.PeerOutputs()
+                n = max(len(v) for v in out_ptrs.values() if isinstance(v, (list, tuple)))
+                if n > _cabi.MAX_PEERS:
+                    raise ValueError(f"at most {_cabi.MAX_PEERS} peer buffers")
+                peers.n_peers = n
+                for k in ("R", "T", "A"):
+                    lst = list(out_ptrs.get(k) or [])
+                    for i in range(n):
+                        getattr(peers, k)[i] = int(lst[i]) if i < len(lst) and lst[i] else None
+                raw = (None, None, None, None)
+            else:
+                raw = tuple(C.c_void_p(int(out_ptrs[k])) if out_ptrs.get(k) else None for k in ("R", "T", "A")) + (None,)
             a, keep = self._grid_args(_ptr(wl_d), _ptr(th_d), _ptr(n_d), _ptr(k_d), layer_mat, layer_d, pols, sweep_layer,
                                       _ptr(sw_d), n_sw, _ptr(ct_d), flags, n_wl, n_theta, n_mat, raw)
+            if peers is not None:
+                a.peers = C.pointer(peers)
             check(self.lib.pst_eval_grid(self.handle.raw, C.byref(a), self._stream()), "pst_eval_grid")
             del keep
             return GridResult(None, None, None, None, pols_of_mask(mask))

@@ -354,6 +354,25 @@ def test_thickness_sweep_axis(eng, ref_cases):
                 np.testing.assert_allclose(out["R"][i], R, rtol=0, atol=1e-12)
 
 
+def test_peer_output_lists_write_every_listed_buffer(eng, ref_cases):
+    """pst_peer_outputs: the kernels store each result once per listed buffer (on a multi-GPU box the entries are
+    peer-mapped addresses of the other GPUs' arrays; here two local buffers stand in) -- K1 typed, K1 untyped, K3."""
+    c = ref_cases["c2_sub"]
+    n = np.asarray(c["n"])
+    args = (c["wl"], c["theta"], n.real, n.imag, list(range(n.shape[0])), list(c["d"]), POLS)
+    for kw in (dict(), dict(flags=16), dict(sweep_layer=2, sweep_d=np.linspace(0.1, 0.3, 5))):
+        ref = eng.eval_grid(*args, **kw)
+        bufs = [{k: torch.full_like(ref.R, float("nan")) for k in ("R", "T", "A")} for _ in range(2)]
+        ptrs = {k: [b[k].data_ptr() for b in bufs] for k in ("R", "T", "A")}
+        eng.eval_grid(*args, out_ptrs=ptrs, **kw)
+        torch.cuda.synchronize()
+        for b in bufs:
+            for k in ("R", "T", "A"):
+                assert torch.equal(b[k], getattr(ref, k)), (kw, k)
+    with pytest.raises(ValueError):
+        eng.eval_grid(*args, out_ptrs={"R": [1] * 9, "T": [], "A": []})
+
+
 def test_thick_absorber_and_deep_bragg_stay_finite(eng):
     from pistachio_b200._cabi import FLAG_FORCE_DEEP_KERNEL
 
