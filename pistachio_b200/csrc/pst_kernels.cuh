@@ -533,6 +533,63 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   }
 }
 
+// Per-thread constants of a thickness sweep (see tmm_sweep_kernel) and its inner loop.
+template <int NPOL>
+struct SweepConsts {
+  double qcr, qci, det_re;
+  cplx al0[NPOL], be0[NPOL], al1[NPOL], be1[NPOL];
+  int kfix[NPOL];
+};
+
+template <int NPOL, bool LOSSLESS, bool FAST>
+__device__ __forceinline__ void sweep_loop(const GridParams& prm, const SweepConsts<NPOL>& k, int s_begin, int s_end,
+                                           unsigned p) {
+  const size_t plane = (size_t)prm.points;
+  const size_t o0 = (size_t)s_begin * NPOL * plane + (size_t)p;
+  double* pR = FAST ? prm.R + o0 : nullptr;
+  double* pT = FAST ? prm.T + o0 : nullptr;
+  double* pA = FAST ? prm.A + o0 : nullptr;
+  double d = __ldg(prm.sweep_d + s_begin);
+  for (int sw = s_begin; sw < s_end; ++sw) {
+    const double d_next = __ldg(prm.sweep_d + min(sw + 1, s_end - 1));  // next thickness in flight during this one
+    double sx, cx;
+    sincos_fast(mul_rn(k.qcr, d), sx, cx);
+    cplx cphi = {cx, 0.0}, sphi = {sx, 0.0};
+    int sc = 0;
+    if constexpr (!LOSSLESS) {
+      double ch, sh;
+      sc = cosh_sinh_scaled(mul_rn(k.qci, d), ch, sh);  // cos, sin of (x + i y), both times 2^sc
+      cphi = {cx * ch, -(sx * sh)};
+      sphi = {sx * ch, cx * sh};
+    }
+#pragma unroll
+    for (int pp = 0; pp < NPOL; ++pp) {
+      cplx m00, m10;
+      if constexpr (LOSSLESS) {
+        m00 = {fma(cx, k.al0[pp].re, sx * k.be0[pp].re), fma(cx, k.al0[pp].im, sx * k.be0[pp].im)};
+        m10 = {fma(cx, k.al1[pp].re, sx * k.be1[pp].re), fma(cx, k.al1[pp].im, sx * k.be1[pp].im)};
+      } else {
+        m00 = cadd(cmul(cphi, k.al0[pp]), cmul(sphi, k.be0[pp]));
+        m10 = cadd(cmul(cphi, k.al1[pp]), cmul(sphi, k.be1[pp]));
+      }
+      const double den = fma(m00.re, m00.re, m00.im * m00.im);
+      const double num = fma(m10.re, m10.re, m10.im * m10.im);
+      const double iden = 1.0 / den;
+      const double R = num * iden;
+      const double T = scale_sq(k.det_re * iden, -(k.kfix[pp] + sc));
+      if constexpr (FAST) {
+        __stcs(pR, R);
+        __stcs(pT, T);
+        __stcs(pA, (1.0 - R) - T);
+        pR += plane; pT += plane; pA += plane;
+      } else {
+        store_point<true>(prm, ((size_t)sw * NPOL + pp) * plane + (size_t)p, R, T, (1.0 - R) - T);
+      }
+    }
+    d = d_next;
+  }
+}
+
 // ------------------------------------------------------------------------------------ K3: thickness sweep
 // One thread per (wavelength, theta) point loops over a chunk of sweep thicknesses.  Everything that does not depend
 // on the swept layer is computed once per thread:
@@ -650,40 +707,23 @@ tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
   }
   const double qcr = mul_rn(srow.qr, ct), qci = mul_rn(srow.qi, ct);  // first rounding of layer_phase()
 
-  // ---- the sweep loop
+  // ---- the sweep loop, specialised on the swept layer's kind and on the output mode so that neither is tested per
+  // thickness (FAST: R, T and A all go to local arrays with streaming stores)
   const int s_begin = blockIdx.y * sweeps_per_block;
   const int s_end = min(s_begin + sweeps_per_block, n_sweep);
-  const size_t plane = (size_t)prm.points;
-  for (int sw = s_begin; sw < s_end; ++sw) {
-    const double d = __ldg(prm.sweep_d + sw);
-    double sx, cx;
-    sincos_fast(mul_rn(qcr, d), sx, cx);
-    cplx cphi = {cx, 0.0}, sphi = {sx, 0.0};
-    int sc = 0;
-    if (!s_lossless) {
-      double ch, sh;
-      sc = cosh_sinh_scaled(mul_rn(qci, d), ch, sh);  // cos, sin of (x + i y), both times 2^sc
-      cphi = {cx * ch, -(sx * sh)};
-      sphi = {sx * ch, cx * sh};
-    }
+  SweepConsts<NPOL> kc;
+  kc.qcr = qcr; kc.qci = qci; kc.det_re = det_re;
 #pragma unroll
-    for (int pp = 0; pp < NPOL; ++pp) {
-      cplx m00, m10;
-      if (s_lossless) {
-        m00 = {fma(cx, al0[pp].re, sx * be0[pp].re), fma(cx, al0[pp].im, sx * be0[pp].im)};
-        m10 = {fma(cx, al1[pp].re, sx * be1[pp].re), fma(cx, al1[pp].im, sx * be1[pp].im)};
-      } else {
-        m00 = cadd(cmul(cphi, al0[pp]), cmul(sphi, be0[pp]));
-        m10 = cadd(cmul(cphi, al1[pp]), cmul(sphi, be1[pp]));
-      }
-      const double den = fma(m00.re, m00.re, m00.im * m00.im);
-      const double num = fma(m10.re, m10.re, m10.im * m10.im);
-      const double iden = 1.0 / den;
-      const double R = num * iden;
-      const double T = scale_sq(det_re * iden, -(kfix[pp] + sc));
-      const size_t o = ((size_t)sw * NPOL + pp) * plane + (size_t)p;
-      store_point<true>(prm, o, R, T, (1.0 - R) - T);
-    }
+  for (int pp = 0; pp < NPOL; ++pp) {
+    kc.al0[pp] = al0[pp]; kc.al1[pp] = al1[pp]; kc.be0[pp] = be0[pp]; kc.be1[pp] = be1[pp]; kc.kfix[pp] = kfix[pp];
+  }
+  const bool fast = prm.R && prm.T && prm.A && prm.n_peers == 0 && !(prm.flags & kFlagMulticastOut);
+  if (s_lossless) {
+    if (fast) sweep_loop<NPOL, true, true>(prm, kc, s_begin, s_end, p);
+    else sweep_loop<NPOL, true, false>(prm, kc, s_begin, s_end, p);
+  } else {
+    if (fast) sweep_loop<NPOL, false, true>(prm, kc, s_begin, s_end, p);
+    else sweep_loop<NPOL, false, false>(prm, kc, s_begin, s_end, p);
   }
 }
 
