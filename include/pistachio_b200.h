@@ -200,6 +200,18 @@ int pst_find_peaks(pst_handle_t h, const double* y /*[dev]*/, int n_outer, int n
                    int* out_idx /*[dev]*/, double* out_height /*[dev] or NULL*/, int* out_count /*[dev]*/,
                    double* out_spacing /*[dev] or NULL*/, void* stream);
 
+/* Lower and upper polariton branch per spectrum, from the peak lists of pst_find_peaks (same y, reverse, axis,
+ * max_peaks): the two highest kept peaks, each refined by the closed-form three-point Lorentzian fit (1/y is a
+ * parabola around a Lorentzian peak).  Stands in, on the device, for the per-angle two-Lorentzian fits of the
+ * reference's notebooks/Polariton Peak Analysis.ipynb (cells 8-17: l1_center = LP, l2_center = UP; the notebook's
+ * lmfit dependency is not part of the reference repository, so there is no numerical oracle for it -- the restated
+ * formula lives in oracle/peaks_oracle.py).  out[s][6] = (x0_lower, x0_upper, hwhm_lower, hwhm_upper, A_lower,
+ * A_upper) in units of `axis`; NaN for spectra with fewer than two peaks. */
+int pst_polariton_branches(pst_handle_t h, const double* y /*[dev]*/, int n_outer, int n_pts, int n_inner, int reverse,
+                           const double* axis /*[dev] n_pts*/, const int* peak_idx /*[dev]*/,
+                           const double* peak_height /*[dev]*/, const int* peak_count /*[dev]*/, int max_peaks,
+                           double* out /*[dev] n_outer*n_inner*6*/, void* stream);
+
 /* ---- measurement helpers ------------------------------------------------------------------------------ */
 /* Independent-DFMA micro-benchmark: the measured FP64 (non-tensor) peak used as the roofline denominator.
  * Runs `iters` dependent FMAs on 8 independent chains per thread over a full-chip grid, returns TFLOP/s. */

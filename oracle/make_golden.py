@@ -106,11 +106,15 @@ def resolved(w):
             "sweep_layer": w.sweep_layer, "sweep_d": w.sweep_d}
 
 
-def main():
-    tm = load_reference()
-    out = {}
+def package_materials(tm):
+    """(lambda, n, k) tables of the reference's data files -> pistachio_b200/data/materials.npz.  The four tables next
+    to transfer_matrix.py are read through the reference's own Layer.get_data_from_csv; the n / nk tables of the
+    refractiveindex_info/ sub-folder (which that method cannot reach: importlib.resources takes no sub-paths) are parsed
+    here with the same column convention (wavelength in micrometres, n, optional k; k = 0 when absent).  Spectra
+    (transmittance_*/reflectance_* files) are not index tables and are left out."""
+    import csv
+    import glob
 
-    # ---- materials shipped with the reference (tables only; used by the package and the tests)
     mats = {}
     for fname in ("Au.csv", "CaF2.csv", "MgF2.csv", "ZnS.csv"):
         l = tm.Layer()
@@ -119,8 +123,33 @@ def main():
         mats[f"{key}/wl"] = l.wavelengths
         mats[f"{key}/n"] = l.refractive_index
         mats[f"{key}/k"] = l.extinction_coeff
+    folder = os.path.join(os.path.dirname(tm.__file__), "data", "refractive_index_data", "refractiveindex_info")
+    for path in sorted(glob.glob(os.path.join(folder, "*.csv"))):
+        stem = os.path.basename(path)[:-4]
+        if stem.lower().startswith(("transmittance", "reflectance")):
+            continue
+        wl, n, k = [], [], []
+        with open(path, "r", encoding="utf-8-sig") as fh:
+            rows = csv.reader(fh)
+            next(rows, None)
+            for row in rows:
+                if len(row) < 2 or row[0] == "":
+                    continue
+                wl.append(float(row[0]))
+                n.append(float(row[1]))
+                k.append(float(row[2]) if len(row) > 2 and row[2] != "" else 0.0)
+        mats[f"{stem}/wl"], mats[f"{stem}/n"], mats[f"{stem}/k"] = np.array(wl), np.array(n), np.array(k)
     os.makedirs(os.path.join(ROOT, "pistachio_b200", "data"), exist_ok=True)
     np.savez_compressed(os.path.join(ROOT, "pistachio_b200", "data", "materials.npz"), **mats)
+
+
+def main():
+    tm = load_reference()
+    out = {}
+
+    package_materials(tm)
+    if "--materials-only" in sys.argv:
+        return
 
     # ---- known-answer tests of the reference (tests/test_layer.py:67-91, tests/test_structure.py:65-71)
     out["kat/D_s"] = tm.Layer().dynamical_matrix(1.0 + 1.0j, 0.0, "s-wave")

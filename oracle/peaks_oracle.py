@@ -70,3 +70,34 @@ def mean_spacing(axis, peaks):
         return float("nan")
     vals = np.asarray(axis, dtype=np.float64)[peaks]
     return float(np.mean(np.diff(vals)))
+
+
+def lorentzian_three_point(x, y, i):
+    """Closed-form Lorentzian through samples i-1, i, i+1: for y = A / (1 + ((x - x0)/g)^2) the reciprocal is a
+    parabola, so divided differences of 1/y give (x0, g, A) exactly.  Restatement of pst_polariton_branches' refinement
+    (there is no reference oracle: the notebook's lmfit two-Lorentzian fit is not part of the reference repository)."""
+    x0, x1, x2 = (float(x[i - 1]), float(x[i]), float(x[i + 1]))
+    z0, z1, z2 = (1.0 / float(y[i - 1]), 1.0 / float(y[i]), 1.0 / float(y[i + 1]))
+    s01, s12 = (z1 - z0) / (x1 - x0), (z2 - z1) / (x2 - x1)
+    a = (s12 - s01) / (x2 - x0)
+    b1 = s01 + a * (x1 - x0)
+    if not (a > 0.0 and np.isfinite(a) and np.isfinite(b1)):
+        return x1, float("nan"), float(y[i])
+    zmin = z1 - b1 * b1 / (4.0 * a)
+    if zmin <= 0.0:
+        return x1 - b1 / (2.0 * a), float("nan"), float("nan")
+    return x1 - b1 / (2.0 * a), float(np.sqrt(zmin / a)), 1.0 / zmin
+
+
+def polariton_branches(x, y, height=None, distance=None):
+    """(x0_lower, x0_upper, g_lower, g_upper, A_lower, A_upper) of the two highest peaks of one spectrum."""
+    peaks = find_peaks(y, height=height, distance=distance)
+    if len(peaks) < 2:
+        return (float("nan"),) * 6
+    h = np.asarray(y)[peaks]
+    j1 = int(np.argmax(h))
+    rest = [k for k in range(len(peaks)) if k != j1]
+    j2 = rest[int(np.argmax(h[rest]))]
+    a, b = lorentzian_three_point(x, y, peaks[j1]), lorentzian_three_point(x, y, peaks[j2])
+    lo, hi = (a, b) if a[0] <= b[0] else (b, a)
+    return lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]

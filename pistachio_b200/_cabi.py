@@ -89,6 +89,8 @@ SYMBOLS = {
     "pst_interface_matrices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pst_find_peaks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pst_polariton_branches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "pst_fp64_peak_probe": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_void_p]),
     "pst_flush_l2": (C.c_int, [C.c_void_p, C.c_void_p]),
 }

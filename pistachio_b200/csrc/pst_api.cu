@@ -750,6 +750,22 @@ extern "C" int pst_find_peaks(pst_handle_t h, const double* y, int n_outer, int 
   return PST_OK;
 }
 
+extern "C" int pst_polariton_branches(pst_handle_t h, const double* y, int n_outer, int n_pts, int n_inner, int reverse,
+                                      const double* axis, const int* peak_idx, const double* peak_height,
+                                      const int* peak_count, int max_peaks, double* out, void* stream) {
+  if (!h) return fail(PST_E_INVALID, "pst_polariton_branches: NULL handle");
+  if (!y || !axis || !peak_idx || !peak_height || !peak_count || !out || n_outer <= 0 || n_pts < 3 || n_inner <= 0 ||
+      max_peaks < 1)
+    return fail(PST_E_INVALID, "pst_polariton_branches: bad argument");
+  DeviceGuard g(h->device);
+  const long long n_spec = (long long)n_outer * n_inner;
+  polariton_branches_kernel<<<(unsigned)((n_spec + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      y, n_outer, n_pts, n_inner, reverse, axis, peak_idx, peak_height, peak_count, max_peaks, out);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PST_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ measurement
 extern "C" int pst_fp64_peak_probe(pst_handle_t h, int iters, double* tflops_out, void* stream) {
   if (!h || !tflops_out || iters <= 0) return fail(PST_E_INVALID, "pst_fp64_peak_probe: bad argument");

@@ -980,6 +980,63 @@ __global__ void find_peaks_kernel(const double* __restrict__ y, int n_outer, int
   }
 }
 
+// Lower / upper polariton branch of every spectrum (the reference's "Polariton Peak Analysis"
+// notebook fits two Lorentzians per angle and reads off their centres, cells 8-17).  Here the two HIGHEST peaks that
+// pst_find_peaks kept are each refined by the exact three-point Lorentzian: for y = A / (1 + ((x - x0)/g)^2) the
+// reciprocal 1/y is a parabola in x, so the peak sample and its two neighbours give x0, g (half width at half maximum)
+// and A in closed form, on a non-uniform axis (wavenumbers of a wavelength grid) through divided differences.
+// out[s][6] = (x0_lower, x0_upper, g_lower, g_upper, A_lower, A_upper), NaN when the spectrum has fewer than two
+// peaks; "lower"/"upper" by position on `axis`.
+__global__ void polariton_branches_kernel(const double* __restrict__ y, int n_outer, int n_pts, int n_inner, int reverse,
+                                          const double* __restrict__ axis, const int* __restrict__ peak_idx,
+                                          const double* __restrict__ peak_height, const int* __restrict__ peak_count,
+                                          int max_peaks, double* __restrict__ out) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= (long long)n_outer * n_inner) return;
+  const int outer = (int)(s / n_inner), inner = (int)(s - (long long)outer * n_inner);
+  const double* base = y + ((size_t)outer * n_pts) * n_inner + inner;
+  auto at = [&](int i) { return __ldg(base + (size_t)(reverse ? n_pts - 1 - i : i) * n_inner); };
+  auto ax = [&](int i) { return __ldg(axis + (reverse ? n_pts - 1 - i : i)); };
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  double* o = out + s * 6;
+  const int n = peak_count[s];
+  if (n < 2) {
+    for (int k = 0; k < 6; ++k) o[k] = nan;
+    return;
+  }
+  // the two highest kept peaks (ties: the earlier one)
+  int j1 = 0, j2 = -1;
+  for (int k = 1; k < n; ++k)
+    if (peak_height[s * max_peaks + k] > peak_height[s * max_peaks + j1]) j1 = k;
+  for (int k = 0; k < n; ++k)
+    if (k != j1 && (j2 < 0 || peak_height[s * max_peaks + k] > peak_height[s * max_peaks + j2])) j2 = k;
+  double res[2][3];
+  int pos[2] = {peak_idx[s * max_peaks + j1], peak_idx[s * max_peaks + j2]};
+  for (int b = 0; b < 2; ++b) {
+    const int i = pos[b];  // 1 <= i <= n_pts - 2: a local maximum is never an end sample
+    const double x0 = ax(i - 1), x1 = ax(i), x2 = ax(i + 1);
+    const double z0 = 1.0 / at(i - 1), z1 = 1.0 / at(i), z2 = 1.0 / at(i + 1);
+    const double s01 = (z1 - z0) / (x1 - x0), s12 = (z2 - z1) / (x2 - x1);
+    const double a = (s12 - s01) / (x2 - x0);                 // curvature of 1/y
+    const double b1 = s01 + a * (x1 - x0);                    // slope of the parabola at x1
+    if (a > 0.0 && isfinite(a) && isfinite(b1)) {
+      const double du = -b1 / (2.0 * a);                      // centre relative to x1
+      const double zmin = z1 - b1 * b1 / (4.0 * a);
+      res[b][0] = x1 + du;
+      res[b][1] = zmin > 0.0 ? sqrt(zmin / a) : nan;
+      res[b][2] = zmin > 0.0 ? 1.0 / zmin : nan;
+    } else {  // not Lorentzian-like around the sample (flat top, non-positive neighbours): report the sample itself
+      res[b][0] = x1;
+      res[b][1] = nan;
+      res[b][2] = at(i);
+    }
+  }
+  const int lo = res[0][0] <= res[1][0] ? 0 : 1, hi = 1 - lo;
+  o[0] = res[lo][0]; o[1] = res[hi][0];
+  o[2] = res[lo][1]; o[3] = res[hi][1];
+  o[4] = res[lo][2]; o[5] = res[hi][2];
+}
+
 // ------------------------------------------------------------------------------ measurement helpers
 // 8 independent dependent-FMA chains per thread: the non-tensor FP64 peak of the chip.
 __global__ void dfma_probe_kernel(int iters, double seed, double* __restrict__ sink) {

@@ -397,6 +397,25 @@ class TMMEngine:
                                       _ptr(spc), self._stream()), "pst_find_peaks")
         return idx, hts, cnt, spc
 
+    def polariton_branches(self, y, idx, hts, cnt, axis, reverse=False):
+        """Lower/upper polariton branch per spectrum from the peak lists `find_peaks` returned for the same `y`, `axis`
+        and `reverse` (pst_polariton_branches): the two highest peaks, each refined by the closed-form three-point
+        Lorentzian.  Returns a device tensor [..., n_theta, 6] = (centre_lower, centre_upper, hwhm_lower, hwhm_upper,
+        amplitude_lower, amplitude_upper) in units of `axis`; NaN where a spectrum has fewer than two peaks."""
+        y = y.contiguous()
+        n_pts, n_inner = y.shape[-2], y.shape[-1]
+        lead = tuple(y.shape[:-2])
+        n_outer = int(np.prod(lead)) if lead else 1
+        ax_d = _dev_f64(axis, self.device)
+        if ax_d.numel() != n_pts:
+            raise ValueError("axis must have one value per wavelength")
+        out = torch.empty(lead + (n_inner, 6), dtype=torch.float64, device=self.device)
+        check(self.lib.pst_polariton_branches(self.handle.raw, _ptr(y), n_outer, n_pts, n_inner, 1 if reverse else 0,
+                                              _ptr(ax_d), _ptr(idx.contiguous()), _ptr(hts.contiguous()),
+                                              _ptr(cnt.contiguous()), int(idx.shape[-1]), _ptr(out), self._stream()),
+              "pst_polariton_branches")
+        return out
+
     # ------------------------------------------------------------------ measurement
     def fp64_peak_tflops(self, iters: int = 4096) -> float:
         out = C.c_double(0.0)

@@ -391,6 +391,39 @@ class Structure:
             out = {k: v[0] for k, v in out.items()}
         return out
 
+    def polariton_dispersion(self, theta=None, pol=S_WAVE, height=None, distance=None, sweep_layer=-1, sweep_d=None,
+                             max_peaks=64):
+        """Additive API: the dispersion step of the reference's "Polariton Peak Analysis"
+        notebook (cells 8-17: a two-Lorentzian fit per angle whose centres are the lower and upper polariton) fused
+        behind the spectrum.  Transmittance spectra are evaluated on the device for every angle (and swept thickness),
+        the two highest peaks on the wavenumber axis nu = 1e4/lambda[um] are located (find_peaks semantics, `height`
+        as a fraction, `distance` in samples) and refined by the closed-form three-point Lorentzian, and only
+        (LP, UP, widths, amplitudes) per spectrum leave the GPU.  Returns a dict of arrays shaped (n_theta,) or
+        (n_sweep, n_theta): `theta`, `LP`, `UP`, `splitting` = UP - LP, `hwhm_LP`, `hwhm_UP`, `amp_LP`, `amp_UP`, and
+        `min_splitting` (the Rabi-splitting estimate: the smallest UP - LP over the angles) with its `theta_at_min`."""
+        theta = np.atleast_1d(np.asarray(self.theta if theta is None else theta, dtype=np.float64))
+        wl, mat_n, mat_k, layer_mat, layer_d = self._stack_on_grid()
+        eng = _eng()
+        res = eng.eval_grid(wl, theta, mat_n, mat_k, layer_mat, layer_d, (pol,), cos_theta=np.cos(theta),
+                            sweep_layer=sweep_layer, sweep_d=sweep_d, want=("T",))
+        nu = 1.0e4 / wl
+        rev = bool(wl.size > 1 and wl[0] < wl[-1])
+        T = res.T[:, 0]
+        idx, hts, cnt, _ = eng.find_peaks(T, height=height, distance=distance, max_peaks=max_peaks, axis=nu, reverse=rev)
+        br = _to_numpy(eng.polariton_branches(T, idx, hts, cnt, nu, reverse=rev))
+        if (_to_numpy(cnt) < 0).any():
+            raise ValueError("more peaks than max_peaks in at least one spectrum")
+        out = {"theta": theta, "LP": br[..., 0], "UP": br[..., 1], "splitting": br[..., 1] - br[..., 0],
+               "hwhm_LP": br[..., 2], "hwhm_UP": br[..., 3], "amp_LP": br[..., 4], "amp_UP": br[..., 5]}
+        with np.errstate(invalid="ignore"):
+            spl = np.where(np.isnan(out["splitting"]), np.inf, out["splitting"])
+        k = spl.argmin(axis=-1)
+        out["min_splitting"] = np.take_along_axis(spl, k[..., None], axis=-1)[..., 0]
+        out["theta_at_min"] = theta[k]
+        if sweep_d is None:
+            out = {key: (v[0] if key != "theta" else v) for key, v in out.items()}
+        return out
+
     # ---- misc -----------------------------------------------------------------------------------------------
     def print_structure(self):
         """Print one line per layer, format of tm.py:630-647."""
