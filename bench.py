@@ -274,6 +274,7 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
 
     flags = (16 if args.no_layer_cse else 0) | (128 if args.no_periodic_power else 0)  # PST_FLAG_NO_LAYER_CSE / _NO_PERIODIC_POWER
+    flags |= 512 if args.fp32 else 0  # PST_FLAG_FP32 (optional mode; the default and every reported headline number is fp64)
 
     def step():
         eng.eval_prepared(prep, pols=pols, out=out, flags=flags)
@@ -453,7 +454,7 @@ def run_ours(args):
     peaks, peaks_src = load_measured_peaks()
     fp64_peak = eng.fp64_peak_tflops(8192)
     layer_steps = points_rank * w.interior_layers
-    flop_model = algorithmic_flops(w, prep, len(pols), cse=not args.no_layer_cse, power=not args.no_periodic_power)
+    flop_model = algorithmic_flops(w, prep, len(pols), cse=not (args.no_layer_cse or args.fp32), power=not args.no_periodic_power)
     achieved_tf = flop_model["flop_per_point"] * points_rank / (ms_per_step / 1e3) / 1e12
     survey_tf = layer_steps * FLOP_PER_LAYER_STEP / (ms_per_step / 1e3) / 1e12
     hbm_gbs = 24.0 * points_rank / (ms_per_step / 1e3) / 1e9
@@ -491,7 +492,8 @@ def run_ours(args):
         pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 chain / f64 phase (optional mode)" if args.fp32 else "f64",
         "data": "synthetic",
         "config": {"workload": desc, "layer_cse": not args.no_layer_cse, "periodic_power": not (args.no_periodic_power or args.no_layer_cse), "points_per_gpu": points_rank, "interior_layers": w.interior_layers,
                    "layer_steps_per_s": value * w.interior_layers, "l2": "flushed between steps (256 MiB memset); outputs 403 MB/step > L2",
@@ -522,6 +524,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-layer-cse", action="store_true", help="ablation: rebuild every layer matrix (PST_FLAG_NO_LAYER_CSE)")
+    ap.add_argument("--fp32", action="store_true", help="optional fp32 mode (PST_FLAG_FP32): fp64 phase, fp32 chain, <= 1e-5")
     ap.add_argument("--no-periodic-power", action="store_true",
                     help="ablation: apply repeated lossless pairs layer by layer (PST_FLAG_NO_PERIODIC_POWER)")
     args = ap.parse_args()

@@ -60,6 +60,10 @@ extern "C" {
                                                  GPU of the mapping -- a sharded sweep is assembled on all devices
                                                  without an all-gather.  The caller synchronises the devices afterwards.
                                                  Not valid with M or with pst_eval_grid_host */
+#define PST_FLAG_FP32 (1u << 9)                /* optional fp32 mode (<= 1e-5): phase and its range reduction stay in fp64,
+                                                 polynomials, layer matrices and the chain run in fp32 with the two
+                                                 polarisations packed in f32x2 registers; inputs/outputs stay fp64.
+                                                 Point kernel without layer CSE; not valid with M */
 #define PST_FLAG_NO_LAYER_CSE (1u << 4)       /* rebuild the matrix of every layer even when layers repeat (ablation;
                                                  results are bit-identical with and without) */
 

@@ -235,6 +235,7 @@ int validate_grid(const pst_grid_args* a, const char* who) {
   if ((a->flags & PST_FLAG_FORCE_POINT_KERNEL) && (a->flags & PST_FLAG_FORCE_DEEP_KERNEL))
     return fail(PST_E_INVALID, w + ": contradictory kernel flags");
   if ((a->flags & PST_FLAG_MULTICAST_OUT) && a->M) return fail(PST_E_INVALID, w + ": PST_FLAG_MULTICAST_OUT does not cover the matrix output M");
+  if ((a->flags & PST_FLAG_FP32) && a->M) return fail(PST_E_INVALID, w + ": PST_FLAG_FP32 does not cover the matrix output M");
   if ((a->flags & PST_FLAG_NUMERIC_DET) && !a->M) return fail(PST_E_INVALID, w + ": PST_FLAG_NUMERIC_DET needs the matrix output M");
   for (int j = 0; j < a->n_layers; ++j)
     if (a->layer_mat[j] < 0 || a->layer_mat[j] >= a->n_mat) return fail(PST_E_INVALID, w + ": layer_mat entry out of range");
@@ -478,6 +479,56 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
   return PST_OK;
 }
 
+// fp32 mode (PST_FLAG_FP32): one thread per point, both polarisations packed, layer loop without CSE.
+int launch_chain_f32(pst_handle_t h, const pst_grid_args* a, int il0, int n_wl_launch, const double* sweep_d_dev,
+                     double* R, double* T, double* A, cudaStream_t st) {
+  const int PB = 128;
+  const int npol = __builtin_popcount(a->pol_mask);
+  GridParams prm;
+  std::memset(&prm, 0, sizeof(prm));
+  prm.n_wl = a->n_wl;
+  prm.n_theta = a->n_theta;
+  prm.n_mat = a->n_mat;
+  prm.n_layers = a->n_layers;
+  prm.sweep_layer = a->sweep_layer;
+  prm.pol_first = 0;
+  prm.pol_mask = a->pol_mask;
+  prm.tl_rows = std::min(n_wl_launch, (PB - 1) / a->n_theta + 2);
+  prm.opt_row_bytes = a->n_mat * 48 + ((a->n_mat % 2 == 0) ? 16 : 0);
+  prm.il0 = il0;
+  prm.flags = a->flags;
+  prm.points = (long long)n_wl_launch * a->n_theta;
+  prm.opt = h->opt.p;
+  prm.mat_flags = h->mat_flags.p;
+  prm.trig = h->trig.p;
+  prm.layers = h->layers_flagged.p;
+  prm.use_bulk = (a->flags & PST_FLAG_NO_BULK_COPY) ? 0 : 1;
+  const size_t smem = (size_t)prm.tl_rows * prm.opt_row_bytes + (size_t)a->n_layers * sizeof(LayerEntry);
+  const bool stage = !(a->flags & PST_FLAG_NO_SMEM_STAGING) && smem <= 64 * 1024;
+  auto fn = stage ? tmm_chain_f32_kernel<true> : tmm_chain_f32_kernel<false>;
+  if (stage && smem > 48 * 1024) PST_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  const long long nblk = (prm.points + PB - 1) / PB;
+  if (nblk > 0x7fffffffLL) return fail(PST_E_INVALID, "pst_eval_grid: too many blocks");
+  const size_t per_sweep = (size_t)npol * (size_t)prm.points;
+  for (int s0 = 0; s0 < a->n_sweep; s0 += 65535) {
+    const int ns = std::min(65535, a->n_sweep - s0);
+    prm.sweep_d = sweep_d_dev ? sweep_d_dev + s0 : nullptr;
+    prm.R = R ? R + (size_t)s0 * per_sweep : nullptr;
+    prm.T = T ? T + (size_t)s0 * per_sweep : nullptr;
+    prm.A = A ? A + (size_t)s0 * per_sweep : nullptr;
+    prm.n_peers = a->peers ? a->peers->n_peers : 0;
+    for (int i = 0; i < prm.n_peers; ++i) {
+      prm.peer_R[i] = a->peers->R[i] ? a->peers->R[i] + (size_t)s0 * per_sweep : nullptr;
+      prm.peer_T[i] = a->peers->T[i] ? a->peers->T[i] + (size_t)s0 * per_sweep : nullptr;
+      prm.peer_A[i] = a->peers->A[i] ? a->peers->A[i] + (size_t)s0 * per_sweep : nullptr;
+    }
+    fn<<<dim3((unsigned)nblk, (unsigned)ns), PB, stage ? smem : 0, st>>>(prm);
+    PST_CUDA(cudaGetLastError());
+    h->launches += 1;
+  }
+  return PST_OK;
+}
+
 using SweepKernel = void (*)(const GridParams, int, int);
 SweepKernel pick_sweep(int npol, bool so, bool sl) {
 #define PST_S(P, O, L) if (npol == P && so == O && sl == L) return tmm_sweep_kernel<P, O, L>;
@@ -556,6 +607,7 @@ extern "C" int pst_eval_grid(pst_handle_t h, const pst_grid_args* a, void* strea
   cudaStream_t st = (cudaStream_t)stream;
   PST_TRY(sync_layers(h, a, st));
   PST_TRY(run_prep(h, a, a->wl, a->theta, a->cos_theta, a->mat_n, a->mat_k, st));
+  if (a->flags & PST_FLAG_FP32) return launch_chain_f32(h, a, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, st);
   if (use_sweep_kernel(a)) return launch_sweep(h, a, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, st);
   ChainPlan pl;
   PST_TRY(plan_chain(h, a, a->n_wl, &pl));
@@ -622,7 +674,9 @@ extern "C" int pst_eval_grid_host(pst_handle_t h, const pst_grid_args* a) {
     ChainPlan pl;
     pst_grid_args loc = *a;
     loc.R = dR; loc.T = dT; loc.A = dA; loc.M = dM;
-    if (use_sweep_kernel(&loc)) {
+    if (loc.flags & PST_FLAG_FP32) {
+      PST_TRY(launch_chain_f32(h, &loc, (int)l0, (int)cw, a->sweep_d ? d_sw : nullptr, dR, dT, dA, sc));
+    } else if (use_sweep_kernel(&loc)) {
       PST_TRY(launch_sweep(h, &loc, (int)l0, (int)cw, d_sw, dR, dT, dA, sc));
     } else {
       PST_TRY(plan_chain(h, &loc, (int)cw, &pl));

@@ -39,6 +39,7 @@ struct GridParams {
   int n_wl, n_theta, n_mat, n_layers;
   int sweep_layer;   // -1: none
   int pol_first;     // NPOL == 1: 0 = s, 1 = p
+  unsigned pol_mask; // requested polarisations (bit 0 = s, bit 1 = p); used by the fp32 kernel, which always steps both
   int tl_rows;       // wavelength rows of the shared-memory optical table (>= max wavelengths per block)
   int opt_row_bytes; // bytes per wavelength row in shared memory: n_mat*48 (+16 pad when n_mat is even)
   int il0;           // first wavelength index of this launch (host pipeline launches wavelength windows)
@@ -1054,3 +1055,5 @@ __global__ void dfma_probe_kernel(int iters, double seed, double* __restrict__ s
 }
 
 }  // namespace pst
+
+#include "pst_f32.cuh"

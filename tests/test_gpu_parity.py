@@ -373,6 +373,56 @@ def test_peer_output_lists_write_every_listed_buffer(eng, ref_cases):
         eng.eval_grid(*args, out_ptrs={"R": [1] * 9, "T": [], "A": []})
 
 
+# ------------------------------------------------------------------------------------------------ optional fp32 mode
+FP32 = 1 << 9  # PST_FLAG_FP32
+
+
+@pytest.mark.parametrize("name,floor", [("c1", 0.1), ("c3_sub_d0", 0.1), ("c3_sub_d66666", 0.1), ("c2_sub", 1.0)])
+def test_fp32_mode_within_1e_5(eng, ref_cases, name, floor):
+    """north_star: <= 1e-5 for the optional fp32 mode.  |got - ref| <= 1e-5 max(|ref|, floor): relative 1e-5 down to
+    values of 0.1 (absolute 1e-6 below) for ordinary stacks; the 2 x 20-pair DBR cavity amplifies fp32 rounding by its
+    finesse, there the bound is 1e-5 of full scale (measured: 9e-6)."""
+    c = ref_cases[name]
+    out = run_case(eng, c, flags=FP32)
+    for key in ("T", "R"):
+        ref = c[key]
+        ok = np.isfinite(ref)
+        err = np.abs(out[key][0] - ref)[ok]
+        tol = 1e-5 * np.maximum(np.abs(ref[ok]), floor)
+        assert (err <= tol).all(), (name, key, float((err / tol).max()))
+    assert np.array_equal(out["A"][0], (1.0 - out["R"][0]) - out["T"][0])
+
+
+def test_fp32_mode_fuzz_and_variants(eng, ref_cases):
+    worst = 0.0
+    for i in range(int(ref_cases["fuzz"]["count"])):
+        c = ref_cases[f"fuzz{i}"]
+        out = run_case(eng, c, flags=FP32)
+        for key in ("T", "R"):
+            ok = np.isfinite(c[key])
+            err = np.abs(out[key][0] - c[key])[ok] / np.maximum(np.abs(c[key][ok]), 0.1)
+            worst = max(worst, float(err.max(initial=0.0)))
+    print(f"fp32 fuzz: worst |d| / max(|ref|, 0.1) = {worst:.2e}")
+    assert worst <= 1e-5
+    # one polarisation = the same plane of the two-polarisation launch; no shared-memory staging = same bits
+    c = ref_cases["c1"]
+    both = run_case(eng, c, flags=FP32)
+    for ip, pol in enumerate(POLS):
+        one = run_case(eng, c, pols=(pol,), flags=FP32)
+        assert np.array_equal(one["T"][0][0], both["T"][0][ip]) and np.array_equal(one["R"][0][0], both["R"][0][ip])
+    plain = run_case(eng, c, flags=FP32 | 8)
+    assert np.array_equal(plain["T"], both["T"]) and np.array_equal(plain["R"], both["R"])
+    # thickness axis, and the matrix output is refused
+    n = np.asarray(c["n"])
+    sw = np.linspace(15.0, 25.0, 7)
+    args = (c["wl"], c["theta"], n.real, n.imag, list(range(n.shape[0])), list(c["d"]), POLS)
+    f64 = eng.eval_grid(*args, sweep_layer=2, sweep_d=sw).numpy()
+    f32 = eng.eval_grid(*args, sweep_layer=2, sweep_d=sw, flags=FP32).numpy()
+    assert np.abs(f32["T"] - f64["T"]).max() <= 1e-6 and np.abs(f32["R"] - f64["R"]).max() <= 1e-6
+    with pytest.raises(ValueError):
+        eng.eval_grid(*args, flags=FP32, want_matrix=True)
+
+
 def test_thick_absorber_and_deep_bragg_stay_finite(eng):
     from pistachio_b200._cabi import FLAG_FORCE_DEEP_KERNEL
 
