@@ -326,7 +326,7 @@ int run_prep(pst_handle_t h, const pst_grid_args* a, const double* wl, const dou
   TypeMats tm;
   tm.n = h->n_types;
   for (int t = 0; t < kMaxTypes; ++t) tm.mat[t] = t < h->n_types ? a->layer_mat[h->type_layer[t]] : 0;
-  flag_layers_kernel<<<(a->n_layers + 255) / 256, 256, 0, st>>>(h->layers_dev.p, h->mat_flags.p, a->n_layers,
+  flag_layers_kernel<<<(a->n_layers + 255) / 256, 256, 0, st>>>(h->layers_dev.p, h->mat_flags.p, a->n_layers, a->n_mat,
                                                                h->layers_flagged.p, tm, h->lossy_types.p);
   PST_CUDA(cudaGetLastError());
   h->launches += 3;
@@ -433,6 +433,7 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
   prm.points = (long long)n_wl_launch * a->n_theta;
   prm.opt = h->opt.p;
   prm.mat_flags = h->mat_flags.p;
+  prm.lossy_word = h->lossy_types.p;
   prm.trig = h->trig.p;
   prm.layers = h->layers_flagged.p;  // `type` field = the material's lossy flag
   TypedPlan tp;
@@ -500,6 +501,7 @@ int launch_chain_f32(pst_handle_t h, const pst_grid_args* a, int il0, int n_wl_l
   prm.points = (long long)n_wl_launch * a->n_theta;
   prm.opt = h->opt.p;
   prm.mat_flags = h->mat_flags.p;
+  prm.lossy_word = h->lossy_types.p;
   prm.trig = h->trig.p;
   prm.layers = h->layers_flagged.p;
   prm.use_bulk = (a->flags & PST_FLAG_NO_BULK_COPY) ? 0 : 1;
@@ -563,6 +565,7 @@ int launch_sweep(pst_handle_t h, const pst_grid_args* a, int il0, int n_wl_launc
   prm.points = (long long)n_wl_launch * a->n_theta;
   prm.opt = h->opt.p;
   prm.mat_flags = h->mat_flags.p;
+  prm.lossy_word = h->lossy_types.p;
   prm.trig = h->trig.p;
   prm.layers = h->layers_flagged.p;
   prm.use_bulk = (a->flags & PST_FLAG_NO_BULK_COPY) ? 0 : 1;

@@ -48,6 +48,7 @@ struct GridParams {
   long long points;  // wavelengths of this launch * n_theta
   const double* opt;        // [n_wl][n_mat][6]: OptRow order qr nr inr ni qi ini
   const int* mat_flags;     // [n_mat] bit0: k != 0 at some wavelength
+  const unsigned* lossy_word;  // bit t: layer type t absorbs (typed kernel); bit 31: some material absorbs
   const double2* trig;      // [n_theta] (cos, 1/cos)
   const LayerEntry* layers; // [n_layers]
   const double* sweep_d;    // [gridDim.y] or nullptr
@@ -180,11 +181,13 @@ struct TypeMats {
   int mat[kMaxTypes];
 };
 __global__ void flag_layers_kernel(const LayerEntry* __restrict__ layers, const int* __restrict__ mat_flags, int n,
-                                   LayerEntry* __restrict__ out, const TypeMats tm, unsigned* __restrict__ lossy_types) {
+                                   int n_mat, LayerEntry* __restrict__ out, const TypeMats tm,
+                                   unsigned* __restrict__ lossy_types) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) {  // bit t: the material of layer type t absorbs (typed kernel)
     unsigned m = 0;
     for (int t = 0; t < tm.n; ++t) m |= (mat_flags[tm.mat[t]] != 0 ? 1u : 0u) << t;
+    for (int i = 0; i < n_mat; ++i) m |= (mat_flags[i] != 0 ? 1u : 0u) << 31;  // any absorbing material at all
     *lossy_types = m;
   }
   if (j >= n) return;
@@ -279,7 +282,58 @@ tmm_chain_kernel(const GridParams prm) {
   if constexpr (SEG) init_identity<NPOL>(st);
   else init_exit_columns<NPOL, NC>(st, exit_row.nr, exit_row.ni, ct, prm.pol_first);
 
-  {
+  bool done = false;
+  if constexpr (SEG) {
+    if (!(__ldg(prm.lossy_word) >> 31)) {
+      // Every layer lossless: M_j = [[c, -i be], [-i al, c]] with real c, al, be, and a product of such matrices keeps
+      // the pattern [[real, i real], [i real, real]] -- the segment product is four real numbers per polarisation
+      // (column 0 = (a, i w), column 1 = (i u, b)), half the arithmetic of the general complex columns, bit for bit
+      // the same values (the general path multiplies the structural zeros).
+      double a[NPOL], w[NPOL], u[NPOL], b[NPOL];
+      int ke[NPOL];
+#pragma unroll
+      for (int pp = 0; pp < NPOL; ++pp) { a[pp] = 1.0; w[pp] = 0.0; u[pp] = 0.0; b[pp] = 1.0; ke[pp] = 0; }
+      int j = j_hi - 1;
+      while (j >= j_lo) {
+        const int j_stop = max(j - kRenormEvery, j_lo - 1);
+        for (; j > j_stop; --j) {
+          const LayerEntry le = lay[j];
+          const double d = (j == prm.sweep_layer) ? d_sweep : le.d;
+          double qr, nr, inr;
+          opt_row_real(le.mat, qr, nr, inr);
+          const RealLayer<NPOL> m = build_real_layer<NPOL>(qr, nr, inr, d, ct, ict, prm.pol_first);
+#pragma unroll
+          for (int pp = 0; pp < NPOL; ++pp) {
+            const double a0 = a[pp], w0 = w[pp], u0 = u[pp], b0 = b[pp];
+            a[pp] = fma(m.c, a0, m.be[pp] * w0);
+            w[pp] = fma(m.c, w0, -(m.al[pp] * a0));
+            u[pp] = fma(m.c, u0, -(m.be[pp] * b0));
+            b[pp] = fma(m.c, b0, m.al[pp] * u0);
+          }
+        }
+#pragma unroll
+        for (int pp = 0; pp < NPOL; ++pp) {  // exact power-of-two rescale, as renormalise()
+          unsigned mh = (unsigned)hi_word(a[pp]) & 0x7fffffffu;
+          mh = max(mh, (unsigned)hi_word(w[pp]) & 0x7fffffffu);
+          mh = max(mh, (unsigned)hi_word(u[pp]) & 0x7fffffffu);
+          mh = max(mh, (unsigned)hi_word(b[pp]) & 0x7fffffffu);
+          int e = (int)(mh >> 20) - 1023;
+          e = e > 1000 ? 1000 : (e < -1000 ? 0 : e);
+          const double sc = from_words((1023 - e) << 20, 0);
+          a[pp] *= sc; w[pp] *= sc; u[pp] *= sc; b[pp] *= sc;
+          ke[pp] += e;
+        }
+      }
+#pragma unroll
+      for (int pp = 0; pp < NPOL; ++pp) {
+        st.v[pp][0][0] = a[pp]; st.v[pp][0][1] = 0.0; st.v[pp][0][2] = 0.0; st.v[pp][0][3] = w[pp];
+        st.v[pp][1][0] = 0.0; st.v[pp][1][1] = u[pp]; st.v[pp][1][2] = b[pp]; st.v[pp][1][3] = 0.0;
+        st.kexp[pp] = ke[pp];
+      }
+      done = true;
+    }
+  }
+  if (!done) {
     int j = j_hi - 1;
     while (j >= j_lo) {
       const int j_stop = max(j - kRenormEvery, j_lo - 1);
