@@ -127,8 +127,10 @@ def algorithmic_flops(w, prep, n_pol, cse=True, power=True):
     epilogue.  NOT counted: sincos / exp evaluations, rescaling, address arithmetic.
       real (lossless-material) layer:   build 4 + 2/pol,  step 12/pol
       complex layer:                    build 20 + 4/pol, step 28/pol   (28 + 28 per pol)
-    With layer CSE a matrix is built once per distinct (material, thickness); K3 builds only the swept layer per
-    thickness and replaces the chain by two 2-vector dot products (28 flop/pol)."""
+    With layer CSE a matrix is built once per distinct (material, thickness).  K3 per thickness: the phase (2 or 4),
+    cos/sin of the complex phase from sincos and cosh/sinh (4, absorbing layer only) and, per polarisation, the two
+    2-term sums M00, M10 (2 x 14 complex, 2 x 6 real), |.|^2 of both (6) and R, T, A (5).  K2 carries both columns of
+    a segment product; for an all-lossless stack they are four reals (12 flop per layer and polarisation)."""
     lossy = (prep["mat_k"] != 0).any(dim=1).cpu().numpy()
     mats = np.asarray(prep["layer_mat"])
     ds = np.asarray(prep["layer_d"])
@@ -138,17 +140,18 @@ def algorithmic_flops(w, prep, n_pol, cse=True, power=True):
     epilogue = 30 * n_pol
     if w.sweep_d is not None and len(w.sweep_d) >= 4:
         m = mats[w.sweep_layer]
-        per_thread = build(m) + step(m) + 28 * n_pol + epilogue  # per (wavelength, theta, thickness)
+        per_thread = (8 + 39 * n_pol) if lossy[m] else (2 + 23 * n_pol)  # per (wavelength, theta, thickness)
         kind = "K3 sweep (prefix/suffix amortised over the chunk, not counted)"
     else:
         n_types = len({(int(mats[j]), float(ds[j])) for j in interior})
         typed = cse and 0 < n_types <= 8 and len(interior) >= 2 * n_types and w.interior_layers < 128 * 16
         cols = 1
         if w.interior_layers >= 128 and len(w.wl) * len(w.theta) < 148 * 512:
-            cols, typed = 2, False  # K2 segments carry both columns
+            # K2 segments carry both columns; for an all-lossless stack they are four reals = one column's worth
+            cols, typed = (1 if not lossy[mats[interior]].any() else 2), False
         builds = {(int(mats[j]), float(ds[j])): build(mats[j]) for j in interior} if typed else None
         steps = cols * sum(step(mats[j]) for j in interior)
-        kind = "K1 typed (layer CSE)" if typed else ("K2 segmented" if cols == 2 else "K1 untyped")
+        kind = "K1 typed (layer CSE)" if typed else ("K2 segmented" if (w.interior_layers >= 128 and len(w.wl) * len(w.theta) < 148 * 512) else "K1 untyped")
         if typed and power:
             # run-length ops as the host builds them; a lossless pair repeated k >= 3 times costs per polarisation:
             # period matrix 12 + (k - 2) recurrence FMAs * 2 + closed form 6 + one real-structured step 12
