@@ -320,7 +320,7 @@ def run_ours(args):
     ablation = None
     if args.workload == "c2" and flags == 0:
         ablation = {}
-        for name, fl in (("layer_by_layer_pairs", 128), ("no_layer_cse", 128 | 16)):
+        for name, fl in (("layer_by_layer_pairs", 128), ("no_layer_cse", 128 | 16), ("pol_degenerate_opt_in", 1024)):
             for _ in range(3):
                 eng.eval_prepared(prep, pols=pols, out=out, flags=fl)
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
@@ -337,7 +337,10 @@ def run_ours(args):
             ablation[name] = {"value": points_rank * world * 20 / float(t_ab.item()), "ms_per_step": float(t_ab.item()) / 20 * 1e3}
         eng.eval_prepared(prep, pols=pols, out=out, flags=flags)  # leave the default path's results in `out`
         ablation["note"] = ("layer_by_layer_pairs: PST_FLAG_NO_PERIODIC_POWER (every layer applied one by one, cached "
-                            "matrices); no_layer_cse: additionally rebuild every layer matrix (sincos per layer)")
+                            "matrices); no_layer_cse: additionally rebuild every layer matrix (sincos per layer); "
+                            "pol_degenerate_opt_in: PST_FLAG_POL_DEGENERATE -- NOT the default and not part of `value`: "
+                            "the reference's model makes s and p the same function (similarity transform), so one chain "
+                            "is computed and written to both planes")
 
     # ---- e2e: the plugin-style call with HOST buffers (pinned), H2D of the inputs and D2H of R, T, A in the timed region
     mat_n_h = prep["mat_n"].cpu().pin_memory()

@@ -64,6 +64,13 @@ extern "C" {
                                                  polynomials, layer matrices and the chain run in fp32 with the two
                                                  polarisations packed in f32x2 registers; inputs/outputs stay fp64.
                                                  Point kernel without layer CSE; not valid with M */
+#define PST_FLAG_POL_DEGENERATE (1u << 10)     /* opt-in: compute the s-wave chain only and write it to both polarisation
+                                                 planes.  In the reference's model (same theta in every layer, tm.py:209,
+                                                 212,270) the p-wave matrices are a similarity transform of the s-wave
+                                                 ones, M_p = L M_s L^-1 with L = diag(1, 1/cos^2 theta), and D_p = cos(theta)
+                                                 L D_s, so R and T are the same function of the inputs for both
+                                                 polarisations; the reference's two results differ only by their
+                                                 rounding.  Needs pol_mask = S | P; not valid with M */
 #define PST_FLAG_NO_LAYER_CSE (1u << 4)       /* rebuild the matrix of every layer even when layers repeat (ablation;
                                                  results are bit-identical with and without) */
 

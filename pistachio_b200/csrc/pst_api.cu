@@ -235,6 +235,8 @@ int validate_grid(const pst_grid_args* a, const char* who) {
   if ((a->flags & PST_FLAG_FORCE_POINT_KERNEL) && (a->flags & PST_FLAG_FORCE_DEEP_KERNEL))
     return fail(PST_E_INVALID, w + ": contradictory kernel flags");
   if ((a->flags & PST_FLAG_MULTICAST_OUT) && a->M) return fail(PST_E_INVALID, w + ": PST_FLAG_MULTICAST_OUT does not cover the matrix output M");
+  if ((a->flags & PST_FLAG_POL_DEGENERATE) && (a->M || a->pol_mask != (PST_POL_S | PST_POL_P)))
+    return fail(PST_E_INVALID, w + ": PST_FLAG_POL_DEGENERATE needs pol_mask = S | P and no matrix output");
   if ((a->flags & PST_FLAG_FP32) && a->M) return fail(PST_E_INVALID, w + ": PST_FLAG_FP32 does not cover the matrix output M");
   if ((a->flags & PST_FLAG_NUMERIC_DET) && !a->M) return fail(PST_E_INVALID, w + ": PST_FLAG_NUMERIC_DET needs the matrix output M");
   for (int j = 0; j < a->n_layers; ++j)
@@ -334,7 +336,7 @@ int run_prep(pst_handle_t h, const pst_grid_args* a, const double* wl, const dou
 }
 
 struct ChainPlan {
-  int npol, ncol, W, PB, tl_rows, opt_row_bytes, type_stride;
+  int npol, npol_out, ncol, W, PB, tl_rows, opt_row_bytes, type_stride;
   bool so, sl, seg, typed;
   size_t smem;
   ChainKernel fn;
@@ -342,7 +344,8 @@ struct ChainPlan {
 };
 
 int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPlan* pl) {
-  pl->npol = __builtin_popcount(a->pol_mask);
+  pl->npol_out = __builtin_popcount(a->pol_mask);
+  pl->npol = (a->flags & PST_FLAG_POL_DEGENERATE) ? 1 : pl->npol_out;  // polarisations the kernel steps
   pl->ncol = a->M ? 2 : 1;
   const int Li = a->n_layers - 2;
   const long long threads1 = (long long)n_wl_launch * a->n_theta * a->n_sweep;
@@ -457,7 +460,8 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
   prm.use_bulk = (a->flags & PST_FLAG_NO_BULK_COPY) ? 0 : 1;
   const long long nblk = (prm.points + pl.PB - 1) / pl.PB;
   if (nblk > 0x7fffffffLL) return fail(PST_E_INVALID, "pst_eval_grid: too many blocks");
-  const size_t per_sweep = (size_t)pl.npol * (size_t)prm.points;
+  prm.pol_dup = (a->flags & PST_FLAG_POL_DEGENERATE) ? 1 : 0;
+  const size_t per_sweep = (size_t)pl.npol_out * (size_t)prm.points;
   for (int s0 = 0; s0 < a->n_sweep; s0 += 65535) {
     const int ns = std::min(65535, a->n_sweep - s0);
     prm.sweep_d = sweep_d_dev ? sweep_d_dev + s0 : nullptr;
@@ -548,7 +552,7 @@ bool use_sweep_kernel(const pst_grid_args* a) {
 // K3 launch for wavelengths [il0, il0 + n_wl_launch): outputs address the window's first element.
 int launch_sweep(pst_handle_t h, const pst_grid_args* a, int il0, int n_wl_launch, const double* sweep_d_dev, double* R,
                  double* T, double* A, cudaStream_t st) {
-  const int npol = __builtin_popcount(a->pol_mask);
+  const int npol = (a->flags & PST_FLAG_POL_DEGENERATE) ? 1 : __builtin_popcount(a->pol_mask);
   const int PB = 128;
   GridParams prm;
   std::memset(&prm, 0, sizeof(prm));
@@ -558,6 +562,7 @@ int launch_sweep(pst_handle_t h, const pst_grid_args* a, int il0, int n_wl_launc
   prm.n_layers = a->n_layers;
   prm.sweep_layer = a->sweep_layer;
   prm.pol_first = (a->pol_mask & PST_POL_S) ? 0 : 1;
+  prm.pol_dup = (a->flags & PST_FLAG_POL_DEGENERATE) ? 1 : 0;
   prm.tl_rows = std::min(n_wl_launch, (PB - 1) / a->n_theta + 2);
   prm.opt_row_bytes = a->n_mat * 48 + ((a->n_mat % 2 == 0) ? 16 : 0);
   prm.il0 = il0;

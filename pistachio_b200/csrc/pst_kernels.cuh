@@ -56,6 +56,8 @@ struct GridParams {
   double* T;
   double* A;
   double* M;
+  int pol_dup;              // 1: one polarisation is computed and written to both polarisation planes
+                            // (PST_FLAG_POL_DEGENERATE: in the reference's model s and p are the same function)
   int n_peers;              // > 0: results go to these peer-mapped buffers instead of R, T, A (pst_peer_outputs)
   double* peer_R[8];
   double* peer_T[8];
@@ -81,7 +83,14 @@ __device__ __forceinline__ void store_result(double* p, double v, bool multicast
 // One spectral point's R, T, A to wherever the call wants them: the local arrays (plain or multicast stores) or, with
 // pst_peer_outputs, one unicast copy per listed GPU over NVLink (the pointer lists sit in the constant bank).
 template <bool STREAMING>
+__device__ __forceinline__ void store_point_once(const GridParams& prm, size_t o, double R, double T, double A);
+template <bool STREAMING>
 __device__ __forceinline__ void store_point(const GridParams& prm, size_t o, double R, double T, double A) {
+  store_point_once<STREAMING>(prm, o, R, T, A);
+  if (prm.pol_dup) store_point_once<STREAMING>(prm, o + (size_t)prm.points, R, T, A);  // the other polarisation's plane
+}
+template <bool STREAMING>
+__device__ __forceinline__ void store_point_once(const GridParams& prm, size_t o, double R, double T, double A) {
   if (prm.n_peers > 0) {
     for (int i = 0; i < prm.n_peers; ++i) {
       if (prm.peer_R[i]) __stcs(prm.peer_R[i] + o, R);
@@ -422,7 +431,7 @@ tmm_chain_kernel(const GridParams prm) {
   for (int pp = 0; pp < NPOL; ++pp) {
     const PointOut r = finish_point<NPOL, NCOL>(fin, pp, in_row.inr, in_row.ini, exit_row.nr, exit_row.ni, ict,
                                                 prm.pol_first, prm.flags);
-    const size_t o = ((size_t)sweep * NPOL + pp) * plane + (size_t)p;
+    const size_t o = ((size_t)sweep * (NPOL << prm.pol_dup) + pp) * plane + (size_t)p;
     store_point<false>(prm, o, r.R, r.T, r.A);
     if constexpr (NCOL == 2) {
       if (prm.M) {
@@ -576,7 +585,7 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
 #pragma unroll
   for (int pp = 0; pp < NPOL; ++pp) {
     const PointOut r = finish_point<NPOL, NCOL>(st, pp, in1.x, in2.y, nfr, nfi, ict, prm.pol_first, prm.flags);
-    const size_t o = ((size_t)blockIdx.y * NPOL + pp) * plane + (size_t)p;
+    const size_t o = ((size_t)blockIdx.y * (NPOL << prm.pol_dup) + pp) * plane + (size_t)p;
     store_point<false>(prm, o, r.R, r.T, r.A);
     if constexpr (NCOL == 2) {
       if (prm.M) {
@@ -638,7 +647,7 @@ __device__ __forceinline__ void sweep_loop(const GridParams& prm, const SweepCon
         __stcs(pA, (1.0 - R) - T);
         pR += plane; pT += plane; pA += plane;
       } else {
-        store_point<true>(prm, ((size_t)sw * NPOL + pp) * plane + (size_t)p, R, T, (1.0 - R) - T);
+        store_point<true>(prm, ((size_t)sw * (NPOL << prm.pol_dup) + pp) * plane + (size_t)p, R, T, (1.0 - R) - T);
       }
     }
     d = d_next;
@@ -772,7 +781,7 @@ tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
   for (int pp = 0; pp < NPOL; ++pp) {
     kc.al0[pp] = al0[pp]; kc.al1[pp] = al1[pp]; kc.be0[pp] = be0[pp]; kc.be1[pp] = be1[pp]; kc.kfix[pp] = kfix[pp];
   }
-  const bool fast = prm.R && prm.T && prm.A && prm.n_peers == 0 && !(prm.flags & kFlagMulticastOut);
+  const bool fast = prm.R && prm.T && prm.A && prm.n_peers == 0 && !(prm.flags & kFlagMulticastOut) && !prm.pol_dup;
   if (s_lossless) {
     if (fast) sweep_loop<NPOL, true, true>(prm, kc, s_begin, s_end, p);
     else sweep_loop<NPOL, true, false>(prm, kc, s_begin, s_end, p);

@@ -373,6 +373,35 @@ def test_peer_output_lists_write_every_listed_buffer(eng, ref_cases):
         eng.eval_grid(*args, out_ptrs={"R": [1] * 9, "T": [], "A": []})
 
 
+def test_polarisation_degeneracy_flag(eng, ref_cases):
+    """PST_FLAG_POL_DEGENERATE: in the reference's model M_p = L M_s L^-1 (L = diag(1, 1/cos^2 theta)) and
+    D_p = cos(theta) L D_s, so R and T are the same function for both polarisations; the flag computes the s chain once
+    and writes both planes.  The p plane must still pass the parity rule against the REFERENCE's p values."""
+    DEG = 1 << 10
+    for name in ("c1", "c2_sub", "c3_sub_d0", "c4_sub"):
+        c = ref_cases[name]
+        out = run_case(eng, c, flags=DEG)
+        base = run_case(eng, c)
+        assert np.array_equal(out["T"][0][0], out["T"][0][1]) and np.array_equal(out["R"][0][0], out["R"][0][1])
+        assert np.array_equal(out["T"][0][0], base["T"][0][0]) and np.array_equal(out["R"][0][0], base["R"][0][0])
+        rep = parity.compare_grid(name + "/deg", out["T"][0], out["R"][0], c["wl"], list(c["n"]), list(c["d"]), c["theta"],
+                                  c["T"], c["R"], got_A=out["A"][0])
+        rep.check(max_loose_fraction=0.05)
+    # thickness sweeps (K3) and the refusal cases
+    c = ref_cases["c1"]
+    n = np.asarray(c["n"])
+    args = (c["wl"], c["theta"], n.real, n.imag, list(range(n.shape[0])), list(c["d"]))
+    sw = np.linspace(15.0, 25.0, 9)
+    a = eng.eval_grid(*args, POLS, sweep_layer=2, sweep_d=sw, flags=DEG).numpy()
+    b = eng.eval_grid(*args, POLS, sweep_layer=2, sweep_d=sw).numpy()
+    assert np.array_equal(a["T"][:, 0], b["T"][:, 0]) and np.array_equal(a["T"][:, 1], a["T"][:, 0])
+    assert np.abs(a["T"][:, 1] - b["T"][:, 1]).max() <= 1e-12
+    with pytest.raises(ValueError):
+        eng.eval_grid(*args, ("s-wave",), flags=DEG)
+    with pytest.raises(ValueError):
+        eng.eval_grid(*args, POLS, flags=DEG, want_matrix=True)
+
+
 # ------------------------------------------------------------------------------------------------ optional fp32 mode
 FP32 = 1 << 9  # PST_FLAG_FP32
 
