@@ -156,13 +156,28 @@ def algorithmic_flops(w, prep, n_pol, cse=True, power=True):
             # run-length ops as the host builds them; a lossless pair repeated k >= 3 times costs per polarisation:
             # period matrix 12 + (k - 2) recurrence FMAs * 2 + closed form 6 + one real-structured step 12
             seq = [(int(mats[j]), float(ds[j])) for j in reversed(interior)]
-            steps, i = 0, 0
+
+            def repeats(at):
+                k = 1
+                while at + 2 * k + 1 < len(seq) and seq[at + 2 * k] == seq[at] and seq[at + 2 * k + 1] == seq[at + 1]:
+                    k += 1
+                return k
+
+            steps, i, prev_power = 0, 0, None
             while i < len(seq):
                 if i + 1 < len(seq):
-                    k = 1
-                    while i + 2 * k + 1 < len(seq) and seq[i + 2 * k] == seq[i] and seq[i + 2 * k + 1] == seq[i + 1]:
-                        k += 1
+                    k = repeats(i)
+                    if k == 1 and i + 2 < len(seq) and repeats(i + 1) >= 2:  # lone layer in front of a periodic run
+                        steps += step(seq[i][0])
+                        i += 1
+                        continue
                     if k >= 3 and not lossy[seq[i][0]] and not lossy[seq[i + 1][0]]:
+                        key = (frozenset((seq[i], seq[i + 1])), k)
+                        if key == prev_power:  # same or mirrored period, same k: the recurrence is shared
+                            steps += n_pol * (12 + 6 + 12)
+                            i += 2 * k
+                            continue
+                        prev_power = key
                         steps += n_pol * (12 + 2 * (k - 2) + 6 + 12)
                     else:
                         steps += k * (step(seq[i][0]) + step(seq[i + 1][0]))
@@ -320,7 +335,8 @@ def run_ours(args):
     ablation = None
     if args.workload == "c2" and flags == 0:
         ablation = {}
-        for name, fl in (("layer_by_layer_pairs", 128), ("no_layer_cse", 128 | 16), ("pol_degenerate_opt_in", 1024)):
+        for name, fl in (("layer_by_layer_pairs", 128), ("no_layer_cse", 128 | 16), ("pol_degenerate_opt_in", 1024),
+                         ("op_interpreter", 2048)):
             for _ in range(3):
                 eng.eval_prepared(prep, pols=pols, out=out, flags=fl)
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
@@ -338,6 +354,8 @@ def run_ours(args):
         eng.eval_prepared(prep, pols=pols, out=out, flags=flags)  # leave the default path's results in `out`
         ablation["note"] = ("layer_by_layer_pairs: PST_FLAG_NO_PERIODIC_POWER (every layer applied one by one, cached "
                             "matrices); no_layer_cse: additionally rebuild every layer matrix (sincos per layer); "
+                            "op_interpreter: PST_FLAG_NO_SHAPE_FASTPATH (the mirror/spacer/mirror program through the general op loop "
+                            "instead of straight-line code; bit-identical); "
                             "pol_degenerate_opt_in: PST_FLAG_POL_DEGENERATE -- NOT the default and not part of `value`: "
                             "the reference's model makes s and p the same function (similarity transform), so one chain "
                             "is computed and written to both planes")

@@ -71,6 +71,9 @@ extern "C" {
                                                  L D_s, so R and T are the same function of the inputs for both
                                                  polarisations; the reference's two results differ only by their
                                                  rounding.  Needs pol_mask = S | P; not valid with M */
+#define PST_FLAG_NO_SHAPE_FASTPATH (1u << 11)  /* run "mirror / spacer / mirror" programs through the general op interpreter
+                                                 of the typed kernel instead of its straight-line form (ablation; results
+                                                 are bit-identical) */
 #define PST_FLAG_NO_LAYER_CSE (1u << 4)       /* rebuild the matrix of every layer even when layers repeat (ablation;
                                                  results are bit-identical with and without) */
 

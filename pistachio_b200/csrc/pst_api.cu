@@ -290,11 +290,21 @@ int sync_layers(pst_handle_t h, const pst_grid_args* a, cudaStream_t st) {
     for (int j = a->n_layers - 2; j >= 1; --j) seq.push_back(cur[j].type);
     const size_t n = seq.size();
     size_t i = 0;
+    auto repeats = [&](size_t at) {  // how often the pair (seq[at], seq[at + 1]) repeats from `at` on
+      int k = 1;
+      while (at + 2 * (size_t)k + 1 < n && seq[at + 2 * k] == seq[at] && seq[at + 2 * k + 1] == seq[at + 1]) ++k;
+      return k;
+    };
     while (i < n) {
       if (i + 1 < n) {
         const int ta = seq[i], tb = seq[i + 1];
-        int k = 1;
-        while (i + 2 * (size_t)k + 1 < n && seq[i + 2 * k] == ta && seq[i + 2 * k + 1] == tb) ++k;
+        const int k = repeats(i);
+        if (k == 1 && i + 2 < n && repeats(i + 1) >= 2) {
+          // a lone layer in front of a periodic run (the spacer of a cavity): keep the run whole
+          ops.push_back(make_int4(ta, -1, 1, 0));
+          i += 1;
+          continue;
+        }
         ops.push_back(make_int4(ta, tb, k, 0));
         i += 2 * (size_t)k;
       } else {
@@ -456,6 +466,15 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
     }
     for (int i = 0; i < tp.n_ops; ++i) tp.ops[i] = h->ops_host[i];
     tp.lossy_types = h->lossy_types.p;
+    // program shape: periodic mirror / spacer / periodic mirror over the same pair of layer types
+    if (tp.n_ops == 3) {
+      const int4 o0 = tp.ops[0], o1 = tp.ops[1], o2 = tp.ops[2];
+      const bool pair_ok = o0.y >= 0 && o0.z >= 3 && o2.y >= 0 && o2.z >= 3 && o0.x != o0.y &&
+                           ((o2.x == o0.x && o2.y == o0.y) || (o2.x == o0.y && o2.y == o0.x));
+      const bool spacer_ok = o1.y < 0 && o1.z == 1 && o1.x != o0.x && o1.x != o0.y;
+      const bool sweep_ok = tp.sweep_type != o0.x && tp.sweep_type != o0.y;
+      if (pair_ok && spacer_ok && sweep_ok) tp.shape = 1;
+    }
   }
   prm.use_bulk = (a->flags & PST_FLAG_NO_BULK_COPY) ? 0 : 1;
   const long long nblk = (prm.points + pl.PB - 1) / pl.PB;

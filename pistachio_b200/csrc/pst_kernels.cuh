@@ -111,6 +111,8 @@ struct TypedPlan {
   int sweep_type;           // type whose thickness is sweep_d[blockIdx.y]; -1: none
   int mat_first, mat_last;  // materials of the incidence and the exit medium
   int type_stride;          // bytes of layer-matrix cache per thread (odd multiple of 16: conflict-free LDS.128)
+  int shape;                // 1: the program is [power(A, B, k1), single C, power({A, B}, k2)] -- a spacer between two
+                            // periodic mirrors (DBR microcavity); the kernel then runs it as straight-line code
   int type_mat[kMaxTypes];
   double type_d[kMaxTypes];
   int4 ops[kMaxOps];        // (type A, type B or -1, repeat count, 0), in application order (exit side first)
@@ -474,109 +476,168 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   const double2 ex0 = __ldg(optp + tp.mat_last * 3), ex1 = __ldg(optp + tp.mat_last * 3 + 1);
   const double nfr = ex0.y, nfi = ex1.y;
 
-  // ---- build each distinct layer matrix once
-  unsigned char* my_types = smem_raw + (size_t)threadIdx.x * tp.type_stride;
-  int* my_sc = reinterpret_cast<int*>(my_types + tp.n_types * kTypeRecBytes);
-  unsigned m_hi = 0;
-  {
-    double2 ra = __ldg(optp + tp.type_mat[0] * 3);
-    for (int t = 0; t < tp.n_types; ++t) {
-      const double2* row = optp + tp.type_mat[t] * 3;
-      const double2 a = ra, b = __ldg(row + 1);  // (q.re, n.re), (1/n).re, n.im): same cache line as a
-      if (t + 1 < tp.n_types) ra = __ldg(optp + tp.type_mat[t + 1] * 3);  // next type's line is in flight during the build
-      const double d = (t == tp.sweep_type) ? d_sweep : tp.type_d[t];
-      const bool lossy = (lossy_mask >> t) & 1u;
-      TypeRegs<NPOL> tmp;
-      if (!lossy) {
-        tmp.set_real(build_real_layer<NPOL>(a.x, a.y, b.x, d, ct, ict, prm.pol_first));
-      } else {
-        const double2 c = __ldg(row + 2);
-        OptRow o;
-        o.qr = a.x; o.nr = a.y; o.inr = b.x; o.ni = b.y; o.qi = c.x; o.ini = c.y;
-        tmp.set_cplx(build_cplx_layer<NPOL>(o, d, ct, ict, prm.pol_first));
-      }
-      const unsigned h = tmp.max_hi(lossy);
-      m_hi = h > m_hi ? h : m_hi;
-      double2* rec = reinterpret_cast<double2*>(my_types + t * kTypeRecBytes);
-      if (!lossy) {
-        rec[0] = make_double2(tmp.a[0], tmp.a[1]);
-        rec[1] = make_double2(tmp.a[2], tmp.a[3]);
-        rec[2] = make_double2(tmp.a[4], 0.0);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) rec[k] = make_double2(tmp.a[2 * k], tmp.a[2 * k + 1]);
-        my_sc[t] = tmp.sc;
-      }
-    }
-  }
-  auto load_type = [&](int t, bool lossy, TypeRegs<NPOL>& out) {
-    const double2* rec = reinterpret_cast<const double2*>(my_types + t * kTypeRecBytes);
-    if (!lossy) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { const double2 v = rec[k]; out.a[2 * k] = v.x; out.a[2 * k + 1] = v.y; }
-      out.sc = 0;
-    } else {
-#pragma unroll
-      for (int k = 0; k < 5; ++k) { const double2 v = rec[k]; out.a[2 * k] = v.x; out.a[2 * k + 1] = v.y; }
-      out.sc = my_sc[t];
-    }
-  };
-
-  // Rescaling interval from the growth bound: after a rescale max|v| < 2 and n layers multiply it by at most G^n,
-  // so n <= 900 / log2 G layers cannot overflow.  Warp-uniform (maximum over the lanes): it sets loop trip counts.
-  // Ordinary mirrors need no rescale inside the chain at all.
-  const int lg = growth_log2(__reduce_max_sync(0xffffffffu, m_hi), lossy_mask != 0);
-  const int every = max(2, min(1024, __float2int_rz(899.5f * __frcp_rn((float)lg)))) & ~1;  // <= 900 / lg, no division
-
   ChainState<NPOL, NC> st;
   init_exit_columns<NPOL, NC>(st, nfr, nfi, ct, prm.pol_first);
-  PairPower<NPOL> S;
-#pragma unroll
-  for (int pp = 0; pp < NPOL; ++pp) { S.sa[pp] = 1.0; S.sb[pp] = 0.0; S.ks[pp] = 0; }
-  int s_lo = -1, s_hi = -1, s_k = -1;  // the period S belongs to
-  int since = 0;                      // layers applied since the last rescale
-  for (int op = 0; op < tp.n_ops; ++op) {
-    const int4 o = tp.ops[op];
-    TypeRegs<NPOL> A, B;
-    const bool la = (lossy_mask >> o.x) & 1u;
-    load_type(o.x, la, A);
-    if (o.y < 0) {
-      for (int k = 0; k < o.z; ++k) {
-        apply_type<NPOL, NC>(st, A, la);
-        if (++since >= every) { renormalise<NPOL, NC>(st); since = 0; }
+
+  // ---- straight-line form of the commonest program: periodic mirror / spacer / periodic mirror (tp.shape == 1, both
+  // mirror layers lossless).  Same functions in the same order as the interpreted form below, so the results are
+  // bit-identical (tested, PST_FLAG_NO_SHAPE_FASTPATH); what goes away is the interpretation: no type records in
+  // shared memory, no loops over types and ops, and the three layer matrices are built in one basic block so that
+  // their sincos chains interleave.
+  bool done = false;
+  if constexpr (NCOL == 1) {
+    const int tA = tp.ops[0].x, tB = tp.ops[0].y, tC = tp.ops[1].x;
+    if (tp.shape == 1 && !(((lossy_mask >> tA) | (lossy_mask >> tB)) & 1u) && !(prm.flags & (128u | 2048u))) {
+      const bool lossyC = (lossy_mask >> tC) & 1u;
+      const double2* rA = optp + tp.type_mat[tA] * 3;
+      const double2* rB = optp + tp.type_mat[tB] * 3;
+      const double2* rC = optp + tp.type_mat[tC] * 3;
+      const double2 a0 = __ldg(rA), a1 = __ldg(rA + 1), b0 = __ldg(rB), b1 = __ldg(rB + 1);
+      const double2 c0 = __ldg(rC), c1 = __ldg(rC + 1), c2 = __ldg(rC + 2);
+      const double dC = (tC == tp.sweep_type) ? d_sweep : tp.type_d[tC];
+      const double xA = layer_phase(a0.x, ct, tp.type_d[tA]), xB = layer_phase(b0.x, ct, tp.type_d[tB]);
+      const double xC = layer_phase(c0.x, ct, dC);
+      double sA, cA, sB, cB, sC, cC;
+      if (sincos_in_fast_range(xA) && sincos_in_fast_range(xB) && sincos_in_fast_range(xC)) {
+        sincos_core(xA, sA, cA);
+        sincos_core(xB, sB, cB);
+        sincos_core(xC, sC, cC);
+      } else {
+        sincos_fast(xA, sA, cA);
+        sincos_fast(xB, sB, cB);
+        sincos_fast(xC, sC, cC);
       }
-      continue;
-    }
-    const bool lb = (lossy_mask >> o.y) & 1u;
-    load_type(o.y, lb, B);
-    if (!la && !lb && o.z >= 3 && !(prm.flags & 128u)) {
-      // a lossless pair repeated k times: closed-form power of the period (Chebyshev identity, pst_chain.cuh).
-      // |U^k entries| <= 2 (2 G^2)^32 G^2 after the recurrence's own rescaling; rescale first only if that times the
-      // current bound 2 G^since could leave the fp64 range
-      if (since * lg + 66 * lg + 40 > 1000) renormalise<NPOL, NC>(st);
-      const int t_lo = min(o.x, o.y), t_hi = max(o.x, o.y);
-      if (t_lo != s_lo || t_hi != s_hi || o.z != s_k) {  // else: same or mirrored period, same trace, same S
-        pair_power_coeffs<NPOL>(A, B, o.z, S);
-        s_lo = t_lo; s_hi = t_hi; s_k = o.z;
+      TypeRegs<NPOL> A, B, C;
+      A.set_real(finish_real_layer<NPOL>(sA, cA, a0.y, a1.x, ct, ict, prm.pol_first));
+      B.set_real(finish_real_layer<NPOL>(sB, cB, b0.y, b1.x, ct, ict, prm.pol_first));
+      if (!lossyC) {
+        C.set_real(finish_real_layer<NPOL>(sC, cC, c0.y, c1.x, ct, ict, prm.pol_first));
+      } else {
+        OptRow o;
+        o.qr = c0.x; o.nr = c0.y; o.inr = c1.x; o.ni = c1.y; o.qi = c2.x; o.ini = c2.y;
+        C.set_cplx(finish_cplx_layer<NPOL>(sC, cC, layer_phase(o.qi, ct, dC), o, ct, ict, prm.pol_first));
       }
-      apply_pair_power<NPOL, NC>(st, A, B, S);
-      renormalise<NPOL, NC>(st);
-      since = 0;
-      continue;
-    }
-    int k = o.z;
-    while (k > 0) {
-      const int n = min(k, max((every - since) / 2, 1));
-      if (!la && !lb) pair_loop<NPOL, NC, false, false>(st, A, B, n);
-      else if (!la) pair_loop<NPOL, NC, false, true>(st, A, B, n);
-      else if (!lb) pair_loop<NPOL, NC, true, false>(st, A, B, n);
-      else pair_loop<NPOL, NC, true, true>(st, A, B, n);
-      k -= n;
-      since += 2 * n;
-      if (since >= every) { renormalise<NPOL, NC>(st); since = 0; }
+      unsigned mh = A.max_hi(false);
+      mh = max(mh, B.max_hi(false));
+      mh = max(mh, C.max_hi(lossyC));
+      const int lg = growth_log2(__reduce_max_sync(0xffffffffu, mh), lossyC);
+      if (lg <= 12) {  // the interpreted form takes exactly this schedule when 67 lg + 40 <= 1000
+        PairPower<NPOL> S;
+        pair_power_coeffs<NPOL>(A, B, tp.ops[0].z, S);
+        apply_pair_power<NPOL, NC>(st, A, B, S);
+        renormalise<NPOL, NC>(st);
+        apply_type<NPOL, NC>(st, C, lossyC);
+        if (tp.ops[2].z != tp.ops[0].z) pair_power_coeffs<NPOL>(A, B, tp.ops[2].z, S);
+        if (tp.ops[2].x == tA) apply_pair_power<NPOL, NC>(st, A, B, S);
+        else apply_pair_power<NPOL, NC>(st, B, A, S);
+        renormalise<NPOL, NC>(st);
+        done = true;
+      }
     }
   }
-  if (since > 0) renormalise<NPOL, NC>(st);
+  if (!done) {
+    // ---- build each distinct layer matrix once
+    unsigned char* my_types = smem_raw + (size_t)threadIdx.x * tp.type_stride;
+    int* my_sc = reinterpret_cast<int*>(my_types + tp.n_types * kTypeRecBytes);
+    unsigned m_hi = 0;
+    {
+      double2 ra = __ldg(optp + tp.type_mat[0] * 3);
+      for (int t = 0; t < tp.n_types; ++t) {
+        const double2* row = optp + tp.type_mat[t] * 3;
+        const double2 a = ra, b = __ldg(row + 1);  // (q.re, n.re), (1/n).re, n.im): same cache line as a
+        if (t + 1 < tp.n_types) ra = __ldg(optp + tp.type_mat[t + 1] * 3);  // next type's line is in flight during the build
+        const double d = (t == tp.sweep_type) ? d_sweep : tp.type_d[t];
+        const bool lossy = (lossy_mask >> t) & 1u;
+        TypeRegs<NPOL> tmp;
+        if (!lossy) {
+          tmp.set_real(build_real_layer<NPOL>(a.x, a.y, b.x, d, ct, ict, prm.pol_first));
+        } else {
+          const double2 c = __ldg(row + 2);
+          OptRow o;
+          o.qr = a.x; o.nr = a.y; o.inr = b.x; o.ni = b.y; o.qi = c.x; o.ini = c.y;
+          tmp.set_cplx(build_cplx_layer<NPOL>(o, d, ct, ict, prm.pol_first));
+        }
+        const unsigned h = tmp.max_hi(lossy);
+        m_hi = h > m_hi ? h : m_hi;
+        double2* rec = reinterpret_cast<double2*>(my_types + t * kTypeRecBytes);
+        if (!lossy) {
+          rec[0] = make_double2(tmp.a[0], tmp.a[1]);
+          rec[1] = make_double2(tmp.a[2], tmp.a[3]);
+          rec[2] = make_double2(tmp.a[4], 0.0);
+        } else {
+  #pragma unroll
+          for (int k = 0; k < 5; ++k) rec[k] = make_double2(tmp.a[2 * k], tmp.a[2 * k + 1]);
+          my_sc[t] = tmp.sc;
+        }
+      }
+    }
+    auto load_type = [&](int t, bool lossy, TypeRegs<NPOL>& out) {
+      const double2* rec = reinterpret_cast<const double2*>(my_types + t * kTypeRecBytes);
+      if (!lossy) {
+  #pragma unroll
+        for (int k = 0; k < 3; ++k) { const double2 v = rec[k]; out.a[2 * k] = v.x; out.a[2 * k + 1] = v.y; }
+        out.sc = 0;
+      } else {
+  #pragma unroll
+        for (int k = 0; k < 5; ++k) { const double2 v = rec[k]; out.a[2 * k] = v.x; out.a[2 * k + 1] = v.y; }
+        out.sc = my_sc[t];
+      }
+    };
+
+    // Rescaling interval from the growth bound: after a rescale max|v| < 2 and n layers multiply it by at most G^n,
+    // so n <= 900 / log2 G layers cannot overflow.  Warp-uniform (maximum over the lanes): it sets loop trip counts.
+    // Ordinary mirrors need no rescale inside the chain at all.
+    const int lg = growth_log2(__reduce_max_sync(0xffffffffu, m_hi), lossy_mask != 0);
+    const int every = max(2, min(1024, __float2int_rz(899.5f * __frcp_rn((float)lg)))) & ~1;  // <= 900 / lg, no division
+
+    PairPower<NPOL> S;
+  #pragma unroll
+    for (int pp = 0; pp < NPOL; ++pp) { S.sa[pp] = 1.0; S.sb[pp] = 0.0; S.ks[pp] = 0; }
+    int s_lo = -1, s_hi = -1, s_k = -1;  // the period S belongs to
+    int since = 0;                      // layers applied since the last rescale
+    for (int op = 0; op < tp.n_ops; ++op) {
+      const int4 o = tp.ops[op];
+      TypeRegs<NPOL> A, B;
+      const bool la = (lossy_mask >> o.x) & 1u;
+      load_type(o.x, la, A);
+      if (o.y < 0) {
+        for (int k = 0; k < o.z; ++k) {
+          apply_type<NPOL, NC>(st, A, la);
+          if (++since >= every) { renormalise<NPOL, NC>(st); since = 0; }
+        }
+        continue;
+      }
+      const bool lb = (lossy_mask >> o.y) & 1u;
+      load_type(o.y, lb, B);
+      if (!la && !lb && o.z >= 3 && !(prm.flags & 128u)) {
+        // a lossless pair repeated k times: closed-form power of the period (Chebyshev identity, pst_chain.cuh).
+        // |U^k entries| <= 2 (2 G^2)^32 G^2 after the recurrence's own rescaling; rescale first only if that times the
+        // current bound 2 G^since could leave the fp64 range
+        if (since * lg + 66 * lg + 40 > 1000) renormalise<NPOL, NC>(st);
+        const int t_lo = min(o.x, o.y), t_hi = max(o.x, o.y);
+        if (t_lo != s_lo || t_hi != s_hi || o.z != s_k) {  // else: same or mirrored period, same trace, same S
+          pair_power_coeffs<NPOL>(A, B, o.z, S);
+          s_lo = t_lo; s_hi = t_hi; s_k = o.z;
+        }
+        apply_pair_power<NPOL, NC>(st, A, B, S);
+        renormalise<NPOL, NC>(st);
+        since = 0;
+        continue;
+      }
+      int k = o.z;
+      while (k > 0) {
+        const int n = min(k, max((every - since) / 2, 1));
+        if (!la && !lb) pair_loop<NPOL, NC, false, false>(st, A, B, n);
+        else if (!la) pair_loop<NPOL, NC, false, true>(st, A, B, n);
+        else if (!lb) pair_loop<NPOL, NC, true, false>(st, A, B, n);
+        else pair_loop<NPOL, NC, true, true>(st, A, B, n);
+        k -= n;
+        since += 2 * n;
+        if (since >= every) { renormalise<NPOL, NC>(st); since = 0; }
+      }
+    }
+    if (since > 0) renormalise<NPOL, NC>(st);
+  }
   if (!valid) return;
 
   // ---- epilogue

@@ -266,6 +266,45 @@ def test_periodic_power_path(eng, ref_cases):
     np.testing.assert_allclose(a["R"] + a["T"], 1.0, atol=1e-9)
 
 
+def test_cavity_shape_fast_path_is_bit_identical(eng):
+    """Mirror / spacer / mirror programs run as straight-line code in the typed kernel; PST_FLAG_NO_SHAPE_FASTPATH sends
+    them through the general op interpreter.  Same functions in the same order: the results must be equal bit for bit
+    -- symmetric and asymmetric mirrors, mirrored and repeated pair order, absorbing and lossless spacer, one and two
+    polarisations, and a swept spacer thickness."""
+    from pistachio_b200 import workloads
+
+    NOFAST = 1 << 11
+    w = workloads.c2_dbr_cavity(n_wl=96, n_theta=40, pairs=20)
+    prep = eng.prepare_workload(w)
+    mats, ds = list(prep["layer_mat"]), list(prep["layer_d"])
+    zns, mgf2, cav = mats[1], mats[2], mats[41]
+    dz, dm, dc = ds[1], ds[2], ds[41]
+    assert cav not in (zns, mgf2)
+    stacks = {
+        "c2": (mats, ds),
+        "asymmetric": ([mats[0]] + [zns, mgf2] * 12 + [cav] + [mgf2, zns] * 7 + [mats[-1]],
+                       [0.0] + [dz, dm] * 12 + [dc] + [dm, dz] * 7 + [0.0]),
+        "same order": ([mats[0]] + [zns, mgf2] * 9 + [cav] + [zns, mgf2] * 9 + [mats[-1]],
+                       [0.0] + [dz, dm] * 9 + [dc] + [dz, dm] * 9 + [0.0]),
+        "lossless spacer": ([mats[0]] + [zns, mgf2] * 8 + [mats[-1]] + [mgf2, zns] * 8 + [mats[-1]],
+                            [0.0] + [dz, dm] * 8 + [0.4] + [dm, dz] * 8 + [0.0]),
+    }
+    for name, (lm, ld) in stacks.items():
+        for pols in (POLS, ("p-wave",)):
+            a = eng.eval_grid(prep["wl"], prep["theta"], prep["mat_n"], prep["mat_k"], lm, ld, pols).numpy()
+            b = eng.eval_grid(prep["wl"], prep["theta"], prep["mat_n"], prep["mat_k"], lm, ld, pols, flags=NOFAST).numpy()
+            for k in ("R", "T", "A"):
+                assert np.array_equal(a[k], b[k]), (name, pols, k)
+            assert np.isfinite(a["R"]).all() and (a["R"] >= 0).all() and (a["R"] <= 1 + 1e-12).all()
+    lm, ld = stacks["c2"]
+    sw = np.linspace(0.2, 0.5, 3)  # fewer than 4 thicknesses: the typed kernel with blockIdx.y = sweep index
+    a = eng.eval_grid(prep["wl"], prep["theta"], prep["mat_n"], prep["mat_k"], lm, ld, POLS, sweep_layer=41, sweep_d=sw).numpy()
+    b = eng.eval_grid(prep["wl"], prep["theta"], prep["mat_n"], prep["mat_k"], lm, ld, POLS, sweep_layer=41, sweep_d=sw,
+                      flags=NOFAST).numpy()
+    assert np.array_equal(a["T"], b["T"]) and np.array_equal(a["R"], b["R"])
+    assert not np.array_equal(a["T"][0], a["T"][2])
+
+
 def test_resonant_cavity_against_50_digit_truth(eng):
     """Where the tight tolerance cannot hold (a cavity sampled through its resonance), the CUDA result must be at
     least as close to the 50-digit evaluation of the model as the reference is, and parity must hold under the
