@@ -196,11 +196,13 @@ ChainKernel pick_chain(int npol, int ncol, bool so, bool sl, bool seg) {
 }
 
 using TypedKernel = void (*)(const GridParams, const TypedPlan);
-TypedKernel pick_typed(int npol, int ncol) {
-  if (npol == 1 && ncol == 1) return tmm_typed_kernel<1, 1, 5>;
-  if (npol == 1 && ncol == 2) return tmm_typed_kernel<1, 2, 4>;
-  if (npol == 2 && ncol == 1) return tmm_typed_kernel<2, 1, 5>;  // 96 registers; 6 blocks/SM (80) spills and gains < 1 %
-  if (npol == 2 && ncol == 2) return tmm_typed_kernel<2, 2, 3>;
+TypedKernel pick_typed(int npol, int ncol, bool row) {
+#define PST_T(P, C, B) if (npol == P && ncol == C) return row ? tmm_typed_kernel<P, C, B, true> : tmm_typed_kernel<P, C, B, false>;
+  PST_T(1, 1, 5)
+  PST_T(1, 2, 4)
+  PST_T(2, 1, 5)  // 96 registers; 6 blocks/SM (80) spills and is slower
+  PST_T(2, 2, 3)
+#undef PST_T
   return nullptr;
 }
 
@@ -347,7 +349,7 @@ int run_prep(pst_handle_t h, const pst_grid_args* a, const double* wl, const dou
 
 struct ChainPlan {
   int npol, npol_out, ncol, W, PB, tl_rows, opt_row_bytes, type_stride;
-  bool so, sl, seg, typed;
+  bool so, sl, seg, typed, row;
   size_t smem;
   ChainKernel fn;
   TypedKernel fn_typed;
@@ -392,6 +394,7 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
   pl->typed = !pl->seg && !(a->flags & PST_FLAG_NO_LAYER_CSE) && h->n_types > 0 && Li >= 2 * h->n_types &&
               (int)h->ops_host.size() <= kMaxOps;
   pl->type_stride = 0;
+  pl->row = false;
   pl->fn_typed = nullptr;
   if (pl->typed) {
     int units = (h->n_types * (kTypeRecBytes + 4) + 15) / 16;  // records + one exponent int per type
@@ -400,7 +403,10 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
     pl->so = pl->sl = false;
     pl->smem = (size_t)pl->PB * pl->type_stride;
     pl->tl_rows = pl->opt_row_bytes = 0;
-    pl->fn_typed = pick_typed(pl->npol, pl->ncol);
+    // row mode: one wavelength per block row when 128-wide theta tiles waste < 7 % of the lanes
+    const int tiles = (a->n_theta + 127) / 128;
+    pl->row = n_wl_launch <= 65535 && a->n_theta >= 120 && tiles * 128 * 100 <= a->n_theta * 107;
+    pl->fn_typed = pick_typed(pl->npol, pl->ncol, pl->row);
     pl->fn = nullptr;
     if (!pl->fn_typed) return fail(PST_E_INVALID, "pst_eval_grid: no typed kernel variant for this configuration");
     if (pl->smem > 48 * 1024)
@@ -495,6 +501,7 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
       prm.peer_A[i] = a->peers->A[i] ? a->peers->A[i] + (size_t)s0 * per_sweep : nullptr;
     }
     dim3 grid((unsigned)nblk, (unsigned)ns), block(pl.PB, pl.W);
+    if (pl.typed && pl.row) grid = dim3((unsigned)((a->n_theta + 127) / 128), (unsigned)n_wl_launch, (unsigned)ns);
     if (pl.typed) pl.fn_typed<<<grid, block, pl.smem, st>>>(prm, tp);
     else pl.fn<<<grid, block, pl.smem, st>>>(prm);
     PST_CUDA(cudaGetLastError());

@@ -456,25 +456,54 @@ tmm_chain_kernel(const GridParams prm) {
 // no staging, no barrier, no global load on the dependent path.  (History in profiles/: v2 read the cached matrix
 // from shared memory per layer and was LSU-bound; a per-layer switch over register-resident types was latency-bound;
 // v7 staged tables with a bulk copy and fetched ops/flags from global memory -- 18 % of its stall samples.)
-template <int NPOL, int NCOL, int MINB>
+// ROW: the launch is a (theta tile, wavelength, sweep) grid -- a block shares its wavelength, so the wavelength index
+// and every table address are block-uniform (no integer division, nothing to spill); used when theta tiles of 128
+// waste little.  Otherwise blocks tile the flattened (wavelength, theta) index and blockIdx.y is the sweep index.
+template <int NPOL, int NCOL, int MINB, bool ROW>
 __global__ void __launch_bounds__(128, MINB)
 tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NC = NCOL;
   const unsigned npts = (unsigned)prm.points, nth = (unsigned)prm.n_theta;
-  const unsigned praw = blockIdx.x * 128u + threadIdx.x;
-  const bool valid = praw < npts;
-  const unsigned p = valid ? praw : npts - 1u;  // tail lanes shadow the last point (warp-wide reductions below)
-  const int il_loc = (int)(p / nth);
-  const int it = (int)(p - (unsigned)il_loc * nth);
+  bool valid;
+  unsigned p, sweep_idx;
+  int il_loc, it;
+  if constexpr (ROW) {
+    const unsigned itr = blockIdx.x * 128u + threadIdx.x;
+    valid = itr < nth;
+    it = (int)(valid ? itr : nth - 1u);  // tail lanes shadow the last angle (warp-wide reductions below)
+    il_loc = (int)blockIdx.y;
+    p = blockIdx.y * nth + (unsigned)it;
+    sweep_idx = blockIdx.z;
+  } else {
+    const unsigned praw = blockIdx.x * 128u + threadIdx.x;
+    valid = praw < npts;
+    p = valid ? praw : npts - 1u;  // tail lanes shadow the last point
+    il_loc = (int)(p / nth);
+    it = (int)(p - (unsigned)il_loc * nth);
+    sweep_idx = blockIdx.y;
+  }
   const int il = prm.il0 + il_loc;
+  const double2* optp = reinterpret_cast<const double2*>(prm.opt + (size_t)il * prm.n_mat * 6);  // rows of 3 double2
+  // straight-line program (below): its table rows are requested before anything waits on a load
+  const bool shape1 = NCOL == 1 && tp.shape == 1 && !(prm.flags & (128u | 2048u));
+  const int tA = tp.ops[0].x, tB = tp.ops[0].y, tC = tp.ops[1].x;
+  double2 a0, a1, b0, b1, c0, c1, c2;
+  if (shape1) {
+    const double2* rA = optp + tp.type_mat[tA] * 3;
+    const double2* rB = optp + tp.type_mat[tB] * 3;
+    const double2* rC = optp + tp.type_mat[tC] * 3;
+    a0 = __ldg(rA); a1 = __ldg(rA + 1); b0 = __ldg(rB); b1 = __ldg(rB + 1);
+    c0 = __ldg(rC); c1 = __ldg(rC + 1); c2 = __ldg(rC + 2);
+  }
   const double2 tr = __ldg(prm.trig + it);
   const unsigned lossy_mask = __ldg(tp.lossy_types);
-  const double d_sweep = prm.sweep_d ? __ldg(prm.sweep_d + blockIdx.y) : 0.0;
+  const double d_sweep = prm.sweep_d ? __ldg(prm.sweep_d + sweep_idx) : 0.0;
   const double ct = tr.x, ict = tr.y;
-  const double2* optp = reinterpret_cast<const double2*>(prm.opt + (size_t)il * prm.n_mat * 6);  // rows of 3 double2
   const double2 ex0 = __ldg(optp + tp.mat_last * 3), ex1 = __ldg(optp + tp.mat_last * 3 + 1);
   const double nfr = ex0.y, nfi = ex1.y;
+  const double2* in_row = optp + tp.mat_first * 3;  // incidence medium: (1/n).re, (1/n).im for the epilogue
+  double2 in1, in2;
 
   ChainState<NPOL, NC> st;
   init_exit_columns<NPOL, NC>(st, nfr, nfi, ct, prm.pol_first);
@@ -486,14 +515,8 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   // their sincos chains interleave.
   bool done = false;
   if constexpr (NCOL == 1) {
-    const int tA = tp.ops[0].x, tB = tp.ops[0].y, tC = tp.ops[1].x;
-    if (tp.shape == 1 && !(((lossy_mask >> tA) | (lossy_mask >> tB)) & 1u) && !(prm.flags & (128u | 2048u))) {
+    if (shape1 && !(((lossy_mask >> tA) | (lossy_mask >> tB)) & 1u)) {
       const bool lossyC = (lossy_mask >> tC) & 1u;
-      const double2* rA = optp + tp.type_mat[tA] * 3;
-      const double2* rB = optp + tp.type_mat[tB] * 3;
-      const double2* rC = optp + tp.type_mat[tC] * 3;
-      const double2 a0 = __ldg(rA), a1 = __ldg(rA + 1), b0 = __ldg(rB), b1 = __ldg(rB + 1);
-      const double2 c0 = __ldg(rC), c1 = __ldg(rC + 1), c2 = __ldg(rC + 2);
       const double dC = (tC == tp.sweep_type) ? d_sweep : tp.type_d[tC];
       const double xA = layer_phase(a0.x, ct, tp.type_d[tA]), xB = layer_phase(b0.x, ct, tp.type_d[tB]);
       const double xC = layer_phase(c0.x, ct, dC);
@@ -527,6 +550,8 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
         apply_pair_power<NPOL, NC>(st, A, B, S);
         renormalise<NPOL, NC>(st);
         apply_type<NPOL, NC>(st, C, lossyC);
+        in1 = __ldg(in_row + 1);  // requested here (registers of C are free again), used in the epilogue
+        in2 = __ldg(in_row + 2);
         if (tp.ops[2].z != tp.ops[0].z) pair_power_coeffs<NPOL>(A, B, tp.ops[2].z, S);
         if (tp.ops[2].x == tA) apply_pair_power<NPOL, NC>(st, A, B, S);
         else apply_pair_power<NPOL, NC>(st, B, A, S);
@@ -637,16 +662,17 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
       }
     }
     if (since > 0) renormalise<NPOL, NC>(st);
+    in1 = __ldg(in_row + 1);
+    in2 = __ldg(in_row + 2);
   }
   if (!valid) return;
 
   // ---- epilogue
-  const double2 in1 = __ldg(optp + tp.mat_first * 3 + 1), in2 = __ldg(optp + tp.mat_first * 3 + 2);
   const size_t plane = (size_t)prm.points;
 #pragma unroll
   for (int pp = 0; pp < NPOL; ++pp) {
     const PointOut r = finish_point<NPOL, NCOL>(st, pp, in1.x, in2.y, nfr, nfi, ict, prm.pol_first, prm.flags);
-    const size_t o = ((size_t)blockIdx.y * (NPOL << prm.pol_dup) + pp) * plane + (size_t)p;
+    const size_t o = ((size_t)sweep_idx * (NPOL << prm.pol_dup) + pp) * plane + (size_t)p;
     store_point<false>(prm, o, r.R, r.T, r.A);
     if constexpr (NCOL == 2) {
       if (prm.M) {
