@@ -465,8 +465,10 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NC = NCOL;
   const unsigned npts = (unsigned)prm.points, nth = (unsigned)prm.n_theta;
+  const unsigned sweep_idx = ROW ? blockIdx.z : blockIdx.y;
+  const double d_sweep = prm.sweep_d ? __ldg(prm.sweep_d + sweep_idx) : 0.0;
   bool valid;
-  unsigned p, sweep_idx;
+  unsigned p;
   int il_loc, it;
   if constexpr (ROW) {
     const unsigned itr = blockIdx.x * 128u + threadIdx.x;
@@ -474,14 +476,12 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
     it = (int)(valid ? itr : nth - 1u);  // tail lanes shadow the last angle (warp-wide reductions below)
     il_loc = (int)blockIdx.y;
     p = blockIdx.y * nth + (unsigned)it;
-    sweep_idx = blockIdx.z;
   } else {
     const unsigned praw = blockIdx.x * 128u + threadIdx.x;
     valid = praw < npts;
     p = valid ? praw : npts - 1u;  // tail lanes shadow the last point
     il_loc = (int)(p / nth);
     it = (int)(p - (unsigned)il_loc * nth);
-    sweep_idx = blockIdx.y;
   }
   const int il = prm.il0 + il_loc;
   const double2* optp = reinterpret_cast<const double2*>(prm.opt + (size_t)il * prm.n_mat * 6);  // rows of 3 double2
@@ -498,7 +498,6 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   }
   const double2 tr = __ldg(prm.trig + it);
   const unsigned lossy_mask = __ldg(tp.lossy_types);
-  const double d_sweep = prm.sweep_d ? __ldg(prm.sweep_d + sweep_idx) : 0.0;
   const double ct = tr.x, ict = tr.y;
   const double2 ex0 = __ldg(optp + tp.mat_last * 3), ex1 = __ldg(optp + tp.mat_last * 3 + 1);
   const double nfr = ex0.y, nfi = ex1.y;
@@ -548,7 +547,9 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
         PairPower<NPOL> S;
         pair_power_coeffs<NPOL>(A, B, tp.ops[0].z, S);
         apply_pair_power<NPOL, NC>(st, A, B, S);
-        renormalise<NPOL, NC>(st);
+        // the interpreted form rescales here; rescaling is exact, so skipping it changes no bit as long as nothing can
+        // overflow before the final one: both powers and the spacer grow the state by < 2^(2 (66 lg + 40) + lg) <= 2^900
+        if (lg > 6) renormalise<NPOL, NC>(st);
         apply_type<NPOL, NC>(st, C, lossyC);
         in1 = __ldg(in_row + 1);  // requested here (registers of C are free again), used in the epilogue
         in2 = __ldg(in_row + 2);

@@ -161,7 +161,10 @@ PST_HD bool sincos_in_fast_range(double x) { return fabs(x) < 1073741824.0; }  /
 PST_HD void sincos_core(double x, double& s, double& c);
 PST_HD void sincos_fast(double x, double& s, double& c) {
   if (!sincos_in_fast_range(x)) {
-    sincos_slow(x, &s, &c);
+    double ts, tc;  // the address-taken pair lives on the cold branch only: s and c themselves stay in registers
+    sincos_slow(x, &ts, &tc);
+    s = ts;
+    c = tc;
     return;
   }
   sincos_core(x, s, c);
