@@ -77,6 +77,17 @@ extern "C" {
 #define PST_FLAG_NO_LAYER_CSE (1u << 4)       /* rebuild the matrix of every layer even when layers repeat (ablation;
                                                  results are bit-identical with and without) */
 
+#define PST_FLAG_SNELL (1u << 12)              /* refraction mode (additive; the reference has no counterpart -- it keeps
+                                                 the incidence angle in every layer, tm.py:270): theta is the angle in the
+                                                 incidence medium and layer j propagates at its refracted angle,
+                                                 cos(theta_j) = sqrt(1 - (n_0 sin(theta_0) / n_j)^2), complex in absorbing
+                                                 layers and beyond the critical angle; the root of the exit medium is the
+                                                 one whose wave decays.  Same characteristic matrices, t, r, R and
+                                                 T = Re(det M) |t|^2 (tm.py:236-277, 482-486); at normal incidence the
+                                                 results equal the default mode's.  Built on the relations the reference
+                                                 lists in fresnel()/transmission_matrix() (tm.py:730-751).  Excludes
+                                                 PST_FLAG_FP32, PST_FLAG_POL_DEGENERATE and PST_FLAG_FORCE_DEEP_KERNEL. */
+
 typedef struct pst_handle_s* pst_handle_t;
 
 /* ---- lifetime ------------------------------------------------------------------------------------- */

@@ -24,6 +24,8 @@ FLAG_NO_PERIODIC_POWER = 1 << 7
 FLAG_MULTICAST_OUT = 1 << 8
 FLAG_FP32 = 1 << 9
 FLAG_POL_DEGENERATE = 1 << 10
+FLAG_NO_SHAPE_FASTPATH = 1 << 11
+FLAG_SNELL = 1 << 12
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)

@@ -240,6 +240,8 @@ int validate_grid(const pst_grid_args* a, const char* who) {
   if ((a->flags & PST_FLAG_POL_DEGENERATE) && (a->M || a->pol_mask != (PST_POL_S | PST_POL_P)))
     return fail(PST_E_INVALID, w + ": PST_FLAG_POL_DEGENERATE needs pol_mask = S | P and no matrix output");
   if ((a->flags & PST_FLAG_FP32) && a->M) return fail(PST_E_INVALID, w + ": PST_FLAG_FP32 does not cover the matrix output M");
+  if ((a->flags & PST_FLAG_SNELL) && (a->flags & (PST_FLAG_FP32 | PST_FLAG_POL_DEGENERATE | PST_FLAG_FORCE_DEEP_KERNEL)))
+    return fail(PST_E_INVALID, w + ": PST_FLAG_SNELL excludes the fp32, polarisation-degenerate and deep-kernel flags");
   if ((a->flags & PST_FLAG_NUMERIC_DET) && !a->M) return fail(PST_E_INVALID, w + ": PST_FLAG_NUMERIC_DET needs the matrix output M");
   for (int j = 0; j < a->n_layers; ++j)
     if (a->layer_mat[j] < 0 || a->layer_mat[j] >= a->n_mat) return fail(PST_E_INVALID, w + ": layer_mat entry out of range");
@@ -561,6 +563,55 @@ int launch_chain_f32(pst_handle_t h, const pst_grid_args* a, int il0, int n_wl_l
   return PST_OK;
 }
 
+// Refraction mode (PST_FLAG_SNELL): one thread per point, plain layer loop with per-layer refracted angles.
+int launch_snell(pst_handle_t h, const pst_grid_args* a, int il0, int n_wl_launch, const double* sweep_d_dev, double* R,
+                 double* T, double* A, double* M, cudaStream_t st) {
+  const int npol = __builtin_popcount(a->pol_mask);
+  GridParams prm;
+  std::memset(&prm, 0, sizeof(prm));
+  prm.n_wl = a->n_wl;
+  prm.n_theta = a->n_theta;
+  prm.n_mat = a->n_mat;
+  prm.n_layers = a->n_layers;
+  prm.sweep_layer = a->sweep_layer;
+  prm.pol_first = (a->pol_mask & PST_POL_S) ? 0 : 1;
+  prm.pol_mask = a->pol_mask;
+  prm.il0 = il0;
+  prm.flags = a->flags;
+  prm.points = (long long)n_wl_launch * a->n_theta;
+  prm.opt = h->opt.p;
+  prm.mat_flags = h->mat_flags.p;
+  prm.lossy_word = h->lossy_types.p;
+  prm.trig = h->trig.p;
+  prm.layers = h->layers_flagged.p;
+  using SnellKernel = void (*)(const GridParams);
+  SnellKernel fn = nullptr;
+  if (npol == 1) fn = M ? tmm_snell_kernel<1, 2> : tmm_snell_kernel<1, 1>;
+  if (npol == 2) fn = M ? tmm_snell_kernel<2, 2> : tmm_snell_kernel<2, 1>;
+  if (!fn) return fail(PST_E_INVALID, "pst_eval_grid: PST_FLAG_SNELL needs one or two polarisations");
+  const long long nblk = (prm.points + 127) / 128;
+  if (nblk > 0x7fffffffLL) return fail(PST_E_INVALID, "pst_eval_grid: too many blocks");
+  const size_t per_sweep = (size_t)npol * (size_t)prm.points;
+  for (int s0 = 0; s0 < a->n_sweep; s0 += 65535) {
+    const int ns = std::min(65535, a->n_sweep - s0);
+    prm.sweep_d = sweep_d_dev ? sweep_d_dev + s0 : nullptr;
+    prm.R = R ? R + (size_t)s0 * per_sweep : nullptr;
+    prm.T = T ? T + (size_t)s0 * per_sweep : nullptr;
+    prm.A = A ? A + (size_t)s0 * per_sweep : nullptr;
+    prm.M = M ? M + (size_t)s0 * per_sweep * 8 : nullptr;
+    prm.n_peers = a->peers ? a->peers->n_peers : 0;
+    for (int i = 0; i < prm.n_peers; ++i) {
+      prm.peer_R[i] = a->peers->R[i] ? a->peers->R[i] + (size_t)s0 * per_sweep : nullptr;
+      prm.peer_T[i] = a->peers->T[i] ? a->peers->T[i] + (size_t)s0 * per_sweep : nullptr;
+      prm.peer_A[i] = a->peers->A[i] ? a->peers->A[i] + (size_t)s0 * per_sweep : nullptr;
+    }
+    fn<<<dim3((unsigned)nblk, (unsigned)ns), 128, 0, st>>>(prm);
+    PST_CUDA(cudaGetLastError());
+    h->launches += 1;
+  }
+  return PST_OK;
+}
+
 using SweepKernel = void (*)(const GridParams, int, int);
 SweepKernel pick_sweep(int npol, bool so, bool sl) {
 #define PST_S(P, O, L) if (npol == P && so == O && sl == L) return tmm_sweep_kernel<P, O, L>;
@@ -641,6 +692,7 @@ extern "C" int pst_eval_grid(pst_handle_t h, const pst_grid_args* a, void* strea
   cudaStream_t st = (cudaStream_t)stream;
   PST_TRY(sync_layers(h, a, st));
   PST_TRY(run_prep(h, a, a->wl, a->theta, a->cos_theta, a->mat_n, a->mat_k, st));
+  if (a->flags & PST_FLAG_SNELL) return launch_snell(h, a, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, a->M, st);
   if (a->flags & PST_FLAG_FP32) return launch_chain_f32(h, a, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, st);
   if (use_sweep_kernel(a)) return launch_sweep(h, a, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, st);
   ChainPlan pl;
@@ -708,7 +760,9 @@ extern "C" int pst_eval_grid_host(pst_handle_t h, const pst_grid_args* a) {
     ChainPlan pl;
     pst_grid_args loc = *a;
     loc.R = dR; loc.T = dT; loc.A = dA; loc.M = dM;
-    if (loc.flags & PST_FLAG_FP32) {
+    if (loc.flags & PST_FLAG_SNELL) {
+      PST_TRY(launch_snell(h, &loc, (int)l0, (int)cw, a->sweep_d ? d_sw : nullptr, dR, dT, dA, dM, sc));
+    } else if (loc.flags & PST_FLAG_FP32) {
       PST_TRY(launch_chain_f32(h, &loc, (int)l0, (int)cw, a->sweep_d ? d_sw : nullptr, dR, dT, dA, sc));
     } else if (use_sweep_kernel(&loc)) {
       PST_TRY(launch_sweep(h, &loc, (int)l0, (int)cw, d_sw, dR, dT, dA, sc));

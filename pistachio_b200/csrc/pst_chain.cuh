@@ -419,8 +419,8 @@ struct PointOut {
 // Rows of D_0^-1, then t, r, R, T, A for one polarisation                            (tm.py:482-486, 568)
 //   D_0^-1 = 1/2 [[w0, w1], [w0, -w1]]:  s: w0 = 1, w1 = 1/(n_0 cos)    p: w0 = 1/cos, w1 = 1/n_0
 template <int NPOL, int NCOL>
-PST_HD PointOut finish_point(const ChainState<NPOL, NCOL>& fin, int p, double in0r, double in0i, double nfr, double nfi,
-                             double ict, int pol_first, unsigned flags) {
+PST_HD PointOut finish_point_det(const ChainState<NPOL, NCOL>& fin, int p, double in0r, double in0i, double det_re,
+                                 double ict, int pol_first, unsigned flags) {
   const bool is_s = pol_is_s<NPOL>(p, pol_first);
   const double w0 = is_s ? 1.0 : ict;
   const cplx w1 = is_s ? cplx{in0r * ict, in0i * ict} : cplx{in0r, in0i};
@@ -438,8 +438,6 @@ PST_HD PointOut finish_point(const ChainState<NPOL, NCOL>& fin, int p, double in
   const double num = fma(m[0][1].re, m[0][1].re, m[0][1].im * m[0][1].im);  // |M10|^2
   const double iden = 1.0 / den;
   out.R = num * iden;
-  // det M = a_last / a_first = n_f / n_0 for both polarisations (the cos factors cancel)
-  const double det_re = fma(nfr, in0r, -(nfi * in0i));
   out.T = scale_sq(det_re * iden, -fin.kexp[p]);
   if constexpr (NCOL == 2) {
     if (flags & 4u) {
@@ -455,6 +453,105 @@ PST_HD PointOut finish_point(const ChainState<NPOL, NCOL>& fin, int p, double in
   }
   out.A = (1.0 - out.R) - out.T;
   return out;
+}
+
+// Same-angle model of the reference: det M = a_last / a_first = n_f / n_0 for both polarisations (the cos factors cancel)
+template <int NPOL, int NCOL>
+PST_HD PointOut finish_point(const ChainState<NPOL, NCOL>& fin, int p, double in0r, double in0i, double nfr, double nfi,
+                             double ict, int pol_first, unsigned flags) {
+  const double det_re = fma(nfr, in0r, -(nfi * in0i));
+  return finish_point_det<NPOL, NCOL>(fin, p, in0r, in0i, det_re, ict, pol_first, flags);
+}
+
+// ---- refraction mode (PST_FLAG_SNELL) ---------------------------------------------------
+// The reference keeps the incidence angle in every layer.  With Snell refraction the conserved quantity is the
+// tangential index s = n_0 sin(theta_0); in the reference's notation layer j then has
+//   cos(theta_j) = sqrt(1 - s^2 / n_j^2)        (complex in absorbing layers and beyond the critical angle),
+//   phi_j = ((n_j w)(1/c) cos(theta_j)) d_j,    a_j = n_j cos(theta_j) (s)  or  n_j / cos(theta_j) (p),
+//   M_j = [[cos phi, -i sin phi / a], [-i a sin phi, cos phi]]     -- the same characteristic matrix (tm.py:236-277),
+// evaluated by the same operations in the same order as the absorbing-layer path above, so at normal incidence
+// (cos(theta_j) = 1 exactly) the two modes agree bit for bit.  M_j is even in the sign of the root; the exit medium
+// needs the root whose forward wave decays: Im(n cos(theta)) >= 0 (k > 0 absorbs in the reference, tm.py:217-234).
+PST_HD cplx csqrt_principal(cplx w) {
+  const double m = hypot(w.re, w.im);
+  if (m == 0.0) return {0.0, 0.0};
+  const double t = sqrt(0.5 * (m + fabs(w.re)));
+  const double u = 0.5 * w.im / t;
+  if (w.re >= 0.0) return {t, u};
+  return {fabs(u), w.im < 0.0 ? -t : t};
+}
+
+struct SnellAngle {
+  cplx c, ic;  // cos(theta_j), 1 / cos(theta_j)
+  cplx kzn;    // n_j cos(theta_j): normal index, Im >= 0
+};
+
+// s2 = (n_0 sin(theta_0))^2.  An exact zero of the cosine (grazing propagation inside the layer) is nudged so that
+// sin(phi)/a keeps its finite limit.
+PST_HD SnellAngle snell_angle(const OptRow& o, cplx s2) {
+  const cplx n = {o.nr, o.ni}, inv_n = {o.inr, o.ini};
+  const cplx r = cmul(s2, cmul(inv_n, inv_n));
+  SnellAngle g;
+  g.c = csqrt_principal({1.0 - r.re, -r.im});
+  if (g.c.re == 0.0 && g.c.im == 0.0) g.c = {0.0, 1e-150};
+  g.kzn = cmul(n, g.c);
+  if (g.kzn.im < 0.0 || (g.kzn.im == 0.0 && g.kzn.re < 0.0)) {
+    g.c = {-g.c.re, -g.c.im};
+    g.kzn = {-g.kzn.re, -g.kzn.im};
+  }
+  g.ic = crecip(g.c);
+  return g;
+}
+
+template <int NPOL>
+PST_HD CplxLayer<NPOL> build_snell_layer(const OptRow& o, double d, cplx s2, int pol_first) {
+  const SnellAngle g = snell_angle(o, s2);
+  const cplx kx = cmul({o.qr, o.qi}, g.c);  // (n w)(1/c) cos(theta_j)
+  double sx, cx, ch, sh;
+  sincos_fast(mul_rn(kx.re, d), sx, cx);
+  CplxLayer<NPOL> m;
+  m.sc = cosh_sinh_scaled(mul_rn(kx.im, d), ch, sh);
+  m.cphi = {cx * ch, -(sx * sh)};
+  const cplx sphi = {sx * ch, cx * sh};
+  const cplx sn = cmul(sphi, {o.nr, o.ni});
+  const cplx si = cmul(sphi, {o.inr, o.ini});
+#pragma unroll
+  for (int p = 0; p < NPOL; ++p) {
+    const bool is_s = pol_is_s<NPOL>(p, pol_first);
+    const cplx as = cmul(sn, is_s ? g.c : g.ic), is = cmul(si, is_s ? g.ic : g.c);
+    m.m10[p] = {as.im, -as.re};  // -i a sin(phi)
+    m.m01[p] = {is.im, -is.re};  // -i sin(phi) / a
+  }
+  return m;
+}
+
+// Exit-medium columns D_f[:, c] with the refracted angle:  s: (1, +-n_f cos(theta_f))   p: (cos(theta_f), +-n_f)
+template <int NPOL, int NC>
+PST_HD void init_exit_columns_snell(ChainState<NPOL, NC>& st, double nfr, double nfi, const SnellAngle& gf,
+                                    int pol_first) {
+#pragma unroll
+  for (int p = 0; p < NPOL; ++p) {
+    const bool is_s = pol_is_s<NPOL>(p, pol_first);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const double sg = c == 0 ? 1.0 : -1.0;
+      st.v[p][c][0] = is_s ? 1.0 : gf.c.re;
+      st.v[p][c][1] = is_s ? 0.0 : gf.c.im;
+      st.v[p][c][2] = sg * (is_s ? gf.kzn.re : nfr);
+      st.v[p][c][3] = sg * (is_s ? gf.kzn.im : nfi);
+    }
+    st.kexp[p] = 0;
+  }
+}
+
+// Tangential index squared for an incidence medium n_0 at cos(theta_0) = ct, and Re det M = Re(n_f cos(theta_f) /
+// (n_0 cos(theta_0))) (both polarisations; T = Re(det M) |t|^2 as tm.py:486)
+PST_HD cplx snell_s2(double n0r, double n0i, double ct) {
+  const double sin2 = fmax(fma(-ct, ct, 1.0), 0.0);
+  return cscale(cmul({n0r, n0i}, {n0r, n0i}), sin2);
+}
+PST_HD double snell_det_re(const SnellAngle& gf, double in0r, double in0i, double ict) {
+  return fma(gf.kzn.re, in0r, -(gf.kzn.im * in0i)) * ict;
 }
 
 // q, n, 1/n of one (material, wavelength) in the reference's rounding order (tm.py:269-270; numpy divides a

@@ -685,6 +685,66 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   }
 }
 
+// ------------------------------------------------------------------------------------ refraction mode
+// PST_FLAG_SNELL: one thread per spectral point, both polarisations, a plain loop over the
+// layers with the refracted angle of every layer (pst_chain.cuh, build_snell_layer).  Every layer goes through the
+// complex form (beyond the critical angle even a lossless layer has a complex phase).  Tables are read through the
+// read-only path: a warp shares its wavelength when n_theta >= 32, so rows and layer entries are broadcast loads.
+template <int NPOL, int NCOL>
+__global__ void __launch_bounds__(128, 4)
+tmm_snell_kernel(const GridParams prm) {
+  const unsigned npts = (unsigned)prm.points, nth = (unsigned)prm.n_theta;
+  const unsigned praw = blockIdx.x * 128u + threadIdx.x;
+  if (praw >= npts) return;
+  const unsigned p = praw;
+  const int il_loc = (int)(p / nth);
+  const int it = (int)(p - (unsigned)il_loc * nth);
+  const double2 tr = __ldg(prm.trig + it);
+  const double ct = tr.x, ict = tr.y;
+  const int sweep = blockIdx.y;
+  const double d_sweep = prm.sweep_d ? __ldg(prm.sweep_d + sweep) : 0.0;
+  const double2* optp = reinterpret_cast<const double2*>(prm.opt + (size_t)(prm.il0 + il_loc) * prm.n_mat * 6);
+  auto opt_row = [&](int mat) {
+    const double2 a = __ldg(optp + mat * 3), b = __ldg(optp + mat * 3 + 1), c = __ldg(optp + mat * 3 + 2);
+    OptRow r;
+    r.qr = a.x; r.nr = a.y; r.inr = b.x; r.ni = b.y; r.qi = c.x; r.ini = c.y;
+    return r;
+  };
+  const int L = prm.n_layers;
+  const OptRow in_row = opt_row(prm.layers[0].mat), exit_row = opt_row(prm.layers[L - 1].mat);
+  const cplx s2 = snell_s2(in_row.nr, in_row.ni, ct);
+  const SnellAngle gf = snell_angle(exit_row, s2);
+
+  ChainState<NPOL, NCOL> st;
+  init_exit_columns_snell<NPOL, NCOL>(st, exit_row.nr, exit_row.ni, gf, prm.pol_first);
+  int j = L - 2;
+  while (j >= 1) {
+    const int j_stop = max(j - kRenormEvery, 0);
+    for (; j > j_stop; --j) {
+      const int4 raw = __ldg(reinterpret_cast<const int4*>(prm.layers + j));  // {d, mat, type}
+      const double d = (j == prm.sweep_layer) ? d_sweep : __hiloint2double(raw.y, raw.x);
+      apply_cplx_layer<NPOL, NCOL>(st, build_snell_layer<NPOL>(opt_row(raw.z), d, s2, prm.pol_first));
+    }
+    renormalise<NPOL, NCOL>(st);
+  }
+
+  const double det_re = snell_det_re(gf, in_row.inr, in_row.ini, ict);
+  const size_t plane = (size_t)prm.points;
+#pragma unroll
+  for (int pp = 0; pp < NPOL; ++pp) {
+    const PointOut r = finish_point_det<NPOL, NCOL>(st, pp, in_row.inr, in_row.ini, det_re, ict, prm.pol_first, prm.flags);
+    const size_t o = ((size_t)sweep * NPOL + pp) * plane + (size_t)p;
+    store_point<false>(prm, o, r.R, r.T, r.A);
+    if constexpr (NCOL == 2) {
+      if (prm.M) {
+        double4* mo = reinterpret_cast<double4*>(prm.M + o * 8);
+        mo[0] = make_double4(r.M[0], r.M[1], r.M[2], r.M[3]);
+        mo[1] = make_double4(r.M[4], r.M[5], r.M[6], r.M[7]);
+      }
+    }
+  }
+}
+
 // Per-thread constants of a thickness sweep (see tmm_sweep_kernel) and its inner loop.
 template <int NPOL>
 struct SweepConsts {

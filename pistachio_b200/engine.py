@@ -14,7 +14,7 @@ import torch
 
 from . import _cabi
 from ._cabi import (FLAG_FORCE_DEEP_KERNEL, FLAG_FORCE_POINT_KERNEL, FLAG_NO_LAYER_CSE, FLAG_NO_SMEM_STAGING,  # noqa: F401
-                    FLAG_NO_SWEEP_REUSE, FLAG_NUMERIC_DET, POL_P,
+                    FLAG_NO_SWEEP_REUSE, FLAG_NUMERIC_DET, FLAG_SNELL, POL_P,
                     POL_S, GridArgs, check)
 
 S_WAVE = "s-wave"

@@ -18,7 +18,11 @@ Documented differences from the reference (DESIGN.md "Reference quirks"):
   * initialize_struct keeps the reference's degrees-as-radians use of theta_i for
     the per-layer caches (tm.py:461-462); Structure.theta is converted correctly.
 Additive API: Structure.spectrum_grid(...) evaluates whole (pol, wavelength, theta
-[, thickness]) grids in one launch and returns R, T, A.
+[, thickness]) grids in one launch and returns R, T, A.  `Structure.snell = True`
+(default False = the reference's model, which keeps the incidence angle in every
+layer, tm.py:270) switches the Structure-level calls to refraction mode: theta is
+the angle in the incidence medium and every layer propagates at its refracted
+angle (PST_FLAG_SNELL).
 """
 from __future__ import annotations
 
@@ -187,6 +191,10 @@ class Structure:
     """Ordered stack of Layers: index 0 is the incidence medium, -1 the exit medium (tm.py:308-353)."""
 
     strict_reference_cache = False
+    snell = False  # True: Snell refraction per layer (additive; not the reference's model)
+
+    def _flags(self):
+        return _engine.FLAG_SNELL if self.snell else 0
 
     def __init__(self):
         self.layers = []
@@ -319,7 +327,7 @@ class Structure:
             raise np.linalg.LinAlgError("0-dimensional array given. Array must be at least two-dimensional")
         wl, mat_n, mat_k, layer_mat, layer_d = self._stack_on_grid()
         res = _eng().eval_grid(wl, None, mat_n, mat_k, layer_mat, layer_d, (wave_type,),
-                               cos_theta=np.array([np.cos(theta)]), want=(), want_matrix=True)
+                               cos_theta=np.array([np.cos(theta)]), want=(), want_matrix=True, flags=self._flags())
         return _to_numpy(res.M[0, 0, :, 0])
 
     def _chain_cached(self):
@@ -358,7 +366,7 @@ class Structure:
         theta = np.atleast_1d(np.asarray(self.theta if theta is None else theta, dtype=np.float64))
         wl, mat_n, mat_k, layer_mat, layer_d = self._stack_on_grid()
         res = _eng().eval_grid(wl, theta, mat_n, mat_k, layer_mat, layer_d, pols, cos_theta=np.cos(theta),
-                               sweep_layer=sweep_layer, sweep_d=sweep_d, want=want).numpy()
+                               sweep_layer=sweep_layer, sweep_d=sweep_d, want=want, flags=self._flags()).numpy()
         if sweep_d is None:
             res = {k: (v[0] if v is not None else None) for k, v in res.items()}
         return res
@@ -375,7 +383,7 @@ class Structure:
         wl, mat_n, mat_k, layer_mat, layer_d = self._stack_on_grid()
         eng = _eng()
         res = eng.eval_grid(wl, theta, mat_n, mat_k, layer_mat, layer_d, (pol,), cos_theta=np.cos(theta),
-                            sweep_layer=sweep_layer, sweep_d=sweep_d, want=("T",))
+                            sweep_layer=sweep_layer, sweep_d=sweep_d, want=("T",), flags=self._flags())
         nu = 1.0e4 / wl
         h = None if height is None else (float(height) / 100.0 if percent else float(height))
         idx, hts, cnt, spc = eng.find_peaks(res.T[:, 0], height=h, distance=distance, max_peaks=max_peaks, axis=nu,
@@ -405,7 +413,7 @@ class Structure:
         wl, mat_n, mat_k, layer_mat, layer_d = self._stack_on_grid()
         eng = _eng()
         res = eng.eval_grid(wl, theta, mat_n, mat_k, layer_mat, layer_d, (pol,), cos_theta=np.cos(theta),
-                            sweep_layer=sweep_layer, sweep_d=sweep_d, want=("T",))
+                            sweep_layer=sweep_layer, sweep_d=sweep_d, want=("T",), flags=self._flags())
         nu = 1.0e4 / wl
         rev = bool(wl.size > 1 and wl[0] < wl[-1])
         T = res.T[:, 0]

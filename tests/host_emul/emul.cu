@@ -23,6 +23,26 @@ static void run(int n_wl, int n_theta, int L, const double* wl, const double* co
     for (int it = 0; it < n_theta; ++it) {
       const double ct = cos_theta[it], ict = 1.0 / ct;
       ChainState<NPOL, NCOL> fin;
+      if (flags & 4096u) {
+        // refraction mode (PST_FLAG_SNELL): the loop of tmm_snell_kernel
+        const cplx s2 = snell_s2(rows[0].nr, rows[0].ni, ct);
+        const SnellAngle gf = snell_angle(rows[L - 1], s2);
+        init_exit_columns_snell<NPOL, NCOL>(fin, rows[L - 1].nr, rows[L - 1].ni, gf, pol_first);
+        int j = L - 2;
+        while (j >= 1) {
+          const int j_stop = j - 16 > 0 ? j - 16 : 0;
+          for (; j > j_stop; --j) apply_cplx_layer<NPOL, NCOL>(fin, build_snell_layer<NPOL>(rows[j], d[j], s2, pol_first));
+          renormalise<NPOL, NCOL>(fin);
+        }
+        const double det_re = snell_det_re(gf, rows[0].inr, rows[0].ini, ict);
+        for (int p = 0; p < NPOL; ++p) {
+          const PointOut r = finish_point_det<NPOL, NCOL>(fin, p, rows[0].inr, rows[0].ini, det_re, ict, pol_first, flags);
+          const size_t o = ((size_t)p * n_wl + il) * n_theta + it;
+          R[o] = r.R; T[o] = r.T; A[o] = r.A;
+          if (NCOL == 2 && M) for (int k = 0; k < 8; ++k) M[o * 8 + k] = r.M[k];
+        }
+        continue;
+      }
       if (W <= 1 && (flags & 256u)) {
         // typed path with run-length ops and the closed-form power of repeated lossless pairs (what the kernel does
         // by default for periodic stacks): layer types by (n at this wavelength, thickness)
