@@ -305,6 +305,43 @@ def test_cavity_shape_fast_path_is_bit_identical(eng):
     assert not np.array_equal(a["T"][0], a["T"][2])
 
 
+def test_row_mode_launch_is_bit_identical(eng):
+    """Grids with >= 120 angles launch the typed kernel as (theta tile, wavelength, sweep) blocks (one wavelength per
+    block row, ragged last tile) instead of tiling the flattened point index.  Same arithmetic per point: the results
+    must equal, bit for bit, the flattened launch (the same angles evaluated in slices of < 120), the op interpreter,
+    and -- without the closed-form power -- the untyped layer loop; a swept spacer uses blockIdx.z."""
+    from pistachio_b200 import workloads
+    from pistachio_b200._cabi import FLAG_NO_LAYER_CSE, FLAG_NO_PERIODIC_POWER
+
+    NOFAST = 1 << 11
+    for n_theta in (250, 128, 385):
+        w = workloads.c2_dbr_cavity(n_wl=24, n_theta=n_theta, pairs=20)
+        prep = eng.prepare_workload(w)
+        a = eng.eval_prepared(prep).numpy()
+        b = eng.eval_prepared(prep, flags=NOFAST).numpy()
+        c = eng.eval_prepared(prep, flags=FLAG_NO_PERIODIC_POWER).numpy()
+        d = eng.eval_prepared(prep, flags=FLAG_NO_PERIODIC_POWER | FLAG_NO_LAYER_CSE).numpy()
+        for k in ("R", "T", "A"):
+            assert np.array_equal(a[k], b[k]), (n_theta, k)
+            assert np.array_equal(c[k], d[k]), (n_theta, k)
+        assert np.isfinite(a["R"]).all() and np.isfinite(a["T"]).all()
+        th = np.asarray(prep["theta"].cpu() if hasattr(prep["theta"], "cpu") else prep["theta"])
+        for lo in range(0, n_theta, 84):
+            sl = eng.eval_grid(prep["wl"], th[lo:lo + 84], prep["mat_n"], prep["mat_k"], list(prep["layer_mat"]),
+                               list(prep["layer_d"])).numpy()
+            for k in ("R", "T", "A"):
+                assert np.array_equal(a[k][..., lo:lo + 84], sl[k]), (n_theta, lo, k)
+    lm, ld = list(prep["layer_mat"]), list(prep["layer_d"])
+    sw = np.linspace(0.2, 0.5, 3)
+    a = eng.eval_grid(prep["wl"], th, prep["mat_n"], prep["mat_k"], lm, ld, sweep_layer=41, sweep_d=sw).numpy()
+    for i, dv in enumerate(sw):
+        ld2 = list(ld)
+        ld2[41] = float(dv)
+        one = eng.eval_grid(prep["wl"], th, prep["mat_n"], prep["mat_k"], lm, ld2).numpy()
+        for k in ("R", "T", "A"):
+            assert np.array_equal(a[k][i], one[k][0]), (i, k)
+
+
 def test_resonant_cavity_against_50_digit_truth(eng):
     """Where the tight tolerance cannot hold (a cavity sampled through its resonance), the CUDA result must be at
     least as close to the 50-digit evaluation of the model as the reference is, and parity must hold under the
