@@ -209,6 +209,15 @@ int pst_fresnel(pst_handle_t h, const double* n1 /*[dev] complex n*/, const doub
 int pst_interface_matrices(pst_handle_t h, const double* r /*[dev] complex n*/, const double* t /*[dev] complex n*/,
                            int64_t n, double* out /*[dev]*/, void* stream);
 
+/* Per-layer field amplitudes (additive; SURVEY.md section 8f-4 -- the reference's YAML files carry A0/B0 amplitude keys
+ * that its code never reads, default/fabry-perot.yaml:13-14).  For every (polarisation, wavelength, theta) point of the
+ * grid described by `a` (same meaning as pst_eval_grid; outputs R/T/A/M and peers are ignored, no thickness sweep, flags
+ * = 0 or PST_FLAG_SNELL) and every layer j: the forward and backward amplitudes (A_j, B_j) = D_j^-1 (E, H)_tangential
+ * at the LEFT boundary of layer j, with D_j the reference's dynamical matrix (tm.py:190-215), normalised to a unit
+ * incident amplitude.  Layer 0 holds (1, r), the exit medium (t, 0), with r and t as in tm.py:482-483.
+ * amp: device, complex128 [n_pol][n_wl][n_theta][n_layers][2]. */
+int pst_field_amplitudes(pst_handle_t h, const pst_grid_args* a, double* amp /*[dev]*/, void* stream);
+
 /* ---- fused spectral reduction --------------------------------------------------------
  * Peak search along the middle axis of y[n_outer][n_pts][n_inner] (a grid result: outer = (sweep, pol), pts =
  * wavelength, inner = theta) with the semantics of scipy.signal.find_peaks(y, height=, distance=) that the reference's

@@ -157,3 +157,25 @@ def truth_point(lam, n_list, d_list, theta0, pol, dps=50):
         R = abs(m10 / m00) ** 2
         T = (kz[-1] / kz[0]).real * abs(1 / m00) ** 2
         return float(T), float(R)
+
+
+# ------------------------------------------------------------------------------ per-layer field amplitudes
+def field_amplitudes_point(lam, n_list, d_list, theta0, pol, snell=True):
+    """(A_j, B_j) at the left boundary of every layer j for a unit incident amplitude (pst_field_amplitudes):
+    D_j^-1 applied to the tangential field pair, D_j as tm.py:190-215.  snell=False is the reference's model (the
+    incidence angle in every layer).  Layer 0 holds (1, r), the exit medium (t, 0).  Returns complex (L, 2)."""
+    omega = 2 * np.pi * C0 / lam
+    L = len(n_list)
+    cs = layer_cosines(n_list, n_list[0], theta0) if snell else [np.cos(theta0) + 0j] * L
+    Df = dynamical_matrix(n_list[-1], cs[-1], pol)
+    v = Df @ np.array([1.0, 0.0], dtype=complex)  # unit transmitted amplitude
+    raw = np.zeros((L, 2), dtype=complex)
+    raw[L - 1] = (1.0, 0.0)
+    for j in range(L - 2, 0, -1):
+        kx = n_list[j] * omega / C0 * cs[j]
+        D = dynamical_matrix(n_list[j], cs[j], pol)
+        P = np.array([[np.exp(-1j * kx * d_list[j]), 0], [0, np.exp(1j * kx * d_list[j])]])
+        v = np.linalg.multi_dot([D, P, np.linalg.inv(D)]) @ v
+        raw[j] = np.linalg.inv(D) @ v
+    raw[0] = np.linalg.inv(dynamical_matrix(n_list[0], cs[0], pol)) @ v
+    return raw / raw[0, 0]

@@ -874,6 +874,46 @@ extern "C" int pst_interface_matrices(pst_handle_t h, const double* r, const dou
   return PST_OK;
 }
 
+extern "C" int pst_field_amplitudes(pst_handle_t h, const pst_grid_args* a, double* amp, void* stream) {
+  if (!h) return fail(PST_E_INVALID, "pst_field_amplitudes: NULL handle");
+  if (!amp) return fail(PST_E_INVALID, "pst_field_amplitudes: NULL output");
+  pst_grid_args loc;
+  if (a) {
+    loc = *a;
+    loc.R = amp;  // validate_grid wants some output
+    loc.T = loc.A = loc.M = nullptr;
+    loc.peers = nullptr;
+  }
+  PST_TRY(validate_grid(a ? &loc : nullptr, "pst_field_amplitudes"));
+  if (a->sweep_layer >= 0) return fail(PST_E_INVALID, "pst_field_amplitudes: thickness sweeps are not covered");
+  if (a->flags & ~(unsigned)PST_FLAG_SNELL) return fail(PST_E_INVALID, "pst_field_amplitudes: only PST_FLAG_SNELL is accepted");
+  DeviceGuard g(h->device);
+  if (!g.ok) return fail(PST_E_CUDA, "pst_field_amplitudes: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  PST_TRY(sync_layers(h, &loc, st));
+  PST_TRY(run_prep(h, &loc, a->wl, a->theta, a->cos_theta, a->mat_n, a->mat_k, st));
+  GridParams prm;
+  std::memset(&prm, 0, sizeof(prm));
+  prm.n_wl = a->n_wl;
+  prm.n_theta = a->n_theta;
+  prm.n_mat = a->n_mat;
+  prm.n_layers = a->n_layers;
+  prm.sweep_layer = -1;
+  prm.flags = a->flags;
+  prm.points = (long long)a->n_wl * a->n_theta;
+  prm.opt = h->opt.p;
+  prm.trig = h->trig.p;
+  prm.layers = h->layers_flagged.p;  // `type` field = the material's lossy flag
+  const int npol = __builtin_popcount(a->pol_mask);
+  const int pol_a = (a->pol_mask & PST_POL_S) ? 0 : 1, pol_b = 1;
+  const dim3 grid((unsigned)((prm.points + 127) / 128), (unsigned)npol);
+  if (a->flags & PST_FLAG_SNELL) field_amplitudes_kernel<true><<<grid, 128, 0, st>>>(prm, pol_a, pol_b, amp);
+  else field_amplitudes_kernel<false><<<grid, 128, 0, st>>>(prm, pol_a, pol_b, amp);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PST_OK;
+}
+
 extern "C" int pst_find_peaks(pst_handle_t h, const double* y, int n_outer, int n_pts, int n_inner, double height,
                               int use_height, int distance, int max_peaks, int reverse, const double* axis, int* out_idx,
                               double* out_height, int* out_count, double* out_spacing, void* stream) {

@@ -745,6 +745,99 @@ tmm_snell_kernel(const GridParams prm) {
   }
 }
 
+// ------------------------------------------------------------------------------------ per-layer field amplitudes
+// pst_field_amplitudes (the reference's YAML carries unused A0/B0 keys, fabry-perot.yaml:13-14).
+// The state of the backward chain after layers N-2 .. j is the tangential field pair at the left boundary of layer j for
+// a unit transmitted amplitude; D_j^-1 turns it into the forward/backward amplitudes (A_j, B_j) of layer j there
+// (tm.py:190-215 for D_j).  Results are normalised to the incident amplitude: layer 0 gets (1, r), the exit medium
+// (t, 0).  One thread per (point, polarisation) runs the chain twice -- once for the incident amplitude and its
+// power-of-two exponent, once to emit the normalised pairs -- so nothing unnormalised (it can exceed the fp64 range in
+// a stop band) is ever stored.  amp[pol][wl][theta][layer][2] complex128.
+template <bool SNELL>
+__global__ void __launch_bounds__(128)
+field_amplitudes_kernel(const GridParams prm, int pol_a, int pol_b, double* __restrict__ amp) {
+  const unsigned npts = (unsigned)prm.points, nth = (unsigned)prm.n_theta;
+  const unsigned p = blockIdx.x * 128u + threadIdx.x;
+  if (p >= npts) return;
+  const int pol = blockIdx.y == 0 ? pol_a : pol_b;  // 0 = s, 1 = p
+  const bool is_s = pol == 0;
+  const int il_loc = (int)(p / nth);
+  const int it = (int)(p - (unsigned)il_loc * nth);
+  const double2 tr = __ldg(prm.trig + it);
+  const double ct = tr.x, ict = tr.y;
+  const double2* optp = reinterpret_cast<const double2*>(prm.opt + (size_t)(prm.il0 + il_loc) * prm.n_mat * 6);
+  auto opt_row = [&](int mat) {
+    const double2 a = __ldg(optp + mat * 3), b = __ldg(optp + mat * 3 + 1), c = __ldg(optp + mat * 3 + 2);
+    OptRow r;
+    r.qr = a.x; r.nr = a.y; r.inr = b.x; r.ni = b.y; r.qi = c.x; r.ini = c.y;
+    return r;
+  };
+  const int L = prm.n_layers;
+  const OptRow in_row = opt_row(prm.layers[0].mat), exit_row = opt_row(prm.layers[L - 1].mat);
+  const cplx s2 = SNELL ? snell_s2(in_row.nr, in_row.ni, ct) : cplx{0.0, 0.0};
+  // rows of 2 D_j^-1 = [[w0, w1], [w0, -w1]]:  s: w0 = 1, w1 = 1/(n cos)   p: w0 = 1/cos, w1 = 1/n
+  auto dinv = [&](const OptRow& o, cplx& w0, cplx& w1) {
+    const cplx inv_n = {o.inr, o.ini};
+    if constexpr (SNELL) {
+      const SnellAngle g = snell_angle(o, s2);
+      w0 = is_s ? cplx{1.0, 0.0} : g.ic;
+      w1 = is_s ? cmul(inv_n, g.ic) : inv_n;
+    } else {
+      w0 = is_s ? cplx{1.0, 0.0} : cplx{ict, 0.0};
+      w1 = is_s ? cscale(inv_n, ict) : inv_n;
+    }
+  };
+  auto step = [&](ChainState<1, 1>& st, int j) {
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(prm.layers + j));  // {d, mat, lossy flag}
+    const double d = __hiloint2double(raw.y, raw.x);
+    const OptRow o = opt_row(raw.z);
+    if constexpr (SNELL) apply_cplx_layer<1, 1>(st, build_snell_layer<1>(o, d, s2, pol));
+    else apply_layer<1, 1>(st, o, raw.w == 0, d, ct, ict, pol);
+    renormalise<1, 1>(st);
+  };
+  auto init = [&](ChainState<1, 1>& st) {
+    if constexpr (SNELL) init_exit_columns_snell<1, 1>(st, exit_row.nr, exit_row.ni, snell_angle(exit_row, s2), pol);
+    else init_exit_columns<1, 1>(st, exit_row.nr, exit_row.ni, ct, pol);
+  };
+  auto amplitudes = [&](const ChainState<1, 1>& st, const OptRow& o, cplx& A, cplx& B) {
+    cplx w0, w1;
+    dinv(o, w0, w1);
+    const cplx a = cscale(cmul(w0, {st.v[0][0][0], st.v[0][0][1]}), 0.5);
+    const cplx b = cscale(cmul(w1, {st.v[0][0][2], st.v[0][0][3]}), 0.5);
+    A = cadd(a, b);
+    B = csub(a, b);
+  };
+
+  ChainState<1, 1> st;
+  init(st);
+  for (int j = L - 2; j >= 1; --j) step(st, j);
+  cplx A0, B0;
+  amplitudes(st, in_row, A0, B0);
+  const cplx inv_A0 = crecip(A0);  // times 2^-kexp0
+  const int kexp0 = st.kexp[0];
+
+  double4* out = reinterpret_cast<double4*>(amp) + ((size_t)blockIdx.y * npts + p) * (size_t)L;
+  auto emit = [&](int j, cplx A, cplx B, int kexp) {
+    const cplx a = cmul(A, inv_A0), b = cmul(B, inv_A0);
+    const int e = kexp - kexp0;
+    out[j] = make_double4(scale2(a.re, e), scale2(a.im, e), scale2(b.re, e), scale2(b.im, e));
+  };
+  emit(0, A0, B0, kexp0);
+  init(st);
+  {
+    cplx A, B;
+    amplitudes(st, exit_row, A, B);
+    emit(L - 1, A, {0.0, 0.0}, 0);  // B is zero by construction (rounding residue dropped)
+  }
+  for (int j = L - 2; j >= 1; --j) {
+    step(st, j);
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(prm.layers + j));
+    cplx A, B;
+    amplitudes(st, opt_row(raw.z), A, B);
+    emit(j, A, B, st.kexp[0]);
+  }
+}
+
 // Per-thread constants of a thickness sweep (see tmm_sweep_kernel) and its inner loop.
 template <int NPOL>
 struct SweepConsts {

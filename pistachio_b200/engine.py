@@ -212,6 +212,27 @@ class TMMEngine:
         del keep
         return GridResult(res["R"], res["T"], res["A"], M, pols_of_mask(mask))
 
+    def field_amplitudes(self, wl, theta, mat_n, mat_k, layer_mat, layer_d, pols=(S_WAVE, P_WAVE), *, cos_theta=None,
+                         flags=0) -> torch.Tensor:
+        """Forward/backward amplitudes (A_j, B_j) at the left boundary of every layer, normalised to a unit incident
+        amplitude (pst_field_amplitudes).  Returns a complex128 CUDA tensor (n_pol, n_wl, n_theta, n_layers, 2)."""
+        wl_d = _dev_f64(wl, self.device)
+        th_d = _dev_f64(theta, self.device) if theta is not None else None
+        ct_d = _dev_f64(cos_theta, self.device) if cos_theta is not None else None
+        n_d = _dev_f64(mat_n, self.device)
+        k_d = _dev_f64(mat_k, self.device)
+        if n_d.dim() != 2 or n_d.shape != k_d.shape or n_d.shape[1] != wl_d.numel():
+            raise ValueError("mat_n / mat_k must have shape (n_mat, n_wl)")
+        n_wl, n_mat = wl_d.numel(), n_d.shape[0]
+        n_theta = (th_d if th_d is not None else ct_d).numel()
+        n_pol = bin(pol_mask(pols)).count("1")
+        amp = torch.empty((n_pol, n_wl, n_theta, len(layer_d), 2), dtype=torch.complex128, device=self.device)
+        a, keep = self._grid_args(_ptr(wl_d), _ptr(th_d), _ptr(n_d), _ptr(k_d), layer_mat, layer_d, pols, -1, None, 1,
+                                  _ptr(ct_d), flags, n_wl, n_theta, n_mat, (None, None, None, None))
+        check(self.lib.pst_field_amplitudes(self.handle.raw, C.byref(a), _ptr(amp), self._stream()), "pst_field_amplitudes")
+        del keep
+        return amp
+
     def eval_grid_host(self, wl, theta, mat_n, mat_k, layer_mat, layer_d, pols=(S_WAVE, P_WAVE), *, sweep_layer=-1,
                        sweep_d=None, cos_theta=None, want=("R", "T", "A"), flags=0, out=None):
         """Host buffers in, host buffers out (pst_eval_grid_host): the plugin-style call.  `out` may carry pinned

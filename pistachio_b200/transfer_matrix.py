@@ -371,6 +371,15 @@ class Structure:
             res = {k: (v[0] if v is not None else None) for k, v in res.items()}
         return res
 
+    def field_amplitudes(self, theta=None, pols=(S_WAVE, P_WAVE)):
+        """Additive API (the reference's YAML carries unused A0/B0 keys): forward and backward
+        amplitudes (A_j, B_j) at the left boundary of every layer for a unit incident amplitude -- layer 0 holds (1, r),
+        the exit medium (t, 0).  Returns a complex128 array (n_pol, n_wl, n_theta, n_layers, 2)."""
+        theta = np.atleast_1d(np.asarray(self.theta if theta is None else theta, dtype=np.float64))
+        wl, mat_n, mat_k, layer_mat, layer_d = self._stack_on_grid()
+        return _to_numpy(_eng().field_amplitudes(wl, theta, mat_n, mat_k, layer_mat, layer_d, pols,
+                                                 cos_theta=np.cos(theta), flags=self._flags()))
+
     def cavity_length_from_peaks(self, n_eff=1.0, theta=None, pol=S_WAVE, height=None, distance=None, percent=True,
                                  sweep_layer=-1, sweep_d=None, max_peaks=64):
         """Additive API: the reference's "Cavity Length Determiner" notebook fused behind the

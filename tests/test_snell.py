@@ -211,3 +211,61 @@ def test_gpu_structure_snell_attribute():
         for il in (0, 31, 63):
             T, R, _ = so.point(s.wavelengths[il], [x[il] for x in n], d, s.theta[-1], pol)
             assert close(out["R"][ip, il, -1], R, 1e-11) and close(out["T"][ip, il, -1], T, 1e-11)
+
+
+# ------------------------------------------------------------------------------------------ per-layer field amplitudes
+def test_oracle_field_amplitudes_properties():
+    """Layer 0 holds (1, r), the exit medium (t, 0) with R = |r|^2 and T = Re(det M)|t|^2 of the spectrum oracle; in a
+    lossless stack the s-wave energy flux Re(n cos)(|A|^2 - |B|^2) is the same in every layer."""
+    rng = np.random.default_rng(11)
+    for snell in (True, False):
+        ns, d = random_stack(rng, 9, lossless=True)
+        lam, th = 0.9, 0.7
+        for pol in POLS:
+            amp = so.field_amplitudes_point(lam, ns, d, th, pol, snell=snell)
+            if snell:
+                T, R, _ = so.point(lam, ns, d, th, pol)
+            else:
+                Tg, Rg = to.spectrum(to.Stack([lam], [np.array([n]) for n in ns], d), th, pol)
+                T, R = Tg[0], Rg[0]
+            assert abs(amp[0, 0] - 1) < 1e-15 and abs(abs(amp[0, 1]) ** 2 - R) < 1e-12 and amp[-1, 1] == 0
+            cs = so.layer_cosines(ns, ns[0], th) if snell else [np.cos(th)] * len(ns)
+            det = (ns[-1] * cs[-1]) / (ns[0] * cs[0])
+            assert abs(det.real * abs(amp[-1, 0]) ** 2 - T) < 1e-12
+        if snell:
+            amp = so.field_amplitudes_point(lam, ns, d, th, so.S_WAVE)
+            cs = so.layer_cosines(ns, ns[0], th)
+            flux = [(n * c).real * (abs(a) ** 2 - abs(b) ** 2) for n, c, (a, b) in zip(ns, cs, amp)]
+            assert np.allclose(flux, flux[0], rtol=1e-11)
+
+
+@pytest.mark.gpu
+def test_gpu_field_amplitudes_match_oracle():
+    from pistachio_b200 import engine
+
+    eng = engine.get_engine()
+    rng = np.random.default_rng(12)
+    wl = np.linspace(0.6, 1.4, 5)
+    thetas = np.array([0.0, 0.5, 1.2, 1.5])
+    for trial in range(8):
+        ns, d = random_stack(rng, int(rng.integers(2, 30)), n0=rng.choice([1.0, 1.5]), nf=rng.choice([1.0, 1.5]))
+        mat_n = np.array([np.full(wl.shape, n.real) for n in ns])
+        mat_k = np.array([np.full(wl.shape, n.imag) for n in ns])
+        for snell in (False, True):
+            amp = eng.field_amplitudes(wl, thetas, mat_n, mat_k, list(range(len(ns))), d, cos_theta=np.cos(thetas),
+                                       flags=engine.FLAG_SNELL if snell else 0).cpu().numpy()
+            assert amp.shape == (2, len(wl), len(thetas), len(ns), 2)
+            for ip, pol in enumerate(POLS):
+                for il in (0, 4):
+                    for it in range(len(thetas)):
+                        ref = so.field_amplitudes_point(wl[il], ns, d, thetas[it], pol, snell=snell)
+                        scale = np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1e-6)
+                        assert np.all(np.abs(amp[ip, il, it] - ref) <= 1e-10 * scale), (trial, snell, pol, il, it)
+    # a deep stop band: 1500 quarter-wave pairs (|t| ~ 1e-348); the unnormalised chain leaves the fp64 range, the amplitudes do not
+    wl = np.array([1.0])
+    mat_n = np.array([[1.0], [2.32], [1.36], [1.5]])
+    lm = [0] + [1, 2] * 1500 + [3]
+    d = [0.0] + [1.0 / (4 * 2.32), 1.0 / (4 * 1.36)] * 1500 + [0.0]
+    amp = eng.field_amplitudes(wl, [0.0], mat_n, np.zeros_like(mat_n), lm, d, ("s-wave",)).cpu().numpy()[0, 0, 0]
+    assert np.isfinite(amp.view(np.float64)).all() and abs(abs(amp[0, 1]) - 1) < 1e-12
+    assert abs(amp[-1, 0]) < 1e-300 and 1e-240 < abs(amp[2001, 0]) < 1e-220 and np.all(np.abs(amp[1:, 0]) <= 2.0)
