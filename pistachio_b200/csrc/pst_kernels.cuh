@@ -1223,31 +1223,29 @@ __global__ void find_peaks_kernel(const double* __restrict__ y, int n_outer, int
     double prev = at(0);
     bool rising = false;
     int start = 0;
-    for (int i0 = 1; i0 < n_pts; i0 += kBatch) {
+    // one sample of the state machine, branch-free except for the (rare) emission of a peak:
+    //   x > prev            opens a plateau at i
+    //   x == prev           keeps the state
+    //   x < prev (or NaN)   closes it; a descent from an open plateau is a peak at the plateau's midpoint
+    auto feed = [&](int i, double x) {
+      const bool gt = x > prev, lt = x < prev, ne = x != prev;
+      if (lt && rising && (!use_height || prev >= height)) {
+        if (n < kPeakCap && n < max_peaks) { idx[n] = (start + i - 1) / 2; hh[n] = prev; keep[n] = 1; ++n; }
+        else overflow = true;
+      }
+      rising = gt || (rising && !ne);
+      start = gt ? i : start;
+      prev = x;
+    };
+    int i0 = 1;
+    for (; i0 + kBatch <= n_pts; i0 += kBatch) {
       double buf[kBatch];
 #pragma unroll
-      for (int k = 0; k < kBatch; ++k) buf[k] = (i0 + k < n_pts) ? at(i0 + k) : 0.0;
+      for (int k = 0; k < kBatch; ++k) buf[k] = at(i0 + k);
 #pragma unroll
-      for (int k = 0; k < kBatch; ++k) {
-        const int i = i0 + k;
-        if (i < n_pts) {
-          const double x = buf[k];
-          if (x > prev) {
-            rising = true;
-            start = i;
-          } else if (x < prev) {
-            if (rising && (!use_height || prev >= height)) {
-              if (n < kPeakCap && n < max_peaks) { idx[n] = (start + i - 1) / 2; hh[n] = prev; keep[n] = 1; ++n; }
-              else overflow = true;
-            }
-            rising = false;
-          } else if (x != prev) {
-            rising = false;  // NaN: scipy's comparisons are all false, no plateau runs through it
-          }
-          prev = x;
-        }
-      }
+      for (int k = 0; k < kBatch; ++k) feed(i0 + k, buf[k]);
     }
+    for (; i0 < n_pts; ++i0) feed(i0, at(i0));
   }
   // ---- distance condition: from the highest peak down, a kept peak removes neighbours closer than `distance`
   if (distance > 1 && n > 1) {
