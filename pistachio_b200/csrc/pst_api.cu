@@ -481,7 +481,20 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
                            ((o2.x == o0.x && o2.y == o0.y) || (o2.x == o0.y && o2.y == o0.x));
       const bool spacer_ok = o1.y < 0 && o1.z == 1 && o1.x != o0.x && o1.x != o0.y;
       const bool sweep_ok = tp.sweep_type != o0.x && tp.sweep_type != o0.y;
-      if (pair_ok && spacer_ok && sweep_ok) tp.shape = 1;
+      if (pair_ok && spacer_ok && sweep_ok) {
+        tp.shape = 1;
+        const int t3[3] = {o0.x, o0.y, o1.x};
+        for (int i = 0; i < 3; ++i) {
+          tp.fast_row[i] = tp.type_mat[t3[i]] * 3;
+          tp.fast_d[i] = tp.type_d[t3[i]];
+        }
+        tp.fast_row_last = tp.mat_last * 3;
+        tp.fast_row_first = tp.mat_first * 3;
+        tp.fast_lossy_ab = (1u << o0.x) | (1u << o0.y);
+        tp.fast_lossy_c = 1u << o1.x;
+        tp.fast_c_swept = (o1.x == tp.sweep_type) ? 1 : 0;
+        tp.fast_mirrored = (o2.x == o0.x) ? 0 : 1;
+      }
     }
   }
   prm.use_bulk = (a->flags & PST_FLAG_NO_BULK_COPY) ? 0 : 1;

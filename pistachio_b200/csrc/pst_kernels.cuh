@@ -116,6 +116,15 @@ struct TypedPlan {
   int type_mat[kMaxTypes];
   double type_d[kMaxTypes];
   int4 ops[kMaxOps];        // (type A, type B or -1, repeat count, 0), in application order (exit side first)
+  // shape == 1: everything the straight-line program needs, resolved on the host so that the kernel's first loads do not
+  // wait on chains of dependent constant-bank reads (ops -> type -> material -> row address)
+  int fast_row[3];          // row offsets (in double2 units) of the materials of types A, B (mirror pair) and C (spacer)
+  int fast_row_last, fast_row_first;
+  unsigned fast_lossy_ab;   // bits of types A and B in the device's lossy-type word; fast_lossy_c: bit of type C
+  unsigned fast_lossy_c;
+  int fast_c_swept;         // 1: the spacer is the swept layer (thickness from sweep_d)
+  int fast_mirrored;        // 1: the second mirror applies (B, A) -- the mirror image of the first
+  double fast_d[3];         // thicknesses of A, B, C
   const unsigned* lossy_types;  // device word, bit t: the material of type t absorbs somewhere on the grid (flag kernel)
 };
 
@@ -466,7 +475,6 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   constexpr int NC = NCOL;
   const unsigned npts = (unsigned)prm.points, nth = (unsigned)prm.n_theta;
   const unsigned sweep_idx = ROW ? blockIdx.z : blockIdx.y;
-  const double d_sweep = prm.sweep_d ? __ldg(prm.sweep_d + sweep_idx) : 0.0;
   bool valid;
   unsigned p;
   int il_loc, it;
@@ -487,21 +495,22 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   const double2* optp = reinterpret_cast<const double2*>(prm.opt + (size_t)il * prm.n_mat * 6);  // rows of 3 double2
   // straight-line program (below): its table rows are requested before anything waits on a load
   const bool shape1 = NCOL == 1 && tp.shape == 1 && !(prm.flags & (128u | 2048u));
-  const int tA = tp.ops[0].x, tB = tp.ops[0].y, tC = tp.ops[1].x;
   double2 a0, a1, b0, b1, c0, c1, c2;
   if (shape1) {
-    const double2* rA = optp + tp.type_mat[tA] * 3;
-    const double2* rB = optp + tp.type_mat[tB] * 3;
-    const double2* rC = optp + tp.type_mat[tC] * 3;
+    const double2* rA = optp + tp.fast_row[0];
+    const double2* rB = optp + tp.fast_row[1];
+    const double2* rC = optp + tp.fast_row[2];
     a0 = __ldg(rA); a1 = __ldg(rA + 1); b0 = __ldg(rB); b1 = __ldg(rB + 1);
     c0 = __ldg(rC); c1 = __ldg(rC + 1); c2 = __ldg(rC + 2);
   }
   const double2 tr = __ldg(prm.trig + it);
   const unsigned lossy_mask = __ldg(tp.lossy_types);
+  const double d_sweep = prm.sweep_d ? __ldg(prm.sweep_d + sweep_idx) : 0.0;
   const double ct = tr.x, ict = tr.y;
-  const double2 ex0 = __ldg(optp + tp.mat_last * 3), ex1 = __ldg(optp + tp.mat_last * 3 + 1);
+  const int row_last = shape1 ? tp.fast_row_last : tp.mat_last * 3;
+  const double2 ex0 = __ldg(optp + row_last), ex1 = __ldg(optp + row_last + 1);
   const double nfr = ex0.y, nfi = ex1.y;
-  const double2* in_row = optp + tp.mat_first * 3;  // incidence medium: (1/n).re, (1/n).im for the epilogue
+  const double2* in_row = optp + (shape1 ? tp.fast_row_first : tp.mat_first * 3);  // incidence medium: 1/n for the epilogue
   double2 in1, in2;
 
   ChainState<NPOL, NC> st;
@@ -514,10 +523,10 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   // their sincos chains interleave.
   bool done = false;
   if constexpr (NCOL == 1) {
-    if (shape1 && !(((lossy_mask >> tA) | (lossy_mask >> tB)) & 1u)) {
-      const bool lossyC = (lossy_mask >> tC) & 1u;
-      const double dC = (tC == tp.sweep_type) ? d_sweep : tp.type_d[tC];
-      const double xA = layer_phase(a0.x, ct, tp.type_d[tA]), xB = layer_phase(b0.x, ct, tp.type_d[tB]);
+    if (shape1 && !(lossy_mask & tp.fast_lossy_ab)) {
+      const bool lossyC = (lossy_mask & tp.fast_lossy_c) != 0u;
+      const double dC = tp.fast_c_swept ? d_sweep : tp.fast_d[2];
+      const double xA = layer_phase(a0.x, ct, tp.fast_d[0]), xB = layer_phase(b0.x, ct, tp.fast_d[1]);
       const double xC = layer_phase(c0.x, ct, dC);
       double sA, cA, sB, cB, sC, cC;
       if (sincos_in_fast_range(xA) && sincos_in_fast_range(xB) && sincos_in_fast_range(xC)) {
@@ -554,7 +563,7 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
         in1 = __ldg(in_row + 1);  // requested here (registers of C are free again), used in the epilogue
         in2 = __ldg(in_row + 2);
         if (tp.ops[2].z != tp.ops[0].z) pair_power_coeffs<NPOL>(A, B, tp.ops[2].z, S);
-        if (tp.ops[2].x == tA) apply_pair_power<NPOL, NC>(st, A, B, S);
+        if (!tp.fast_mirrored) apply_pair_power<NPOL, NC>(st, A, B, S);
         else apply_pair_power<NPOL, NC>(st, B, A, S);
         renormalise<NPOL, NC>(st);
         done = true;
