@@ -494,6 +494,7 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
         tp.fast_lossy_c = 1u << o1.x;
         tp.fast_c_swept = (o1.x == tp.sweep_type) ? 1 : 0;
         tp.fast_mirrored = (o2.x == o0.x) ? 0 : 1;
+        tp.fast_first_is_hi = (o0.x > o0.y) ? 1 : 0;
       }
     }
   }

@@ -278,37 +278,75 @@ PST_HD void pair_power_coeffs(const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, 
   }
 }
 
-// v <- U^k v with U = B A (A applied first) and U^k = S_{k-1} U - S_{k-2} I
-template <int NPOL, int NC>
-PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B,
-                             const PairPower<NPOL>& S) {
+// U^k = S_{k-1} U - S_{k-2} I as a matrix [[p00, -i p01], [-i p10, p11]] (real entries) times 2^ks, U = B A with A the
+// FIRST layer applied.  The off-diagonal entries of U = B A and of its mirror image A B are the same two numbers
+// (u01 = cB beA + beB cA, u10 = alB cA + cB alA) and the diagonal ones swap; `first_is_hi` (the first layer has the
+// higher type id) picks the operand order of those sums by type instead of by position, so that a mirror pair and
+// its mirror image round identically: the second Bragg stack of a symmetric cavity is the first one's matrix with
+// p00 and p11 exchanged, bit for bit.
+template <int NPOL>
+struct PairMatrix {
+  double p00[NPOL], p11[NPOL], p01[NPOL], p10[NPOL];
+  int ks[NPOL];
+};
+
+template <int NPOL>
+PST_HD void pair_power_matrix(const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, const PairPower<NPOL>& S,
+                              bool first_is_hi, PairMatrix<NPOL>& P) {
   const double cA = A.a[0], cB = B.a[0];
   const double cc = cB * cA;
 #pragma unroll
   for (int p = 0; p < NPOL; ++p) {
     const double alA = A.a[1 + 2 * p], beA = A.a[2 + 2 * p], alB = B.a[1 + 2 * p], beB = B.a[2 + 2 * p];
     const double u00 = fma(-beB, alA, cc), u11 = fma(-alB, beA, cc);
-    const double u01 = fma(cB, beA, beB * cA), u10 = fma(alB, cA, cB * alA);
-    const double p00 = fma(S.sa[p], u00, -S.sb[p]), p11 = fma(S.sa[p], u11, -S.sb[p]);
-    const double p01 = S.sa[p] * u01, p10 = S.sa[p] * u10;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      double* v = st.v[p][c];
-      const double v0r = v[0], v0i = v[1], v1r = v[2], v1i = v[3];
-      v[0] = fma(p00, v0r, p01 * v1i);
-      v[1] = fma(p00, v0i, -(p01 * v1r));
-      v[2] = fma(p11, v1r, p10 * v0i);
-      v[3] = fma(p11, v1i, -(p10 * v0r));
+    double u01, u10;
+    if (!first_is_hi) {
+      u01 = fma(cB, beA, beB * cA);
+      u10 = fma(alB, cA, cB * alA);
+    } else {
+      u01 = fma(cA, beB, beA * cB);
+      u10 = fma(alA, cB, cA * alB);
     }
-    st.kexp[p] += S.ks[p];
+    P.p00[p] = fma(S.sa[p], u00, -S.sb[p]);
+    P.p11[p] = fma(S.sa[p], u11, -S.sb[p]);
+    P.p01[p] = S.sa[p] * u01;
+    P.p10[p] = S.sa[p] * u10;
+    P.ks[p] = S.ks[p];
   }
 }
 
 template <int NPOL, int NC>
-PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, int k) {
+PST_HD void apply_pair_matrix(ChainState<NPOL, NC>& st, const PairMatrix<NPOL>& P) {
+#pragma unroll
+  for (int p = 0; p < NPOL; ++p) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      double* v = st.v[p][c];
+      const double v0r = v[0], v0i = v[1], v1r = v[2], v1i = v[3];
+      v[0] = fma(P.p00[p], v0r, P.p01[p] * v1i);
+      v[1] = fma(P.p00[p], v0i, -(P.p01[p] * v1r));
+      v[2] = fma(P.p11[p], v1r, P.p10[p] * v0i);
+      v[3] = fma(P.p11[p], v1i, -(P.p10[p] * v0r));
+    }
+    st.kexp[p] += P.ks[p];
+  }
+}
+
+// v <- U^k v with U = B A (A applied first)
+template <int NPOL, int NC>
+PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B,
+                             const PairPower<NPOL>& S, bool first_is_hi) {
+  PairMatrix<NPOL> P;
+  pair_power_matrix<NPOL>(A, B, S, first_is_hi, P);
+  apply_pair_matrix<NPOL, NC>(st, P);
+}
+
+template <int NPOL, int NC>
+PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, int k,
+                             bool first_is_hi) {
   PairPower<NPOL> S;
   pair_power_coeffs<NPOL>(A, B, k, S);
-  apply_pair_power<NPOL, NC>(st, A, B, S);
+  apply_pair_power<NPOL, NC>(st, A, B, S, first_is_hi);
 }
 
 // Build + apply in one go (the untyped path).  `lossless` is the MATERIAL's flag (k = 0 at every wavelength), so

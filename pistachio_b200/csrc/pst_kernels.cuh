@@ -124,6 +124,8 @@ struct TypedPlan {
   unsigned fast_lossy_c;
   int fast_c_swept;         // 1: the spacer is the swept layer (thickness from sweep_d)
   int fast_mirrored;        // 1: the second mirror applies (B, A) -- the mirror image of the first
+  int fast_first_is_hi;     // 1: type A (applied first in the first mirror) has the higher type id (operand order of the
+                            // period's off-diagonal sums, pst_chain.cuh pair_power_matrix)
   double fast_d[3];         // thicknesses of A, B, C
   const unsigned* lossy_types;  // device word, bit t: the material of type t absorbs somewhere on the grid (flag kernel)
 };
@@ -555,16 +557,33 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
       if (lg <= 12) {  // the interpreted form takes exactly this schedule when 67 lg + 40 <= 1000
         PairPower<NPOL> S;
         pair_power_coeffs<NPOL>(A, B, tp.ops[0].z, S);
-        apply_pair_power<NPOL, NC>(st, A, B, S);
-        // the interpreted form rescales here; rescaling is exact, so skipping it changes no bit as long as nothing can
-        // overflow before the final one: both powers and the spacer grow the state by < 2^(2 (66 lg + 40) + lg) <= 2^900
-        if (lg > 6) renormalise<NPOL, NC>(st);
-        apply_type<NPOL, NC>(st, C, lossyC);
-        in1 = __ldg(in_row + 1);  // requested here (registers of C are free again), used in the epilogue
-        in2 = __ldg(in_row + 2);
-        if (tp.ops[2].z != tp.ops[0].z) pair_power_coeffs<NPOL>(A, B, tp.ops[2].z, S);
-        if (!tp.fast_mirrored) apply_pair_power<NPOL, NC>(st, A, B, S);
-        else apply_pair_power<NPOL, NC>(st, B, A, S);
+        if (tp.ops[2].z == tp.ops[0].z) {
+          // both mirrors have the same number of pairs: one matrix serves both (exchanged diagonal when the second
+          // mirror is the mirror image), and the layer matrices and coefficients are dead from here on
+          PairMatrix<NPOL> P;
+          pair_power_matrix<NPOL>(A, B, S, tp.fast_first_is_hi != 0, P);
+          apply_pair_matrix<NPOL, NC>(st, P);
+          // the interpreted form rescales here; rescaling is exact, so skipping it changes no bit as long as nothing
+          // can overflow before the final one: both powers and the spacer grow the state by < 2^(2 (66 lg + 40) + lg)
+          if (lg > 6) renormalise<NPOL, NC>(st);
+          apply_type<NPOL, NC>(st, C, lossyC);
+          in1 = __ldg(in_row + 1);  // requested here (registers of C are free again), used in the epilogue
+          in2 = __ldg(in_row + 2);
+          if (tp.fast_mirrored) {
+#pragma unroll
+            for (int pp = 0; pp < NPOL; ++pp) { const double t = P.p00[pp]; P.p00[pp] = P.p11[pp]; P.p11[pp] = t; }
+          }
+          apply_pair_matrix<NPOL, NC>(st, P);
+        } else {
+          apply_pair_power<NPOL, NC>(st, A, B, S, tp.fast_first_is_hi != 0);
+          if (lg > 6) renormalise<NPOL, NC>(st);
+          apply_type<NPOL, NC>(st, C, lossyC);
+          in1 = __ldg(in_row + 1);
+          in2 = __ldg(in_row + 2);
+          pair_power_coeffs<NPOL>(A, B, tp.ops[2].z, S);
+          if (!tp.fast_mirrored) apply_pair_power<NPOL, NC>(st, A, B, S, tp.fast_first_is_hi != 0);
+          else apply_pair_power<NPOL, NC>(st, B, A, S, tp.fast_first_is_hi == 0);
+        }
         renormalise<NPOL, NC>(st);
         done = true;
       }
@@ -654,7 +673,7 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
           pair_power_coeffs<NPOL>(A, B, o.z, S);
           s_lo = t_lo; s_hi = t_hi; s_k = o.z;
         }
-        apply_pair_power<NPOL, NC>(st, A, B, S);
+        apply_pair_power<NPOL, NC>(st, A, B, S, o.x > o.y);
         renormalise<NPOL, NC>(st);
         since = 0;
         continue;
