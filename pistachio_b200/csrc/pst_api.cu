@@ -349,6 +349,11 @@ int run_prep(pst_handle_t h, const pst_grid_args* a, const double* wl, const dou
   return PST_OK;
 }
 
+// plain_out: the stores of a launch need no per-value tests (all three arrays present and local)
+inline void set_plain_out(GridParams& prm) {
+  prm.plain_out = (prm.R && prm.T && prm.A && prm.n_peers == 0 && !(prm.flags & PST_FLAG_MULTICAST_OUT) && !prm.pol_dup) ? 1 : 0;
+}
+
 struct ChainPlan {
   int npol, npol_out, ncol, W, PB, tl_rows, opt_row_bytes, type_stride;
   bool so, sl, seg, typed, row;
@@ -494,7 +499,6 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
         tp.fast_lossy_c = 1u << o1.x;
         tp.fast_c_swept = (o1.x == tp.sweep_type) ? 1 : 0;
         tp.fast_mirrored = (o2.x == o0.x) ? 0 : 1;
-        tp.fast_first_is_hi = (o0.x > o0.y) ? 1 : 0;
       }
     }
   }
@@ -516,6 +520,7 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
       prm.peer_T[i] = a->peers->T[i] ? a->peers->T[i] + (size_t)s0 * per_sweep : nullptr;
       prm.peer_A[i] = a->peers->A[i] ? a->peers->A[i] + (size_t)s0 * per_sweep : nullptr;
     }
+    set_plain_out(prm);
     dim3 grid((unsigned)nblk, (unsigned)ns), block(pl.PB, pl.W);
     if (pl.typed && pl.row) grid = dim3((unsigned)((a->n_theta + 127) / 128), (unsigned)n_wl_launch, (unsigned)ns);
     if (pl.typed) pl.fn_typed<<<grid, block, pl.smem, st>>>(prm, tp);
@@ -570,6 +575,7 @@ int launch_chain_f32(pst_handle_t h, const pst_grid_args* a, int il0, int n_wl_l
       prm.peer_T[i] = a->peers->T[i] ? a->peers->T[i] + (size_t)s0 * per_sweep : nullptr;
       prm.peer_A[i] = a->peers->A[i] ? a->peers->A[i] + (size_t)s0 * per_sweep : nullptr;
     }
+    set_plain_out(prm);
     fn<<<dim3((unsigned)nblk, (unsigned)ns), PB, stage ? smem : 0, st>>>(prm);
     PST_CUDA(cudaGetLastError());
     h->launches += 1;
@@ -619,6 +625,7 @@ int launch_snell(pst_handle_t h, const pst_grid_args* a, int il0, int n_wl_launc
       prm.peer_T[i] = a->peers->T[i] ? a->peers->T[i] + (size_t)s0 * per_sweep : nullptr;
       prm.peer_A[i] = a->peers->A[i] ? a->peers->A[i] + (size_t)s0 * per_sweep : nullptr;
     }
+    set_plain_out(prm);
     fn<<<dim3((unsigned)nblk, (unsigned)ns), 128, 0, st>>>(prm);
     PST_CUDA(cudaGetLastError());
     h->launches += 1;

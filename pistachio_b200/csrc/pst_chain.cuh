@@ -280,10 +280,10 @@ PST_HD void pair_power_coeffs(const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, 
 
 // U^k = S_{k-1} U - S_{k-2} I as a matrix [[p00, -i p01], [-i p10, p11]] (real entries) times 2^ks, U = B A with A the
 // FIRST layer applied.  The off-diagonal entries of U = B A and of its mirror image A B are the same two numbers
-// (u01 = cB beA + beB cA, u10 = alB cA + cB alA) and the diagonal ones swap; `first_is_hi` (the first layer has the
-// higher type id) picks the operand order of those sums by type instead of by position, so that a mirror pair and
-// its mirror image round identically: the second Bragg stack of a symmetric cavity is the first one's matrix with
-// p00 and p11 exchanged, bit for bit.
+// (u01 = cB beA + beB cA, u10 = alB cA + cB alA) and the diagonal ones swap; `mirror_image` (this call applies the
+// layers in the opposite order to the call its coefficients S were computed for) makes those sums round in the
+// operand order of that earlier call, so that a period and its mirror image agree bit for bit: the second Bragg
+// stack of a symmetric cavity is the first one's matrix with p00 and p11 exchanged.
 template <int NPOL>
 struct PairMatrix {
   double p00[NPOL], p11[NPOL], p01[NPOL], p10[NPOL];
@@ -292,7 +292,7 @@ struct PairMatrix {
 
 template <int NPOL>
 PST_HD void pair_power_matrix(const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, const PairPower<NPOL>& S,
-                              bool first_is_hi, PairMatrix<NPOL>& P) {
+                              bool mirror_image, PairMatrix<NPOL>& P) {
   const double cA = A.a[0], cB = B.a[0];
   const double cc = cB * cA;
 #pragma unroll
@@ -300,7 +300,7 @@ PST_HD void pair_power_matrix(const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, 
     const double alA = A.a[1 + 2 * p], beA = A.a[2 + 2 * p], alB = B.a[1 + 2 * p], beB = B.a[2 + 2 * p];
     const double u00 = fma(-beB, alA, cc), u11 = fma(-alB, beA, cc);
     double u01, u10;
-    if (!first_is_hi) {
+    if (!mirror_image) {
       u01 = fma(cB, beA, beB * cA);
       u10 = fma(alB, cA, cB * alA);
     } else {
@@ -335,18 +335,18 @@ PST_HD void apply_pair_matrix(ChainState<NPOL, NC>& st, const PairMatrix<NPOL>& 
 // v <- U^k v with U = B A (A applied first)
 template <int NPOL, int NC>
 PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B,
-                             const PairPower<NPOL>& S, bool first_is_hi) {
+                             const PairPower<NPOL>& S, bool mirror_image) {
   PairMatrix<NPOL> P;
-  pair_power_matrix<NPOL>(A, B, S, first_is_hi, P);
+  pair_power_matrix<NPOL>(A, B, S, mirror_image, P);
   apply_pair_matrix<NPOL, NC>(st, P);
 }
 
 template <int NPOL, int NC>
 PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, int k,
-                             bool first_is_hi) {
+                             bool mirror_image) {
   PairPower<NPOL> S;
   pair_power_coeffs<NPOL>(A, B, k, S);
-  apply_pair_power<NPOL, NC>(st, A, B, S, first_is_hi);
+  apply_pair_power<NPOL, NC>(st, A, B, S, mirror_image);
 }
 
 // Build + apply in one go (the untyped path).  `lossless` is the MATERIAL's flag (k = 0 at every wavelength), so

@@ -56,6 +56,7 @@ struct GridParams {
   double* T;
   double* A;
   double* M;
+  int plain_out;            // 1: R, T and A all present, local, no peers, no multicast, no duplication: stores need no tests
   int pol_dup;              // 1: one polarisation is computed and written to both polarisation planes
                             // (PST_FLAG_POL_DEGENERATE: in the reference's model s and p are the same function)
   int n_peers;              // > 0: results go to these peer-mapped buffers instead of R, T, A (pst_peer_outputs)
@@ -86,6 +87,12 @@ template <bool STREAMING>
 __device__ __forceinline__ void store_point_once(const GridParams& prm, size_t o, double R, double T, double A);
 template <bool STREAMING>
 __device__ __forceinline__ void store_point(const GridParams& prm, size_t o, double R, double T, double A) {
+  if (prm.plain_out) {  // the common call: one uniform test instead of seven
+    store_result<STREAMING>(prm.R + o, R, false);
+    store_result<STREAMING>(prm.T + o, T, false);
+    store_result<STREAMING>(prm.A + o, A, false);
+    return;
+  }
   store_point_once<STREAMING>(prm, o, R, T, A);
   if (prm.pol_dup) store_point_once<STREAMING>(prm, o + (size_t)prm.points, R, T, A);  // the other polarisation's plane
 }
@@ -124,8 +131,6 @@ struct TypedPlan {
   unsigned fast_lossy_c;
   int fast_c_swept;         // 1: the spacer is the swept layer (thickness from sweep_d)
   int fast_mirrored;        // 1: the second mirror applies (B, A) -- the mirror image of the first
-  int fast_first_is_hi;     // 1: type A (applied first in the first mirror) has the higher type id (operand order of the
-                            // period's off-diagonal sums, pst_chain.cuh pair_power_matrix)
   double fast_d[3];         // thicknesses of A, B, C
   const unsigned* lossy_types;  // device word, bit t: the material of type t absorbs somewhere on the grid (flag kernel)
 };
@@ -561,7 +566,7 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
           // both mirrors have the same number of pairs: one matrix serves both (exchanged diagonal when the second
           // mirror is the mirror image), and the layer matrices and coefficients are dead from here on
           PairMatrix<NPOL> P;
-          pair_power_matrix<NPOL>(A, B, S, tp.fast_first_is_hi != 0, P);
+          pair_power_matrix<NPOL>(A, B, S, false, P);
           apply_pair_matrix<NPOL, NC>(st, P);
           // the interpreted form rescales here; rescaling is exact, so skipping it changes no bit as long as nothing
           // can overflow before the final one: both powers and the spacer grow the state by < 2^(2 (66 lg + 40) + lg)
@@ -575,14 +580,14 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
           }
           apply_pair_matrix<NPOL, NC>(st, P);
         } else {
-          apply_pair_power<NPOL, NC>(st, A, B, S, tp.fast_first_is_hi != 0);
+          apply_pair_power<NPOL, NC>(st, A, B, S, false);
           if (lg > 6) renormalise<NPOL, NC>(st);
           apply_type<NPOL, NC>(st, C, lossyC);
           in1 = __ldg(in_row + 1);
           in2 = __ldg(in_row + 2);
           pair_power_coeffs<NPOL>(A, B, tp.ops[2].z, S);
-          if (!tp.fast_mirrored) apply_pair_power<NPOL, NC>(st, A, B, S, tp.fast_first_is_hi != 0);
-          else apply_pair_power<NPOL, NC>(st, B, A, S, tp.fast_first_is_hi == 0);
+          if (!tp.fast_mirrored) apply_pair_power<NPOL, NC>(st, A, B, S, false);
+          else apply_pair_power<NPOL, NC>(st, B, A, S, false);  // new coefficients: a period of its own (see the op loop)
         }
         renormalise<NPOL, NC>(st);
         done = true;
@@ -648,6 +653,7 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   #pragma unroll
     for (int pp = 0; pp < NPOL; ++pp) { S.sa[pp] = 1.0; S.sb[pp] = 0.0; S.ks[pp] = 0; }
     int s_lo = -1, s_hi = -1, s_k = -1;  // the period S belongs to
+    int s_first = -1;                   // the layer type applied first when S was computed (orientation of its sums)
     int since = 0;                      // layers applied since the last rescale
     for (int op = 0; op < tp.n_ops; ++op) {
       const int4 o = tp.ops[op];
@@ -672,8 +678,9 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
         if (t_lo != s_lo || t_hi != s_hi || o.z != s_k) {  // else: same or mirrored period, same trace, same S
           pair_power_coeffs<NPOL>(A, B, o.z, S);
           s_lo = t_lo; s_hi = t_hi; s_k = o.z;
+          s_first = o.x;
         }
-        apply_pair_power<NPOL, NC>(st, A, B, S, o.x > o.y);
+        apply_pair_power<NPOL, NC>(st, A, B, S, o.x != s_first);  // a mirror image rounds like the period it mirrors
         renormalise<NPOL, NC>(st);
         since = 0;
         continue;
