@@ -86,10 +86,11 @@ struct pst_handle_s {
   std::vector<LayerEntry> layers_host;  // what layers_dev currently holds
   DevBuf<int> taboff;
   DevBuf<int> mat_flags;
+  DevBuf<unsigned> prep_ticket;
   int n_types = 0;                 // layer-type analysis of the current layer list (sync_layers)
   int type_layer[kMaxTypes] = {0};
   std::vector<int4> ops_host;      // run-length ops of the typed path (passed by value: TypedPlan)
-  DevBuf<unsigned> lossy_types;    // bit t: the material of layer type t absorbs (flag_layers_kernel)
+  DevBuf<unsigned> lossy_types;    // bit t: the material of layer type t absorbs (prep_kernel)
   DevBuf<unsigned char> l2buf;
   DevBuf<double> sink;
   // host-buffer pipeline (pst_eval_grid_host)
@@ -130,7 +131,7 @@ extern "C" int pst_destroy(pst_handle_t h) {
   if (!h) return PST_OK;
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
-  h->opt.release(); h->trig.release(); h->layers_dev.release(); h->layers_flagged.release(); h->taboff.release(); h->mat_flags.release(); h->lossy_types.release(); h->l2buf.release();
+  h->opt.release(); h->trig.release(); h->layers_dev.release(); h->layers_flagged.release(); h->taboff.release(); h->mat_flags.release(); h->prep_ticket.release(); h->lossy_types.release(); h->l2buf.release();
   h->sink.release(); h->hp_in.release(); h->hp_out[0].release(); h->hp_out[1].release();
   for (int i = 0; i < 2; ++i) {
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -330,22 +331,25 @@ int run_prep(pst_handle_t h, const pst_grid_args* a, const double* wl, const dou
   const long long nm = (long long)a->n_wl * a->n_mat;
   PST_TRY(h->opt.ensure((size_t)nm * 6));
   PST_TRY(h->trig.ensure(a->n_theta));
-  PST_TRY(h->mat_flags.ensure(a->n_mat));
-  PST_CUDA(cudaMemsetAsync(h->mat_flags.p, 0, a->n_mat * sizeof(int), st));
-  prep_optical_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(wl, mat_n, mat_k, a->n_wl, a->n_mat, h->opt.p,
-                                                                   h->mat_flags.p);
-  PST_CUDA(cudaGetLastError());
-  prep_trig_kernel<<<(a->n_theta + 255) / 256, 256, 0, st>>>(theta, cos_theta, a->n_theta, h->trig.p);
-  PST_CUDA(cudaGetLastError());
   PST_TRY(h->layers_flagged.ensure(a->n_layers));
   PST_TRY(h->lossy_types.ensure(1));
+  // flags and ticket are zero between calls (the kernel's last block clears them); zero them when (re)allocated
+  const int* flags_before = h->mat_flags.p;
+  PST_TRY(h->mat_flags.ensure((size_t)a->n_mat + 1));  // [cap - 1] is unused; the ticket has its own buffer
+  if (h->mat_flags.p != flags_before) PST_CUDA(cudaMemsetAsync(h->mat_flags.p, 0, h->mat_flags.cap * sizeof(int), st));
+  const unsigned* ticket_before = h->prep_ticket.p;
+  PST_TRY(h->prep_ticket.ensure(1));
+  if (h->prep_ticket.p != ticket_before) PST_CUDA(cudaMemsetAsync(h->prep_ticket.p, 0, h->prep_ticket.cap * sizeof(unsigned), st));
   TypeMats tm;
   tm.n = h->n_types;
   for (int t = 0; t < kMaxTypes; ++t) tm.mat[t] = t < h->n_types ? a->layer_mat[h->type_layer[t]] : 0;
-  flag_layers_kernel<<<(a->n_layers + 255) / 256, 256, 0, st>>>(h->layers_dev.p, h->mat_flags.p, a->n_layers, a->n_mat,
-                                                               h->layers_flagged.p, tm, h->lossy_types.p);
+  const int n_opt_blocks = (int)((nm + 255) / 256);
+  const int n_trig_blocks = (a->n_theta + 255) / 256;
+  prep_kernel<<<(unsigned)(n_opt_blocks + n_trig_blocks), 256, 0, st>>>(
+      wl, mat_n, mat_k, a->n_wl, a->n_mat, h->opt.p, h->mat_flags.p, theta, cos_theta, a->n_theta, h->trig.p, n_opt_blocks,
+      h->layers_dev.p, a->n_layers, h->layers_flagged.p, tm, h->lossy_types.p, h->prep_ticket.p);
   PST_CUDA(cudaGetLastError());
-  h->launches += 3;
+  h->launches += 1;
   return PST_OK;
 }
 

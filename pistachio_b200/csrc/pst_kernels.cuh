@@ -2,8 +2,8 @@
 // a chain of 2x2 complex products is not a dense contraction).
 //
 //   resample_kernel      K0  dispersion-table lookup            (reference tm.py:117-170)
-//   prep_optical_kernel      per (material, lambda): q = (n w)(1/c), n, 1/n   (tm.py:269-270)
-//   prep_trig_kernel         per theta: cos, 1/cos
+//   prep_kernel              per (material, lambda): q = (n w)(1/c), n, 1/n (tm.py:269-270); per theta: cos, 1/cos;
+//                            lossy flags of materials, layers and layer types -- one launch
 //   tmm_chain_kernel     K1  one thread per (lambda, theta) point, both polarisations in the thread,
 //                            optical table + layer list staged in shared memory once per block
 //                        K2  same kernel with SEG=true: the interior layers are cut into blockDim.y
@@ -177,58 +177,76 @@ __global__ void resample_kernel(int n_tab, const int* __restrict__ tab_off, cons
 }
 
 // ------------------------------------------------------------------------------------------- prep
-__global__ void prep_optical_kernel(const double* __restrict__ wl, const double* __restrict__ mat_n,
-                                    const double* __restrict__ mat_k, int n_wl, int n_mat,
-                                    double* __restrict__ opt, int* __restrict__ mat_flags) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)n_wl * n_mat) return;
-  const int m = (int)(idx / n_wl);
-  const int i = (int)(idx - (long long)m * n_wl);
-  const double nk = mat_k[idx];
-  const OptRow r = make_opt_row(wl[i], mat_n[idx], nk);
-  double2* o = reinterpret_cast<double2*>(opt + ((size_t)i * n_mat + m) * 6);
-  o[0] = make_double2(r.qr, r.nr);
-  o[1] = make_double2(r.inr, r.ni);
-  o[2] = make_double2(r.qi, r.ini);
-  // the material absorbs (or amplifies) somewhere on the grid: one atomic per warp and material at most
-  const unsigned act = __activemask();
-  const int m0 = __shfl_sync(act, m, __ffs(act) - 1);
-  const bool any_here = __any_sync(act, nk != 0.0 && m == m0);
-  if (m == m0) {
-    if (any_here && (threadIdx.x & 31) == __ffs(act) - 1) atomicOr(mat_flags + m, 1);
-  } else if (nk != 0.0) {
-    atomicOr(mat_flags + m, 1);  // warp straddling two materials
-  }
-}
-
-// Layer list for the untyped paths: `type` replaced by the material's lossy flag, so the layer loop needs no
-// second lookup and the list can be staged by a plain bulk copy.
+// One launch prepares everything the chain kernels read (it used to be a memset and three launches, 12 us of a 275 us
+// bench step):
+//   blocks [0, n_opt_blocks)   optical table row entries q, n, 1/n per (material, wavelength) and the materials'
+//                              lossy flags (k != 0 somewhere on the grid; warp-aggregated atomicOr)
+//   the remaining blocks       (cos, 1/cos) per angle
+//   the block that finishes last (ticket counter) derives what depends on the complete flags: the layer list with the
+//   material's lossy flag in its `type` field (untyped kernels need no second lookup and can stage the list with a
+//   plain bulk copy), the lossy bits of the typed kernel's layer types, and then clears flags and ticket for the next
+//   call.
 struct TypeMats {
   int n;
   int mat[kMaxTypes];
 };
-__global__ void flag_layers_kernel(const LayerEntry* __restrict__ layers, const int* __restrict__ mat_flags, int n,
-                                   int n_mat, LayerEntry* __restrict__ out, const TypeMats tm,
-                                   unsigned* __restrict__ lossy_types) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j == 0) {  // bit t: the material of layer type t absorbs (typed kernel)
+
+__global__ void __launch_bounds__(256)
+prep_kernel(const double* __restrict__ wl, const double* __restrict__ mat_n, const double* __restrict__ mat_k, int n_wl,
+            int n_mat, double* __restrict__ opt, int* __restrict__ mat_flags, const double* __restrict__ theta,
+            const double* __restrict__ cos_theta, int n_theta, double2* __restrict__ trig, int n_opt_blocks,
+            const LayerEntry* __restrict__ layers, int n_layers, LayerEntry* __restrict__ layers_out, const TypeMats tm,
+            unsigned* __restrict__ lossy_types, unsigned* __restrict__ ticket) {
+  if ((int)blockIdx.x < n_opt_blocks) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < (long long)n_wl * n_mat) {
+      const int m = (int)(idx / n_wl);
+      const int i = (int)(idx - (long long)m * n_wl);
+      const double nk = mat_k[idx];
+      const OptRow r = make_opt_row(wl[i], mat_n[idx], nk);
+      double2* o = reinterpret_cast<double2*>(opt + ((size_t)i * n_mat + m) * 6);
+      o[0] = make_double2(r.qr, r.nr);
+      o[1] = make_double2(r.inr, r.ni);
+      o[2] = make_double2(r.qi, r.ini);
+      // the material absorbs (or amplifies) somewhere on the grid: one atomic per warp and material at most
+      const unsigned act = __activemask();
+      const int m0 = __shfl_sync(act, m, __ffs(act) - 1);
+      const bool any_here = __any_sync(act, nk != 0.0 && m == m0);
+      if (m == m0) {
+        if (any_here && (threadIdx.x & 31) == __ffs(act) - 1) atomicOr(mat_flags + m, 1);
+      } else if (nk != 0.0) {
+        atomicOr(mat_flags + m, 1);  // warp straddling two materials
+      }
+    }
+  } else {
+    const int i = ((int)blockIdx.x - n_opt_blocks) * blockDim.x + threadIdx.x;
+    if (i < n_theta) {
+      const double c = cos_theta ? cos_theta[i] : cos(theta[i]);
+      trig[i] = make_double2(c, 1.0 / c);
+    }
+  }
+  // ---- the last block to arrive finishes the flag-dependent part
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1u) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) {  // bit t: the material of layer type t absorbs (typed kernel); bit 31: any material does
     unsigned m = 0;
-    for (int t = 0; t < tm.n; ++t) m |= (mat_flags[tm.mat[t]] != 0 ? 1u : 0u) << t;
-    for (int i = 0; i < n_mat; ++i) m |= (mat_flags[i] != 0 ? 1u : 0u) << 31;  // any absorbing material at all
+    for (int t = 0; t < tm.n; ++t) m |= (__ldcg(mat_flags + tm.mat[t]) != 0 ? 1u : 0u) << t;
+    for (int i = 0; i < n_mat; ++i) m |= (__ldcg(mat_flags + i) != 0 ? 1u : 0u) << 31;
     *lossy_types = m;
   }
-  if (j >= n) return;
-  LayerEntry e = layers[j];
-  e.type = mat_flags[e.mat];
-  out[j] = e;
-}
-
-__global__ void prep_trig_kernel(const double* __restrict__ theta, const double* __restrict__ cos_theta, int n_theta,
-                                 double2* __restrict__ trig) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_theta) return;
-  const double c = cos_theta ? cos_theta[i] : cos(theta[i]);
-  trig[i] = make_double2(c, 1.0 / c);
+  for (int j = threadIdx.x; j < n_layers; j += blockDim.x) {
+    LayerEntry e = layers[j];
+    e.type = __ldcg(mat_flags + e.mat);
+    layers_out[j] = e;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_mat; i += blockDim.x) mat_flags[i] = 0;
+  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 // ------------------------------------------------------------------------------------ K1 / K2
@@ -367,7 +385,7 @@ tmm_chain_kernel(const GridParams prm) {
       for (; j > j_stop; --j) {
         const LayerEntry le = lay[j];
         const double d = (j == prm.sweep_layer) ? d_sweep : le.d;
-        const int lossy = le.type;  // untyped launches get the flagged layer list (flag_layers_kernel)
+        const int lossy = le.type;  // untyped launches get the flagged layer list (prep_kernel)
         if (lossy == 0) {
           double qr, nr, inr;
           opt_row_real(le.mat, qr, nr, inr);
@@ -975,7 +993,7 @@ tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
     r.qr = a.x; r.nr = a.y; r.inr = b.x; r.ni = b.y; r.qi = c.x; r.ini = c.y;
     return r;
   };
-  auto lossy_of = [&](const LayerEntry& le) { return le.type; };  // flagged layer list (flag_layers_kernel)
+  auto lossy_of = [&](const LayerEntry& le) { return le.type; };  // flagged layer list (prep_kernel)
   const int js = prm.sweep_layer;
   const OptRow exit_row = opt_row(lay[L - 1].mat);
   const OptRow in_row = opt_row(lay[0].mat);
