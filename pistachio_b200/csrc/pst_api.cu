@@ -372,10 +372,16 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
   pl->ncol = a->M ? 2 : 1;
   const int Li = a->n_layers - 2;
   const long long threads1 = (long long)n_wl_launch * a->n_theta * a->n_sweep;
+  // A stack that compiles into a short run-length program (<= 8 layer types, <= 24 ops: periodic mirrors of any depth)
+  // goes to the typed point kernel however deep it is: its layer matrices are built once per thread and repeated
+  // lossless pairs cost two FMAs per period (closed-form power), against one sincos per layer in the layer-parallel
+  // kernel -- 10 000 periodic layers on 16 384 points take tens of microseconds instead of 0.65 ms.
+  const bool typed_ok = !(a->flags & PST_FLAG_NO_LAYER_CSE) && h->n_types > 0 && Li >= 2 * h->n_types &&
+                        (int)h->ops_host.size() <= kMaxOps;
   int W = 1;
   if (a->flags & PST_FLAG_FORCE_DEEP_KERNEL) {
     W = 8;
-  } else if (!(a->flags & PST_FLAG_FORCE_POINT_KERNEL)) {
+  } else if (!(a->flags & PST_FLAG_FORCE_POINT_KERNEL) && !typed_ok) {
     const long long want = (long long)h->sm_count * 512;
     if (threads1 < want && Li >= 128) {
       while (W < 16 && threads1 * W < want && Li / (2 * W) >= 32) W *= 2;
@@ -402,8 +408,7 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
   }
   const int nthr = pl->PB * W;
   // typed path (single-segment kernel only): worth it when layer matrices repeat
-  pl->typed = !pl->seg && !(a->flags & PST_FLAG_NO_LAYER_CSE) && h->n_types > 0 && Li >= 2 * h->n_types &&
-              (int)h->ops_host.size() <= kMaxOps;
+  pl->typed = !pl->seg && typed_ok;
   pl->type_stride = 0;
   pl->row = false;
   pl->fn_typed = nullptr;

@@ -261,6 +261,14 @@ def test_periodic_power_path(eng, ref_cases):
     a = eng.eval_grid(wl, th, mat_n, np.zeros_like(mat_n), lm, d, flags=FLAG_FORCE_POINT_KERNEL).numpy()
     b = eng.eval_grid(wl, th, mat_n, np.zeros_like(mat_n), lm, d, flags=FLAG_FORCE_POINT_KERNEL | FLAG_NO_PERIODIC_POWER).numpy()
     assert not np.array_equal(a["R"], b["R"])
+    # few points and 2000 layers: the planner keeps a periodic stack on the typed point kernel (closed-form power)
+    # instead of the layer-parallel kernel, which remains available on request and agrees to rounding
+    from pistachio_b200._cabi import FLAG_FORCE_DEEP_KERNEL
+
+    dflt = eng.eval_grid(wl, th, mat_n, np.zeros_like(mat_n), lm, d).numpy()
+    deep = eng.eval_grid(wl, th, mat_n, np.zeros_like(mat_n), lm, d, flags=FLAG_FORCE_DEEP_KERNEL).numpy()
+    assert np.array_equal(dflt["R"], a["R"]) and np.array_equal(dflt["T"], a["T"])
+    np.testing.assert_allclose(deep["R"], a["R"], rtol=0, atol=1e-10)
     assert np.isfinite(a["R"]).all() and np.isfinite(a["T"]).all()
     np.testing.assert_allclose(a["R"], b["R"], rtol=0, atol=1e-10)
     np.testing.assert_allclose(a["R"] + a["T"], 1.0, atol=1e-9)
