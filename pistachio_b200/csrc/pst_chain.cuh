@@ -171,6 +171,26 @@ struct TypeRegs {
     }
     return m;
   }
+  // The same bound from fewer entries.  With both polarisations in the thread the p-wave's a sin(phi) = (1/cos) n sin
+  // dominates the s-wave's cos n sin entry by entry, and the s-wave's sin(phi)/a the p-wave's (|cos(theta)| <= 1);
+  // cos(phi) of a lossless layer never exceeds one and is no part of the growth bound (pst_chain.cuh growth_log2).
+  PST_HD unsigned max_hi_dominant(bool lossy) const {
+    if (NPOL != 2) return max_hi(lossy);
+    unsigned m = 0;
+    auto take = [&](int k) {
+      const unsigned h = (unsigned)hi_word(a[k]) & 0x7fffffffu;
+      m = h > m ? h : m;
+    };
+    if (!lossy) {
+      take(3);  // al of the p-wave
+      take(2);  // be of the s-wave
+    } else {
+      take(0); take(1);  // cos(phi)
+      take(6); take(7);  // m10 of the p-wave
+      take(4); take(5);  // m01 of the s-wave
+    }
+    return m;
+  }
 };
 
 template <int NPOL, int NC>
@@ -462,12 +482,15 @@ PST_HD PointOut finish_point_det(const ChainState<NPOL, NCOL>& fin, int p, doubl
   const bool is_s = pol_is_s<NPOL>(p, pol_first);
   const double w0 = is_s ? 1.0 : ict;
   const cplx w1 = is_s ? cplx{in0r * ict, in0i * ict} : cplx{in0r, in0i};
+  // The 1/2 of D_0^-1 is an exact power of two: without the matrix output it is left out of M00 and M10 (it cancels in
+  // R) and returned to T through the exponent -- the same bits with eight multiplications fewer per polarisation.
+  constexpr double kHalf = NCOL == 2 ? 0.5 : 1.0;
   cplx m[NCOL][2];
 #pragma unroll
   for (int c = 0; c < NCOL; ++c) {
     const double* v = fin.v[p][c];
-    const cplx a = {0.5 * w0 * v[0], 0.5 * w0 * v[1]};
-    const cplx b = cscale(cmul(w1, {v[2], v[3]}), 0.5);
+    const cplx a = {kHalf * w0 * v[0], kHalf * w0 * v[1]};
+    const cplx b = cscale(cmul(w1, {v[2], v[3]}), kHalf);
     m[c][0] = cadd(a, b);  // M[0][c]
     m[c][1] = csub(a, b);  // M[1][c]
   }
@@ -476,7 +499,7 @@ PST_HD PointOut finish_point_det(const ChainState<NPOL, NCOL>& fin, int p, doubl
   const double num = fma(m[0][1].re, m[0][1].re, m[0][1].im * m[0][1].im);  // |M10|^2
   const double iden = 1.0 / den;
   out.R = num * iden;
-  out.T = scale_sq(det_re * iden, -fin.kexp[p]);
+  out.T = scale_sq(det_re * iden, (NCOL == 2 ? 0 : 1) - fin.kexp[p]);
   if constexpr (NCOL == 2) {
     if (flags & 4u) {
       // numeric determinant like np.linalg.det (tm.py:486); the 2^kexp factors cancel

@@ -573,9 +573,9 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
         o.qr = c0.x; o.nr = c0.y; o.inr = c1.x; o.ni = c1.y; o.qi = c2.x; o.ini = c2.y;
         C.set_cplx(finish_cplx_layer<NPOL>(sC, cC, layer_phase(o.qi, ct, dC), o, ct, ict, prm.pol_first));
       }
-      unsigned mh = A.max_hi(false);
-      mh = max(mh, B.max_hi(false));
-      mh = max(mh, C.max_hi(lossyC));
+      unsigned mh = A.max_hi_dominant(false);
+      mh = max(mh, B.max_hi_dominant(false));
+      mh = max(mh, C.max_hi_dominant(lossyC));
       const int lg = growth_log2(__reduce_max_sync(0xffffffffu, mh), lossyC);
       if (lg <= 12) {  // the interpreted form takes exactly this schedule when 67 lg + 40 <= 1000
         PairPower<NPOL> S;
