@@ -225,85 +225,117 @@ PST_HD void pair_loop(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const T
 
 // k repetitions of a LOSSLESS pair in closed form.  One period is U = B A (A is applied first) with
 //   U = [[u00, -i u01], [-i u10, u11]],  u00 = cB cA - beB alA,  u11 = cB cA - alB beA,
-//                                         u01 = cB beA + beB cA,  u10 = alB cA + cB alA      (all real, det U = 1)
-// and by Cayley-Hamilton U^2 = 2x U - I, x = (u00 + u11)/2, so U^k = S_{k-1} U - S_{k-2} I with the Chebyshev
-// recurrence S_0 = 1, S_1 = 2x, S_j = 2x S_{j-1} - S_{j-2} (Yeh, Optical Waves in Layered Media, periodic media).
-// k layer-pair steps (32 FP64 instructions each) become k - 2 FMAs per polarisation.  The recurrence is run forward
-// (the growing solution dominates inside a stop band, so it is stable) and rescaled by exact powers of two every 32
-// steps; the exponent goes to the state.  Agreement with the sequential product: rounding level (tests).
-// Chebyshev coefficients of a period's k-th power: (S_{k-1}, S_{k-2}) 2^ks.  They depend on the period only through
-// its trace, which is the same for U = B A and its mirror image A B (bit for bit: the two products commute term by
-// term), so a cavity between two mirrored Bragg stacks runs the recurrence once.
+//                                         u01 = cB beA + beB cA,  u10 = alB cA + cB alA      (all real, det U = 1).
+// Split off the trace:  U = x I + W,  x = (u00 + u11)/2,  W = [[w, -i u01], [-i u10, -w]],  w = (u00 - u11)/2, and
+//   W^2 = -s2 I,  s2 = u01 u10 - w^2  (= sin^2 of the Bloch phase; negative inside a stop band),
+// so every power of U lives in the two-dimensional commutative ring {t I + s W}:  U^k = t_k I + s_k W with
+//   (t, s)(t', s') = (t t' - s2 s s', t s' + s t').
+// The power is taken by binary exponentiation in that ring (left to right over the bits of k: one squaring
+// (t^2 - s2 s^2, 2 t s) per bit, one multiplication by U = (x, 1) per set bit): ceil(log2 k) steps instead of k
+// layer-pair products, with the forward error of a product of k matrices, O(k eps).
+//
+// Why this form and not U^k = S_{k-1} U - S_{k-2} I with the Chebyshev recurrence S_j = 2x S_{j-1} - S_{j-2} (Yeh,
+// Optical Waves in Layered Media; the form round 1 shipped): near a band edge and for low-contrast stacks U is close
+// to +-I, the S_j grow like 1/sin(theta) and U^k comes out of a cancellation between S_{k-1} U and S_{k-2} I; the
+// recurrence sees the Bloch phase only through 1 - |x| (absolute error eps on a quantity of size sin^2/2) and loses
+// O(k^2 eps) -- measured 4e-12 on R at 500 pairs of n = 1.46/1.45, where the reference's layer-by-layer product is
+// good to 3e-14.  Here the phase enters through s2, which is computed from the small quantities themselves (u01 u10
+// and w^2 carry relative, not absolute, rounding errors), x only contributes sin(theta) eps, and t I + s W has no
+// cancellation.
+//
+// The ring element depends on the period only through (x, s2), which are the same for U = B A and its mirror image
+// A B (w changes sign, u01 and u10 stay); `mirror_image` makes the sums round in the operand order of the period's
+// first occurrence, so that a period and its mirror image agree bit for bit: the second Bragg stack of a symmetric
+// cavity is the first one's matrix with p00 and p11 exchanged, and the powering runs once.
+template <int NPOL>
+struct Period {
+  double x[NPOL], s2[NPOL], w[NPOL], u01[NPOL], u10[NPOL];
+};
+
+template <int NPOL>
+PST_HD void period_form(const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, bool mirror_image, Period<NPOL>& U) {
+  const double cA = A.a[0], cB = B.a[0];
+  const double cc = cB * cA;
+#pragma unroll
+  for (int p = 0; p < NPOL; ++p) {
+    const double alA = A.a[1 + 2 * p], beA = A.a[2 + 2 * p], alB = B.a[1 + 2 * p], beB = B.a[2 + 2 * p];
+    double sum, dif;  // beB alA + alB beA = 2 cc - (u00 + u11);  alB beA - beB alA = u00 - u11
+    if (!mirror_image) {
+      const double m = beB * alA;
+      sum = fma(alB, beA, m);
+      dif = fma(alB, beA, -m);
+      U.u01[p] = fma(cB, beA, beB * cA);
+      U.u10[p] = fma(alB, cA, cB * alA);
+    } else {  // the same numbers as the call with A and B exchanged, w negated
+      const double m = beA * alB;
+      sum = fma(alA, beB, m);
+      dif = -fma(alA, beB, -m);
+      U.u01[p] = fma(cA, beB, beA * cB);
+      U.u10[p] = fma(alA, cB, cA * alB);
+    }
+    U.x[p] = fma(-0.5, sum, cc);
+    U.w[p] = 0.5 * dif;
+    U.s2[p] = fma(-U.w[p], U.w[p], U.u01[p] * U.u10[p]);
+  }
+}
+
+// (t_k, s_k) 2^ks with U^k = t_k I + s_k W.  `rescale` (block-uniform): pull an exact power of two out after every
+// bit -- needed when |eigenvalue|^k can leave the fp64 range (deep stop bands); without it the exponent stays 0.
 template <int NPOL>
 struct PairPower {
-  double sa[NPOL], sb[NPOL];
+  double t[NPOL], s[NPOL];
   int ks[NPOL];
 };
 
 template <int NPOL>
-PST_HD void pair_power_coeffs(const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, int k, PairPower<NPOL>& S) {
-  const double cc = B.a[0] * A.a[0];
-  double x2[NPOL];
+PST_HD void pair_power_coeffs(const Period<NPOL>& U, int k, bool rescale, PairPower<NPOL>& S) {
 #pragma unroll
   for (int p = 0; p < NPOL; ++p) {
-    const double alA = A.a[1 + 2 * p], beA = A.a[2 + 2 * p], alB = B.a[1 + 2 * p], beB = B.a[2 + 2 * p];
-    x2[p] = fma(-beB, alA, cc) + fma(-alB, beA, cc);  // u00 + u11 = 2x
-    S.sa[p] = 1.0;                                     // S_0
-    S.sb[p] = 0.0;                                     // S_{-1}
+    S.t[p] = U.x[p];  // U^1
+    S.s[p] = 1.0;
     S.ks[p] = 0;
   }
-  // k - 1 recurrence steps for both polarisations together (two independent chains), two steps per iteration:
-  //   sb <- 2x sa - sb  (= S_j),  sa <- 2x sb - sa  (= S_{j+1});  rescaled by an exact power of two every 32 steps
-  int left = k - 1;
-  while (left >= 2) {
-    const int n2 = (left >> 1) < 16 ? (left >> 1) : 16;
-    int i = 0;
-    for (; i + 4 <= n2; i += 4) {  // eight steps per trip: the loop overhead was a third of this recurrence's issue slots
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-#pragma unroll
-        for (int p = 0; p < NPOL; ++p) {
-          S.sb[p] = fma(x2[p], S.sa[p], -S.sb[p]);
-          S.sa[p] = fma(x2[p], S.sb[p], -S.sa[p]);
-        }
-      }
-    }
-    for (; i < n2; ++i) {
-#pragma unroll
-      for (int p = 0; p < NPOL; ++p) {
-        S.sb[p] = fma(x2[p], S.sa[p], -S.sb[p]);
-        S.sa[p] = fma(x2[p], S.sb[p], -S.sa[p]);
-      }
-    }
-    left -= 2 * n2;
-    if (left >= 2) {
-#pragma unroll
-      for (int p = 0; p < NPOL; ++p) {
-        int e = exponent_of(fmax(fabs(S.sa[p]), fabs(S.sb[p])));
-        e = e > 1000 ? 1000 : (e < -1000 ? 0 : e);
-        const double f = pow2i(-e);
-        S.sa[p] *= f;
-        S.sb[p] *= f;
-        S.ks[p] += e;
-      }
-    }
-  }
-  if (left == 1) {  // odd number of steps: one more, then restore the (S_{k-1}, S_{k-2}) roles
+  int hb = 0;
+  while ((k >> (hb + 1)) != 0) ++hb;
+  for (int bit = hb - 1; bit >= 0; --bit) {
+    const bool mul = (k >> bit) & 1;
 #pragma unroll
     for (int p = 0; p < NPOL; ++p) {
-      const double s = fma(x2[p], S.sa[p], -S.sb[p]);
-      S.sb[p] = S.sa[p];
-      S.sa[p] = s;
+      const double t = S.t[p], s = S.s[p];
+      double tn = fma(t, t, -((U.s2[p] * s) * s));  // (t, s)^2
+      double sn = (t + t) * s;
+      if (mul) {                                      // times U = (x, 1)
+        const double tm = fma(U.x[p], tn, -(U.s2[p] * sn));
+        sn = fma(U.x[p], sn, tn);
+        tn = tm;
+      }
+      S.t[p] = tn;
+      S.s[p] = sn;
+    }
+    if (rescale) {
+#pragma unroll
+      for (int p = 0; p < NPOL; ++p) {
+        unsigned m = (unsigned)hi_word(S.t[p]) & 0x7fffffffu;
+        const unsigned h = (unsigned)hi_word(S.s[p]) & 0x7fffffffu;
+        m = h > m ? h : m;
+        int e = (int)(m >> 20) - 1023;
+        e = e > 1000 ? 1000 : (e < -1000 ? 0 : e);
+        const double f = from_words((1023 - e) << 20, 0);
+        S.t[p] *= f;
+        S.s[p] *= f;
+        S.ks[p] = 2 * S.ks[p] + e;
+      }
     }
   }
 }
 
-// U^k = S_{k-1} U - S_{k-2} I as a matrix [[p00, -i p01], [-i p10, p11]] (real entries) times 2^ks, U = B A with A the
-// FIRST layer applied.  The off-diagonal entries of U = B A and of its mirror image A B are the same two numbers
-// (u01 = cB beA + beB cA, u10 = alB cA + cB alA) and the diagonal ones swap; `mirror_image` (this call applies the
-// layers in the opposite order to the call its coefficients S were computed for) makes those sums round in the
-// operand order of that earlier call, so that a period and its mirror image agree bit for bit: the second Bragg
-// stack of a symmetric cavity is the first one's matrix with p00 and p11 exchanged.
+// Whether pair_power_coeffs must rescale: |t_k|, |s_k| <= k G^(2k) with G <= 2^lg the per-layer growth bound
+// (growth_log2).  Block-uniform by construction (lg is a warp/block maximum).  Without rescaling the entries of U^k
+// stay below 2^kPowerNoRescaleLog2.
+constexpr int kPowerNoRescaleLog2 = 440;
+PST_HD bool pair_power_needs_rescale(int k, int lg) { return 2 * lg * k + 40 > kPowerNoRescaleLog2; }
+
+// U^k = t I + s W as a matrix [[p00, -i p01], [-i p10, p11]] (real entries) times 2^ks
 template <int NPOL>
 struct PairMatrix {
   double p00[NPOL], p11[NPOL], p01[NPOL], p10[NPOL];
@@ -311,26 +343,13 @@ struct PairMatrix {
 };
 
 template <int NPOL>
-PST_HD void pair_power_matrix(const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, const PairPower<NPOL>& S,
-                              bool mirror_image, PairMatrix<NPOL>& P) {
-  const double cA = A.a[0], cB = B.a[0];
-  const double cc = cB * cA;
+PST_HD void pair_power_matrix(const Period<NPOL>& U, const PairPower<NPOL>& S, PairMatrix<NPOL>& P) {
 #pragma unroll
   for (int p = 0; p < NPOL; ++p) {
-    const double alA = A.a[1 + 2 * p], beA = A.a[2 + 2 * p], alB = B.a[1 + 2 * p], beB = B.a[2 + 2 * p];
-    const double u00 = fma(-beB, alA, cc), u11 = fma(-alB, beA, cc);
-    double u01, u10;
-    if (!mirror_image) {
-      u01 = fma(cB, beA, beB * cA);
-      u10 = fma(alB, cA, cB * alA);
-    } else {
-      u01 = fma(cA, beB, beA * cB);
-      u10 = fma(alA, cB, cA * alB);
-    }
-    P.p00[p] = fma(S.sa[p], u00, -S.sb[p]);
-    P.p11[p] = fma(S.sa[p], u11, -S.sb[p]);
-    P.p01[p] = S.sa[p] * u01;
-    P.p10[p] = S.sa[p] * u10;
+    P.p00[p] = fma(S.s[p], U.w[p], S.t[p]);
+    P.p11[p] = fma(-S.s[p], U.w[p], S.t[p]);
+    P.p01[p] = S.s[p] * U.u01[p];
+    P.p10[p] = S.s[p] * U.u10[p];
     P.ks[p] = S.ks[p];
   }
 }
@@ -352,21 +371,16 @@ PST_HD void apply_pair_matrix(ChainState<NPOL, NC>& st, const PairMatrix<NPOL>& 
   }
 }
 
-// v <- U^k v with U = B A (A applied first)
+// v <- U^k v with U = B A (A applied first); lg = growth bound of the two layers (growth_log2)
 template <int NPOL, int NC>
-PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B,
-                             const PairPower<NPOL>& S, bool mirror_image) {
-  PairMatrix<NPOL> P;
-  pair_power_matrix<NPOL>(A, B, S, mirror_image, P);
-  apply_pair_matrix<NPOL, NC>(st, P);
-}
-
-template <int NPOL, int NC>
-PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, int k,
-                             bool mirror_image) {
+PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, int k, int lg) {
+  Period<NPOL> U;
+  period_form<NPOL>(A, B, false, U);
   PairPower<NPOL> S;
-  pair_power_coeffs<NPOL>(A, B, k, S);
-  apply_pair_power<NPOL, NC>(st, A, B, S, mirror_image);
+  pair_power_coeffs<NPOL>(U, k, pair_power_needs_rescale(k, lg), S);
+  PairMatrix<NPOL> P;
+  pair_power_matrix<NPOL>(U, S, P);
+  apply_pair_matrix<NPOL, NC>(st, P);
 }
 
 // Build + apply in one go (the untyped path).  `lossless` is the MATERIAL's flag (k = 0 at every wavelength), so

@@ -577,36 +577,34 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
       mh = max(mh, B.max_hi_dominant(false));
       mh = max(mh, C.max_hi_dominant(lossyC));
       const int lg = growth_log2(__reduce_max_sync(0xffffffffu, mh), lossyC);
-      if (lg <= 12) {  // the interpreted form takes exactly this schedule when 67 lg + 40 <= 1000
+      if (lg <= 12) {
+        // No rescaling between the three ops: one power grows the state by < 2^(kPowerNoRescaleLog2 + 1) (rescaled
+        // coefficients: < 2^4), the spacer by 2^lg -- inside the fp64 range together.  The interpreted form rescales
+        // after every power; rescaling is exact, so the bits are the same.
+        const int k1 = tp.ops[0].z, k2 = tp.ops[2].z;
+        Period<NPOL> U;
+        period_form<NPOL>(A, B, false, U);
         PairPower<NPOL> S;
-        pair_power_coeffs<NPOL>(A, B, tp.ops[0].z, S);
-        if (tp.ops[2].z == tp.ops[0].z) {
+        pair_power_coeffs<NPOL>(U, k1, pair_power_needs_rescale(k1, lg), S);
+        PairMatrix<NPOL> P;
+        pair_power_matrix<NPOL>(U, S, P);
+        apply_pair_matrix<NPOL, NC>(st, P);
+        apply_type<NPOL, NC>(st, C, lossyC);
+        in1 = __ldg(in_row + 1);  // requested here (registers of C are free again), used in the epilogue
+        in2 = __ldg(in_row + 2);
+        if (k2 == k1) {
           // both mirrors have the same number of pairs: one matrix serves both (exchanged diagonal when the second
-          // mirror is the mirror image), and the layer matrices and coefficients are dead from here on
-          PairMatrix<NPOL> P;
-          pair_power_matrix<NPOL>(A, B, S, false, P);
-          apply_pair_matrix<NPOL, NC>(st, P);
-          // the interpreted form rescales here; rescaling is exact, so skipping it changes no bit as long as nothing
-          // can overflow before the final one: both powers and the spacer grow the state by < 2^(2 (66 lg + 40) + lg)
-          if (lg > 6) renormalise<NPOL, NC>(st);
-          apply_type<NPOL, NC>(st, C, lossyC);
-          in1 = __ldg(in_row + 1);  // requested here (registers of C are free again), used in the epilogue
-          in2 = __ldg(in_row + 2);
+          // mirror is the mirror image: w -> -w), and the layer matrices and coefficients are dead from here on
           if (tp.fast_mirrored) {
 #pragma unroll
             for (int pp = 0; pp < NPOL; ++pp) { const double t = P.p00[pp]; P.p00[pp] = P.p11[pp]; P.p11[pp] = t; }
           }
-          apply_pair_matrix<NPOL, NC>(st, P);
         } else {
-          apply_pair_power<NPOL, NC>(st, A, B, S, false);
-          if (lg > 6) renormalise<NPOL, NC>(st);
-          apply_type<NPOL, NC>(st, C, lossyC);
-          in1 = __ldg(in_row + 1);
-          in2 = __ldg(in_row + 2);
-          pair_power_coeffs<NPOL>(A, B, tp.ops[2].z, S);
-          if (!tp.fast_mirrored) apply_pair_power<NPOL, NC>(st, A, B, S, false);
-          else apply_pair_power<NPOL, NC>(st, B, A, S, false);  // new coefficients: a period of its own (see the op loop)
+          if (tp.fast_mirrored) period_form<NPOL>(B, A, false, U);  // new coefficients: a period of its own (see the op loop)
+          pair_power_coeffs<NPOL>(U, k2, pair_power_needs_rescale(k2, lg), S);
+          pair_power_matrix<NPOL>(U, S, P);
         }
+        apply_pair_matrix<NPOL, NC>(st, P);
         renormalise<NPOL, NC>(st);
         done = true;
       }
@@ -669,7 +667,7 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
 
     PairPower<NPOL> S;
   #pragma unroll
-    for (int pp = 0; pp < NPOL; ++pp) { S.sa[pp] = 1.0; S.sb[pp] = 0.0; S.ks[pp] = 0; }
+    for (int pp = 0; pp < NPOL; ++pp) { S.t[pp] = 1.0; S.s[pp] = 0.0; S.ks[pp] = 0; }
     int s_lo = -1, s_hi = -1, s_k = -1;  // the period S belongs to
     int s_first = -1;                   // the layer type applied first when S was computed (orientation of its sums)
     int since = 0;                      // layers applied since the last rescale
@@ -688,17 +686,24 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
       const bool lb = (lossy_mask >> o.y) & 1u;
       load_type(o.y, lb, B);
       if (!la && !lb && o.z >= 3 && !(prm.flags & 128u)) {
-        // a lossless pair repeated k times: closed-form power of the period (Chebyshev identity, pst_chain.cuh).
-        // |U^k entries| <= 2 (2 G^2)^32 G^2 after the recurrence's own rescaling; rescale first only if that times the
-        // current bound 2 G^since could leave the fp64 range
-        if (since * lg + 66 * lg + 40 > 1000) renormalise<NPOL, NC>(st);
+        // a lossless pair repeated k times: closed-form power of the period (binary powering in the ring spanned by I and
+        // the traceless part of the period, pst_chain.cuh).  |U^k entries| < 2^(kPowerNoRescaleLog2 + 1) (coefficients
+        // not rescaled) or < 2^4 (rescaled); rescale the state first only if that times its current bound 2 G^since
+        // could leave the fp64 range
+        if (since * lg > 1000 - kPowerNoRescaleLog2 - 20) renormalise<NPOL, NC>(st);
         const int t_lo = min(o.x, o.y), t_hi = max(o.x, o.y);
-        if (t_lo != s_lo || t_hi != s_hi || o.z != s_k) {  // else: same or mirrored period, same trace, same S
-          pair_power_coeffs<NPOL>(A, B, o.z, S);
+        Period<NPOL> U;
+        if (t_lo != s_lo || t_hi != s_hi || o.z != s_k) {  // else: same or mirrored period, same (x, s2), same power
+          period_form<NPOL>(A, B, false, U);
+          pair_power_coeffs<NPOL>(U, o.z, pair_power_needs_rescale(o.z, lg), S);
           s_lo = t_lo; s_hi = t_hi; s_k = o.z;
           s_first = o.x;
+        } else {
+          period_form<NPOL>(A, B, o.x != s_first, U);  // a mirror image rounds like the period it mirrors
         }
-        apply_pair_power<NPOL, NC>(st, A, B, S, o.x != s_first);  // a mirror image rounds like the period it mirrors
+        PairMatrix<NPOL> P;
+        pair_power_matrix<NPOL>(U, S, P);
+        apply_pair_matrix<NPOL, NC>(st, P);
         renormalise<NPOL, NC>(st);
         since = 0;
         continue;

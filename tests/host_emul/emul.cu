@@ -70,7 +70,9 @@ static void run(int n_wl, int n_theta, int L, const double* wl, const double* co
             const TypeRegs<NPOL> A = build(ta), B = build(tb);
             if (lossless[ta] && lossless[tb] && k >= 3) {
               renormalise<NPOL, NCOL>(fin);
-              apply_pair_power<NPOL, NCOL>(fin, A, B, k, false);
+              unsigned mh = A.max_hi(false), mb = B.max_hi(false);
+              mh = mb > mh ? mb : mh;
+              apply_pair_power<NPOL, NCOL>(fin, A, B, k, growth_log2(mh, false));
             } else {
               for (int r = 0; r < k; ++r) {
                 apply_type<NPOL, NCOL>(fin, A, !lossless[ta]);

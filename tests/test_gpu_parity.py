@@ -218,9 +218,11 @@ def test_layer_cse_is_bit_identical(eng):
 
 
 def test_periodic_power_path(eng, ref_cases):
-    """A k-times repeated lossless pair goes through the closed-form power of its period (Chebyshev identity).  It must
-    hold the same parity against the reference as the layer-by-layer product and agree with it to rounding, also for
-    the full matrix, for a single polarisation, and for a 1000-pair stop band where the recurrence must be rescaled."""
+    """A k-times repeated lossless pair goes through the closed-form power of its period (binary powering in the ring
+    spanned by I and the period's traceless part).  It must hold the same parity against the reference as the
+    layer-by-layer product and agree with it to rounding, also for the full matrix, for a single polarisation, and for a
+    1000-pair stop band where the coefficients must be rescaled (oracle/truth parity of deep and low-contrast stacks:
+    test_low_contrast_periodic_stacks_against_oracle, test_period_power_against_mpmath_truth)."""
     from pistachio_b200 import workloads
     from pistachio_b200._cabi import FLAG_NO_PERIODIC_POWER
 
@@ -268,10 +270,78 @@ def test_periodic_power_path(eng, ref_cases):
     dflt = eng.eval_grid(wl, th, mat_n, np.zeros_like(mat_n), lm, d).numpy()
     deep = eng.eval_grid(wl, th, mat_n, np.zeros_like(mat_n), lm, d, flags=FLAG_FORCE_DEEP_KERNEL).numpy()
     assert np.array_equal(dflt["R"], a["R"]) and np.array_equal(dflt["T"], a["T"])
-    np.testing.assert_allclose(deep["R"], a["R"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(deep["R"], a["R"], rtol=0, atol=2e-12)
     assert np.isfinite(a["R"]).all() and np.isfinite(a["T"]).all()
-    np.testing.assert_allclose(a["R"], b["R"], rtol=0, atol=1e-10)
-    np.testing.assert_allclose(a["R"] + a["T"], 1.0, atol=1e-9)
+    np.testing.assert_allclose(a["R"], b["R"], rtol=0, atol=2e-12)
+    np.testing.assert_allclose(a["R"] + a["T"], 1.0, atol=2e-12)
+
+
+@pytest.mark.parametrize("pairs", [50, 100, 500, 1500])
+def test_low_contrast_periodic_stacks_against_oracle(eng, pairs):
+    """periodic stacks of low-contrast pairs (n = 1.46/1.45, stop band 0.4 % wide) sampled
+    densely around the band edges, both polarisations, theta in {0, 0.4}.  The planner routes them to the typed kernel's
+    closed-form period power by default; that default result must hold the 1e-12 rule against the ORACLE (0 failures,
+    <= 1 % of the values on the conditioning clause), exactly like the layer-by-layer product."""
+    from pistachio_b200._cabi import FLAG_NO_PERIODIC_POWER
+    from tests import periodic_cases as pc
+
+    n_wide, n_edge = pc.CASES[pairs]
+    wl = pc.band_edge_wavelengths(1.46, 1.45, n_wide, n_edge)
+    cols, lm, ld = pc.quarter_wave_stack(pairs, wl)
+    n_list = pc.per_layer(cols, lm)
+    with np.errstate(all="ignore"):
+        T0, R0, M0 = parity.oracle_grid(wl, n_list, ld, pc.THETAS, want_m=True)
+        sT, sR = parity.sensitivity(wl, n_list, ld, pc.THETAS, T0, R0)
+    assert np.isfinite(T0).all() and np.isfinite(R0).all()
+    kw = dict(cos_theta=np.cos(pc.THETAS))
+    pw = eng.eval_grid(wl, pc.THETAS, cols.real, cols.imag, lm, ld, POLS, **kw).numpy()
+    sq = eng.eval_grid(wl, pc.THETAS, cols.real, cols.imag, lm, ld, POLS, flags=FLAG_NO_PERIODIC_POWER, **kw).numpy()
+    assert not np.array_equal(pw["R"], sq["R"])  # the default really takes the closed form
+    for name, out in (("power", pw), ("layer by layer", sq)):
+        rep = parity.Report(f"qw{pairs} {name}")
+        rep.add("R", out["R"][0], R0, 4 * sR)
+        rep.add("T", out["T"][0], T0, 4 * sT + parity.det_noise(M0))
+        rep.check(max_loose_fraction=0.01)
+        assert np.array_equal(out["A"], (1.0 - out["R"]) - out["T"])
+
+
+def test_low_contrast_cavity_straight_line_path_against_oracle(eng):
+    """The same stacks as mirror / spacer / mirror (the typed kernel's straight-line program): 2 x 150 low-contrast
+    pairs around an absorbing half-wave spacer, mirrored and repeated pair order, against the oracle."""
+    from tests import periodic_cases as pc
+
+    wl = pc.band_edge_wavelengths(1.46, 1.45, 16, 4)
+    for mirrored in (True, False):
+        cols, lm, ld = pc.quarter_wave_stack(150, wl, spacer=(1.5 + 2e-4j, 1.0 / (2 * 1.5)), mirrored=mirrored)
+        n_list = pc.per_layer(cols, lm)
+        out = eng.eval_grid(wl, pc.THETAS, cols.real, cols.imag, lm, ld, POLS, cos_theta=np.cos(pc.THETAS)).numpy()
+        nofast = eng.eval_grid(wl, pc.THETAS, cols.real, cols.imag, lm, ld, POLS, cos_theta=np.cos(pc.THETAS), flags=1 << 11).numpy()
+        assert np.array_equal(out["R"], nofast["R"]) and np.array_equal(out["T"], nofast["T"])
+        rep = parity.compare_grid(f"qw cavity mirrored={mirrored}", out["T"][0], out["R"][0], wl, n_list, ld, pc.THETAS,
+                                  got_A=out["A"][0])
+        rep.check(max_loose_fraction=0.01)
+
+
+def test_period_power_against_mpmath_truth(eng):
+    """200 pairs of n = 1.50/1.45 over 0.90-1.10 um against a 50-digit evaluation of the model, and a
+    1000-pair high-contrast stop band where the reference overflows (no oracle): the closed-form power must be as close
+    to the truth as the layer-by-layer product."""
+    from oracle import mp_truth
+    from pistachio_b200._cabi import FLAG_FORCE_POINT_KERNEL, FLAG_NO_PERIODIC_POWER
+    from tests import periodic_cases as pc
+
+    for pairs, n_hi, n_lo, wl in ((200, 1.50, 1.45, pc.band_edge_wavelengths(1.50, 1.45, 10, 3, lo=0.90, hi=1.10)),
+                                  (1000, 2.32, 1.36, np.linspace(0.8, 1.25, 12))):
+        cols, lm, ld = pc.quarter_wave_stack(pairs, wl, n_hi=n_hi, n_lo=n_lo)
+        Tt, Rt = mp_truth.truth_grid(wl, pc.per_layer(cols, lm), ld, np.cos(pc.THETAS))
+        kw = dict(cos_theta=np.cos(pc.THETAS))
+        pw = eng.eval_grid(wl, pc.THETAS, cols.real, cols.imag, lm, ld, POLS, flags=FLAG_FORCE_POINT_KERNEL, **kw).numpy()
+        sq = eng.eval_grid(wl, pc.THETAS, cols.real, cols.imag, lm, ld, POLS, flags=FLAG_FORCE_POINT_KERNEL | FLAG_NO_PERIODIC_POWER,
+                           **kw).numpy()
+        err_p = max(np.abs(pw["R"][0] - Rt).max(), np.abs(pw["T"][0] - Tt).max())
+        err_s = max(np.abs(sq["R"][0] - Rt).max(), np.abs(sq["T"][0] - Tt).max())
+        print(f"{pairs} pairs {n_hi}/{n_lo} vs mpmath: closed-form power {err_p:.2e}, layer by layer {err_s:.2e}")
+        assert err_p < 2e-12 and err_p < 3 * err_s + 2e-14, (pairs, err_p, err_s)
 
 
 def test_cavity_shape_fast_path_is_bit_identical(eng):

@@ -53,7 +53,7 @@ def test_emul_matches_reference_cases(emul, ref_cases, name):
     c = ref_cases[name]
     R, T, A, _ = run_emul(emul, c["wl"], list(c["n"]), list(c["d"]), c["theta"])
     rep = parity.compare_grid(name, T, R, c["wl"], list(c["n"]), list(c["d"]), c["theta"], c["T"], c["R"], got_A=A)
-    rep.check(max_loose_fraction=0.05)
+    rep.check(max_loose_fraction=0.01)
 
 
 def test_emul_segmented_combine_matches_pointwise(emul, ref_cases):
@@ -67,7 +67,7 @@ def test_emul_segmented_combine_matches_pointwise(emul, ref_cases):
     R1, T1, _, _ = run_emul(emul, c["wl"], list(c["n"]), list(c["d"]), c["theta"])
     R, T, _, _ = run_emul(emul, c["wl"], list(c["n"]), list(c["d"]), c["theta"], W=4)
     rep = parity.compare_grid("c2_sub_W4", T, R, c["wl"], list(c["n"]), list(c["d"]), c["theta"], c["T"], c["R"])
-    rep.check(max_loose_fraction=0.05)
+    rep.check(max_loose_fraction=0.01)
 
 
 def test_emul_full_matrix_and_numeric_det(emul, ref_cases):
@@ -116,13 +116,14 @@ def test_emul_thick_absorber_and_deep_bragg_stay_finite(emul):
 
 
 def test_emul_periodic_power_matches_reference_and_sequential(emul, ref_cases):
-    """Closed-form power of a repeated lossless pair (Chebyshev identity, apply_pair_power) vs the reference fixture
-    and vs the layer-by-layer product, on the 2 x 20-pair DBR cavity and on a 1000-pair stop band (rescaled recurrence)."""
+    """Closed-form power of a repeated lossless pair (binary powering of the period, apply_pair_power) vs the reference
+    fixture and vs the layer-by-layer product, on the 2 x 20-pair DBR cavity and on a 1000-pair stop band (rescaled
+    coefficients)."""
     c = ref_cases["c2_sub"]
     Rs, Ts, _, Ms = run_emul(emul, c["wl"], list(c["n"]), list(c["d"]), c["theta"], ncol=2)
     Rp, Tp, Ap, Mp = run_emul(emul, c["wl"], list(c["n"]), list(c["d"]), c["theta"], ncol=2, flags=256)
     rep = parity.compare_grid("c2_sub_power", Tp, Rp, c["wl"], list(c["n"]), list(c["d"]), c["theta"], c["T"], c["R"], got_A=Ap)
-    rep.check(max_loose_fraction=0.05)
+    rep.check(max_loose_fraction=0.01)
     assert np.abs(Rp - Rs).max() < 2e-13 and np.abs(Tp - Ts).max() < 2e-13
     scale = np.abs(Ms).max(axis=(-1, -2), keepdims=True)
     assert np.all(np.abs(Mp - Ms) <= 1e-12 * scale)
@@ -134,6 +135,53 @@ def test_emul_periodic_power_matches_reference_and_sequential(emul, ref_cases):
     Rs, Ts, _, _ = run_emul(emul, wl, n_list, d, [0.0, 0.6])
     Rp, Tp, _, _ = run_emul(emul, wl, n_list, d, [0.0, 0.6], flags=256)
     assert np.isfinite(Rp).all() and np.isfinite(Tp).all()
-    np.testing.assert_allclose(Rp, Rs, rtol=0, atol=1e-10)
-    np.testing.assert_allclose(Tp, Ts, rtol=0, atol=1e-10)
-    np.testing.assert_allclose(Rp + Tp, 1.0, atol=1e-9)
+    np.testing.assert_allclose(Rp, Rs, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(Tp, Ts, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(Rp + Tp, 1.0, atol=1e-12)
+    # the reference overflows here (no oracle): adjudicate against the 50-digit evaluation of the model
+    from oracle import mp_truth
+
+    Tt, Rt = mp_truth.truth_grid(wl, n_list, d, np.cos([0.0, 0.6]))
+    err_p = max(np.abs(Rp - Rt).max(), np.abs(Tp - Tt).max())
+    err_s = max(np.abs(Rs - Rt).max(), np.abs(Ts - Tt).max())
+    assert err_p < 2e-12 and err_p < 2 * err_s + 1e-13, (err_p, err_s)
+
+
+@pytest.mark.parametrize("pairs", [50, 100, 500, 1500])
+def test_emul_low_contrast_periodic_stacks_against_oracle(emul, pairs):
+    """Low-contrast quarter-wave stacks around their band edges, both polarisations, theta in {0, 0.4}: the closed-form
+    period power (flags = 256: what the typed kernel does by default) must hold the 1e-12 rule against the ORACLE like
+    the layer-by-layer product does -- not merely agree with the other path (VERDICT round 1, weak #1)."""
+    from tests import periodic_cases as pc
+
+    n_wide, n_edge = pc.CASES[pairs]
+    wl = pc.band_edge_wavelengths(1.46, 1.45, n_wide, n_edge)
+    cols, lm, ld = pc.quarter_wave_stack(pairs, wl)
+    n_list = pc.per_layer(cols, lm)
+    T0, R0, M0 = parity.oracle_grid(wl, n_list, ld, pc.THETAS, want_m=True)
+    assert np.isfinite(T0).all() and np.isfinite(R0).all()
+    sT, sR = parity.sensitivity(wl, n_list, ld, pc.THETAS, T0, R0)
+    for flags in (256, 0):
+        R, T, A, _ = run_emul(emul, wl, n_list, ld, pc.THETAS, flags=flags)
+        rep = parity.Report(f"qw{pairs} flags={flags}")
+        rep.add("R", R, R0, 4 * sR)
+        rep.add("T", T, T0, 4 * sT + parity.det_noise(M0))
+        rep.check(max_loose_fraction=0.01)
+
+
+def test_emul_period_power_against_mpmath_truth(emul):
+    """ADVICE round 1: n = 1.50/1.45 quarter-wave stack, 200 pairs, against a 50-digit evaluation of the model.  The
+    closed-form power must be as close to the truth as the layer-by-layer product (round 1's recurrence: 4.6e-12)."""
+    from oracle import mp_truth
+    from tests import periodic_cases as pc
+
+    wl = pc.band_edge_wavelengths(1.50, 1.45, 10, 3, lo=0.90, hi=1.10)
+    cols, lm, ld = pc.quarter_wave_stack(200, wl, n_hi=1.50, n_lo=1.45)
+    n_list = pc.per_layer(cols, lm)
+    Tt, Rt = mp_truth.truth_grid(wl, n_list, ld, np.cos(pc.THETAS))
+    Rp, Tp, _, _ = run_emul(emul, wl, n_list, ld, pc.THETAS, flags=256)
+    Rs, Ts, _, _ = run_emul(emul, wl, n_list, ld, pc.THETAS, flags=0)
+    err_p = max(np.abs(Rp - Rt).max(), np.abs(Tp - Tt).max())
+    err_s = max(np.abs(Rs - Rt).max(), np.abs(Ts - Tt).max())
+    print(f"200 pairs 1.50/1.45 vs mpmath: closed-form power {err_p:.2e}, layer by layer {err_s:.2e}")
+    assert err_p < 1e-12 and err_p < 3 * err_s + 2e-14
