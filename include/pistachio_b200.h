@@ -15,7 +15,11 @@
  *    (small [host] metadata is copied during the call).
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Work
  *    is enqueued asynchronously; the caller synchronises.  A handle owns device
- *    scratch memory and must be used from one stream at a time.
+ *    scratch memory (optical tables, layer lists); calls that use it are ordered
+ *    across streams by the library itself (each such call waits, on the device, for
+ *    the previous one's work before overwriting the tables), so one handle may be
+ *    used from several streams in turn.  A handle is NOT safe for concurrent calls
+ *    from several host threads: use one handle per thread.
  *  - complex numbers are interleaved (re, im) doubles, numpy complex128 layout.
  *  - polarisation codes: PST_POL_S / PST_POL_P, the reference's "s-wave"/"p-wave".
  *  - angles are radians; wavelengths and thicknesses share one (arbitrary) unit.
@@ -51,8 +55,10 @@ extern "C" {
 #define PST_FLAG_NO_SWEEP_REUSE (1u << 5)     /* thickness sweeps: rebuild the whole chain for every thickness instead
                                                  of reusing the prefix/suffix products (K3) -- ablation */
 #define PST_FLAG_NO_PERIODIC_POWER (1u << 7)  /* apply a k-times repeated lossless layer pair k times instead of through
-                                                 the closed-form power of its period U^k = S_{k-1} U - S_{k-2} I
-                                                 (Chebyshev identity); both agree to rounding -- ablation */
+                                                 the closed-form power of its period (binary powering of U = x I + W in
+                                                 the ring spanned by I and the traceless part W, W^2 = -s2 I: log2 k
+                                                 steps, forward error O(k eps) like the product); both agree to
+                                                 rounding -- ablation */
 #define PST_FLAG_NO_BULK_COPY (1u << 6)       /* stage tables with plain 128-bit loads instead of cp.async.bulk (ablation) */
 #define PST_FLAG_MULTICAST_OUT (1u << 8)       /* R, T, A are addresses inside an NVLink multicast mapping (CUDA multicast
                                                  object, e.g. torch symmetric memory's multicast_ptr, offset to this

@@ -98,7 +98,28 @@ struct pst_handle_s {
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   DevBuf<double> hp_in;       // wl | theta | cos | mat_n | mat_k | sweep_d
   DevBuf<double> hp_out[2];   // per-chunk R|T|A (|M)
+  // Ordering of the scratch above across streams: every entry point that touches it first makes its stream wait for
+  // the event recorded behind the previous such call (scratch_acquire) and records the event again behind its own
+  // work (scratch_release).  Calls on one stream pay one event record; a call on another stream -- or
+  // pst_eval_grid_host, which runs on internal streams -- queues behind the work that still reads the tables.
+  cudaEvent_t ev_scratch = nullptr;
+  cudaStream_t scratch_stream = nullptr;
+  bool scratch_busy = false;
 };
+
+namespace {
+int scratch_acquire(pst_handle_t h, cudaStream_t st) {
+  if (!h->ev_scratch) PST_CUDA(cudaEventCreateWithFlags(&h->ev_scratch, cudaEventDisableTiming));
+  if (h->scratch_busy && h->scratch_stream != st) PST_CUDA(cudaStreamWaitEvent(st, h->ev_scratch, 0));
+  return PST_OK;
+}
+int scratch_release(pst_handle_t h, cudaStream_t st) {
+  PST_CUDA(cudaEventRecord(h->ev_scratch, st));
+  h->scratch_stream = st;
+  h->scratch_busy = true;
+  return PST_OK;
+}
+}  // namespace
 
 // ------------------------------------------------------------------------------------------------ lifetime
 extern "C" int pst_abi_version(void) { return PST_ABI_VERSION; }
@@ -139,6 +160,7 @@ extern "C" int pst_destroy(pst_handle_t h) {
   }
   if (h->s_compute) cudaStreamDestroy(h->s_compute);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  if (h->ev_scratch) cudaEventDestroy(h->ev_scratch);
   delete h;
   return PST_OK;
 }
@@ -162,6 +184,7 @@ extern "C" int pst_resample_tables(pst_handle_t h, int n_tab, const int* tab_off
   }
   DeviceGuard g(h->device);
   cudaStream_t st = (cudaStream_t)stream;
+  PST_TRY(scratch_acquire(h, st));
   PST_TRY(h->taboff.ensure(n_tab + 1));
   PST_CUDA(cudaMemcpyAsync(h->taboff.p, tab_off, (n_tab + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
   const size_t smem = (size_t)max_rows * sizeof(double) <= 32 * 1024 ? (size_t)max_rows * sizeof(double) : 0;
@@ -169,7 +192,7 @@ extern "C" int pst_resample_tables(pst_handle_t h, int n_tab, const int* tab_off
   resample_kernel<<<grid, 256, smem, st>>>(n_tab, h->taboff.p, tab_wl, tab_n, tab_k, wl, n_wl, out_n, out_k);
   PST_CUDA(cudaGetLastError());
   h->launches += 1;
-  return PST_OK;
+  return scratch_release(h, st);
 }
 
 // ------------------------------------------------------------------------------------------------ grid
@@ -193,6 +216,14 @@ ChainKernel pick_chain(int npol, int ncol, bool so, bool sl, bool seg) {
   if (npol == 1 && ncol == 2) return chain_variant<1, 2>(so, sl, seg);
   if (npol == 2 && ncol == 1) return chain_variant<2, 1>(so, sl, seg);
   if (npol == 2 && ncol == 2) return chain_variant<2, 2>(so, sl, seg);
+  return nullptr;
+}
+
+using CavityKernel = void (*)(const GridParams, const CavityPlan);
+CavityKernel pick_cavity(int npol, bool row) {
+  // 2 polarisations: 80 registers, 6 blocks/SM; 1 polarisation: 64 registers, 8 blocks/SM
+  if (npol == 2) return row ? tmm_cavity_kernel<2, 6, true> : tmm_cavity_kernel<2, 6, false>;
+  if (npol == 1) return row ? tmm_cavity_kernel<1, 8, true> : tmm_cavity_kernel<1, 8, false>;
   return nullptr;
 }
 
@@ -360,11 +391,50 @@ inline void set_plain_out(GridParams& prm) {
 
 struct ChainPlan {
   int npol, npol_out, ncol, W, PB, tl_rows, opt_row_bytes, type_stride;
-  bool so, sl, seg, typed, row;
+  bool so, sl, seg, typed, row, cavity;
   size_t smem;
   ChainKernel fn;
   TypedKernel fn_typed;
+  CavityKernel fn_cavity;
+  CavityPlan cp;
 };
+
+// Program shape "periodic mirror / spacer / periodic mirror over the same pair of layer types" (a DBR microcavity):
+// fills the cavity kernel's plan from the run-length ops of sync_layers.
+bool cavity_shape(pst_handle_t h, const pst_grid_args* a, CavityPlan* cp) {
+  if (h->ops_host.size() != 3) return false;
+  const int4 o0 = h->ops_host[0], o1 = h->ops_host[1], o2 = h->ops_host[2];
+  const bool pair_ok = o0.y >= 0 && o0.z >= 3 && o2.y >= 0 && o2.z >= 3 && o0.x != o0.y &&
+                       ((o2.x == o0.x && o2.y == o0.y) || (o2.x == o0.y && o2.y == o0.x));
+  const bool spacer_ok = o1.y < 0 && o1.z == 1 && o1.x != o0.x && o1.x != o0.y;
+  if (!pair_ok || !spacer_ok) return false;
+  int sweep_type = -1;
+  for (int t = 0; t < h->n_types; ++t)
+    if (h->type_layer[t] == a->sweep_layer) sweep_type = t;
+  if (sweep_type == o0.x || sweep_type == o0.y) return false;  // a swept mirror layer is not a periodic mirror
+  std::memset(cp, 0, sizeof(*cp));
+  const int t3[3] = {o0.x, o0.y, o1.x};
+  for (int i = 0; i < 3; ++i) {
+    const int j = h->type_layer[t3[i]];
+    for (int f = 0; f < 6; ++f) cp->src[6 * i + f] = a->layer_mat[j] * 6 + f;  // OptRow order: qr nr inr ni qi ini
+    cp->d[i] = a->layer_d[j];
+  }
+  const int m_last = a->layer_mat[a->n_layers - 1], m_first = a->layer_mat[0];
+  cp->src[18] = m_last * 6 + 1;   // n_exit
+  cp->src[19] = m_last * 6 + 3;
+  cp->src[20] = m_first * 6 + 2;  // 1 / n_incidence
+  cp->src[21] = m_first * 6 + 5;
+  cp->k1 = o0.z;
+  cp->k2 = o2.z;
+  cp->mirrored = (o2.x == o0.x) ? 0 : 1;
+  cp->c_swept = (o1.x == sweep_type) ? 1 : 0;
+  cp->lossy_a = 1u << o0.x;
+  cp->lossy_ab = (1u << o0.x) | (1u << o0.y);
+  cp->lossy_c = 1u << o1.x;
+  cp->tiles = 1;
+  cp->lossy_types = h->lossy_types.p;
+  return true;
+}
 
 int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPlan* pl) {
   pl->npol_out = __builtin_popcount(a->pol_mask);
@@ -411,7 +481,9 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
   pl->typed = !pl->seg && typed_ok;
   pl->type_stride = 0;
   pl->row = false;
+  pl->cavity = false;
   pl->fn_typed = nullptr;
+  pl->fn_cavity = nullptr;
   if (pl->typed) {
     int units = (h->n_types * (kTypeRecBytes + 4) + 15) / 16;  // records + one exponent int per type
     if (units % 2 == 0) units += 1;
@@ -422,8 +494,26 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
     // row mode: one wavelength per block row when 128-wide theta tiles waste < 7 % of the lanes
     const int tiles = (a->n_theta + 127) / 128;
     pl->row = n_wl_launch <= 65535 && a->n_theta >= 120 && tiles * 128 * 100 <= a->n_theta * 107;
-    pl->fn_typed = pick_typed(pl->npol, pl->ncol, pl->row);
     pl->fn = nullptr;
+    if (pl->ncol == 1 && !(a->flags & (PST_FLAG_NO_PERIODIC_POWER | PST_FLAG_NO_SHAPE_FASTPATH)) && cavity_shape(h, a, &pl->cp)) {
+      // straight-line cavity kernel; in row mode a block walks several theta tiles of its wavelength so that the
+      // block-uniform table rows are fetched once -- as many tiles as still leave >= 16 waves of blocks
+      pl->cavity = true;
+      pl->smem = 0;
+      pl->fn_cavity = pick_cavity(pl->npol, pl->row);
+      if (!pl->fn_cavity) return fail(PST_E_INVALID, "pst_eval_grid: no cavity kernel variant for this configuration");
+      if (pl->row) {
+        const long long slots = (long long)h->sm_count * (pl->npol == 2 ? 6 : 8);
+        for (int t : {8, 4, 2}) {
+          if (t <= tiles && (long long)((tiles + t - 1) / t) * n_wl_launch * a->n_sweep >= 16 * slots) {
+            pl->cp.tiles = t;
+            break;
+          }
+        }
+      }
+      return PST_OK;
+    }
+    pl->fn_typed = pick_typed(pl->npol, pl->ncol, pl->row);
     if (!pl->fn_typed) return fail(PST_E_INVALID, "pst_eval_grid: no typed kernel variant for this configuration");
     if (pl->smem > 48 * 1024)
       PST_CUDA(cudaFuncSetAttribute((const void*)pl->fn_typed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
@@ -488,28 +578,6 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
     }
     for (int i = 0; i < tp.n_ops; ++i) tp.ops[i] = h->ops_host[i];
     tp.lossy_types = h->lossy_types.p;
-    // program shape: periodic mirror / spacer / periodic mirror over the same pair of layer types
-    if (tp.n_ops == 3) {
-      const int4 o0 = tp.ops[0], o1 = tp.ops[1], o2 = tp.ops[2];
-      const bool pair_ok = o0.y >= 0 && o0.z >= 3 && o2.y >= 0 && o2.z >= 3 && o0.x != o0.y &&
-                           ((o2.x == o0.x && o2.y == o0.y) || (o2.x == o0.y && o2.y == o0.x));
-      const bool spacer_ok = o1.y < 0 && o1.z == 1 && o1.x != o0.x && o1.x != o0.y;
-      const bool sweep_ok = tp.sweep_type != o0.x && tp.sweep_type != o0.y;
-      if (pair_ok && spacer_ok && sweep_ok) {
-        tp.shape = 1;
-        const int t3[3] = {o0.x, o0.y, o1.x};
-        for (int i = 0; i < 3; ++i) {
-          tp.fast_row[i] = tp.type_mat[t3[i]] * 3;
-          tp.fast_d[i] = tp.type_d[t3[i]];
-        }
-        tp.fast_row_last = tp.mat_last * 3;
-        tp.fast_row_first = tp.mat_first * 3;
-        tp.fast_lossy_ab = (1u << o0.x) | (1u << o0.y);
-        tp.fast_lossy_c = 1u << o1.x;
-        tp.fast_c_swept = (o1.x == tp.sweep_type) ? 1 : 0;
-        tp.fast_mirrored = (o2.x == o0.x) ? 0 : 1;
-      }
-    }
   }
   prm.use_bulk = (a->flags & PST_FLAG_NO_BULK_COPY) ? 0 : 1;
   const long long nblk = (prm.points + pl.PB - 1) / pl.PB;
@@ -531,8 +599,12 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
     }
     set_plain_out(prm);
     dim3 grid((unsigned)nblk, (unsigned)ns), block(pl.PB, pl.W);
-    if (pl.typed && pl.row) grid = dim3((unsigned)((a->n_theta + 127) / 128), (unsigned)n_wl_launch, (unsigned)ns);
-    if (pl.typed) pl.fn_typed<<<grid, block, pl.smem, st>>>(prm, tp);
+    if (pl.typed && pl.row) {
+      const int tiles = (a->n_theta + 127) / 128, per = pl.cavity ? pl.cp.tiles : 1;
+      grid = dim3((unsigned)((tiles + per - 1) / per), (unsigned)n_wl_launch, (unsigned)ns);
+    }
+    if (pl.cavity) pl.fn_cavity<<<grid, block, 0, st>>>(prm, pl.cp);
+    else if (pl.typed) pl.fn_typed<<<grid, block, pl.smem, st>>>(prm, tp);
     else pl.fn<<<grid, block, pl.smem, st>>>(prm);
     PST_CUDA(cudaGetLastError());
     h->launches += 1;
@@ -720,14 +792,21 @@ extern "C" int pst_eval_grid(pst_handle_t h, const pst_grid_args* a, void* strea
   DeviceGuard g(h->device);
   if (!g.ok) return fail(PST_E_CUDA, "pst_eval_grid: cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
+  PST_TRY(scratch_acquire(h, st));
   PST_TRY(sync_layers(h, a, st));
   PST_TRY(run_prep(h, a, a->wl, a->theta, a->cos_theta, a->mat_n, a->mat_k, st));
-  if (a->flags & PST_FLAG_SNELL) return launch_snell(h, a, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, a->M, st);
-  if (a->flags & PST_FLAG_FP32) return launch_chain_f32(h, a, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, st);
-  if (use_sweep_kernel(a)) return launch_sweep(h, a, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, st);
-  ChainPlan pl;
-  PST_TRY(plan_chain(h, a, a->n_wl, &pl));
-  return launch_chain(h, a, pl, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, a->M, st);
+  if (a->flags & PST_FLAG_SNELL) {
+    PST_TRY(launch_snell(h, a, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, a->M, st));
+  } else if (a->flags & PST_FLAG_FP32) {
+    PST_TRY(launch_chain_f32(h, a, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, st));
+  } else if (use_sweep_kernel(a)) {
+    PST_TRY(launch_sweep(h, a, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, st));
+  } else {
+    ChainPlan pl;
+    PST_TRY(plan_chain(h, a, a->n_wl, &pl));
+    PST_TRY(launch_chain(h, a, pl, 0, a->n_wl, a->sweep_d, a->R, a->T, a->A, a->M, st));
+  }
+  return scratch_release(h, st);
 }
 
 extern "C" int pst_eval_grid_host(pst_handle_t h, const pst_grid_args* a) {
@@ -746,6 +825,7 @@ extern "C" int pst_eval_grid_host(pst_handle_t h, const pst_grid_args* a) {
     }
   }
   cudaStream_t sc = h->s_compute, sd = h->s_copy;
+  PST_TRY(scratch_acquire(h, sc));  // work of an earlier pst_eval_grid on the caller's stream may still read the tables
   const int npol = __builtin_popcount(a->pol_mask);
   const size_t nwl = a->n_wl, nth = a->n_theta, nm = a->n_mat, nsw = a->n_sweep;
   // ---- inputs: one device block, host -> device on the compute stream
@@ -816,6 +896,7 @@ extern "C" int pst_eval_grid_host(pst_handle_t h, const pst_grid_args* a) {
   }
   PST_CUDA(cudaStreamSynchronize(sd));
   PST_CUDA(cudaStreamSynchronize(sc));
+  h->scratch_busy = false;  // everything this handle enqueued on its internal streams has completed
   return PST_OK;
 }
 
@@ -920,6 +1001,7 @@ extern "C" int pst_field_amplitudes(pst_handle_t h, const pst_grid_args* a, doub
   DeviceGuard g(h->device);
   if (!g.ok) return fail(PST_E_CUDA, "pst_field_amplitudes: cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
+  PST_TRY(scratch_acquire(h, st));
   PST_TRY(sync_layers(h, &loc, st));
   PST_TRY(run_prep(h, &loc, a->wl, a->theta, a->cos_theta, a->mat_n, a->mat_k, st));
   GridParams prm;
@@ -941,7 +1023,7 @@ extern "C" int pst_field_amplitudes(pst_handle_t h, const pst_grid_args* a, doub
   else field_amplitudes_kernel<false><<<grid, 128, 0, st>>>(prm, pol_a, pol_b, amp);
   PST_CUDA(cudaGetLastError());
   h->launches += 1;
-  return PST_OK;
+  return scratch_release(h, st);
 }
 
 extern "C" int pst_find_peaks(pst_handle_t h, const double* y, int n_outer, int n_pts, int n_inner, double height,

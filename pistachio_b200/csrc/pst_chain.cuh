@@ -38,6 +38,7 @@ template <int NPOL>
 struct RealLayer {
   double c;
   double al[NPOL], be[NPOL];
+  double sn, si;  // n sin(phi), sin(phi)/n: the polarisation-independent parts of al = g sn, be = sin(phi)/(n g) = si/g
 };
 // General layer: M = 2^sc [[cphi, m01], [m10, cphi]] with complex entries.
 template <int NPOL>
@@ -58,6 +59,8 @@ PST_HD RealLayer<NPOL> finish_real_layer(double sx, double cx, double nr, double
   const double sn = sx * nr, si = sx * inr;
   RealLayer<NPOL> m;
   m.c = cx;
+  m.sn = sn;
+  m.si = si;
 #pragma unroll
   for (int p = 0; p < NPOL; ++p) {
     const bool is_s = pol_is_s<NPOL>(p, pol_first);
@@ -137,7 +140,8 @@ PST_HD void apply_cplx_layer(ChainState<NPOL, NC>& st, const CplxLayer<NPOL>& m)
   }
 }
 
-// A cached layer matrix in either form (the typed paths).  Real form: a[0] = c, a[1 + 2p] = al[p], a[2 + 2p] = be[p].
+// A cached layer matrix in either form (the typed paths).  Real form: a[0] = c, a[1 + 2p] = al[p], a[2 + 2p] = be[p],
+// a[5] = sn, a[6] = si (polarisation-independent parts, used by the period power).
 // Complex form: a[0..1] = cphi, a[2 + 4p .. 5 + 4p] = m10[p], m01[p]; sc = power-of-two exponent.
 template <int NPOL>
 struct TypeRegs {
@@ -147,6 +151,8 @@ struct TypeRegs {
     a[0] = m.c;
 #pragma unroll
     for (int p = 0; p < NPOL; ++p) { a[1 + 2 * p] = m.al[p]; a[2 + 2 * p] = m.be[p]; }
+    a[5] = m.sn;
+    a[6] = m.si;
     sc = 0;
   }
   PST_HD void set_cplx(const CplxLayer<NPOL>& m) {
@@ -157,39 +163,6 @@ struct TypeRegs {
       a[4 + 4 * p] = m.m01[p].re; a[5 + 4 * p] = m.m01[p].im;
     }
     sc = m.sc;
-  }
-  // Largest high word (sign cleared) over the entries: an integer stand-in for max|entry| (monotone in magnitude).
-  PST_HD unsigned max_hi(bool lossy) const {
-    unsigned m = 0;
-    const int n = lossy ? 2 + 4 * NPOL : 1 + 2 * NPOL;
-#pragma unroll
-    for (int k = 0; k < 10; ++k) {
-      if (k < n) {
-        const unsigned h = (unsigned)hi_word(a[k]) & 0x7fffffffu;
-        m = h > m ? h : m;
-      }
-    }
-    return m;
-  }
-  // The same bound from fewer entries.  With both polarisations in the thread the p-wave's a sin(phi) = (1/cos) n sin
-  // dominates the s-wave's cos n sin entry by entry, and the s-wave's sin(phi)/a the p-wave's (|cos(theta)| <= 1);
-  // cos(phi) of a lossless layer never exceeds one and is no part of the growth bound (pst_chain.cuh growth_log2).
-  PST_HD unsigned max_hi_dominant(bool lossy) const {
-    if (NPOL != 2) return max_hi(lossy);
-    unsigned m = 0;
-    auto take = [&](int k) {
-      const unsigned h = (unsigned)hi_word(a[k]) & 0x7fffffffu;
-      m = h > m ? h : m;
-    };
-    if (!lossy) {
-      take(3);  // al of the p-wave
-      take(2);  // be of the s-wave
-    } else {
-      take(0); take(1);  // cos(phi)
-      take(6); take(7);  // m10 of the p-wave
-      take(4); take(5);  // m01 of the s-wave
-    }
-    return m;
   }
 };
 
@@ -226,7 +199,13 @@ PST_HD void pair_loop(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const T
 // k repetitions of a LOSSLESS pair in closed form.  One period is U = B A (A is applied first) with
 //   U = [[u00, -i u01], [-i u10, u11]],  u00 = cB cA - beB alA,  u11 = cB cA - alB beA,
 //                                         u01 = cB beA + beB cA,  u10 = alB cA + cB alA      (all real, det U = 1).
-// Split off the trace:  U = x I + W,  x = (u00 + u11)/2,  W = [[w, -i u01], [-i u10, -w]],  w = (u00 - u11)/2, and
+// With al = g sn and be = si / g (g = cos(theta) for s-waves, 1/cos(theta) for p-waves; sn = n sin(phi), si = sin(phi)/n)
+// the diagonal of U does not depend on the polarisation and the off-diagonal entries only through one factor:
+//   u00 = cB cA - siB snA,  u11 = cB cA - snB siA,  u01 = (cB siA + siB cA) / g,  u10 = g (snB cA + cB snA),
+// so the period is formed ONCE per point from the bare quantities (u01, u10 below are the bracketed sums) and the
+// polarisations part ways only when the finished power is applied to their state vectors -- the same sharing as for the
+// phase and the sincos of a layer.
+// Split off the trace:  U = x I + W,  x = (u00 + u11)/2,  W = [[w, -i u01/g], [-i g u10, -w]],  w = (u00 - u11)/2, and
 //   W^2 = -s2 I,  s2 = u01 u10 - w^2  (= sin^2 of the Bloch phase; negative inside a stop band),
 // so every power of U lives in the two-dimensional commutative ring {t I + s W}:  U^k = t_k I + s_k W with
 //   (t, s)(t', s') = (t t' - s2 s s', t s' + s t').
@@ -247,111 +226,138 @@ PST_HD void pair_loop(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const T
 // A B (w changes sign, u01 and u10 stay); `mirror_image` makes the sums round in the operand order of the period's
 // first occurrence, so that a period and its mirror image agree bit for bit: the second Bragg stack of a symmetric
 // cavity is the first one's matrix with p00 and p11 exchanged, and the powering runs once.
-template <int NPOL>
 struct Period {
-  double x[NPOL], s2[NPOL], w[NPOL], u01[NPOL], u10[NPOL];
+  double x, s2, w, u01, u10;
 };
+// the polarisation-independent part of a lossless layer matrix: cos(phi), n sin(phi), sin(phi)/n
+struct BareLayer {
+  double c, sn, si;
+};
+PST_HD BareLayer finish_bare_layer(double sx, double cx, double nr, double inr) { return {cx, sx * nr, sx * inr}; }
 
-template <int NPOL>
-PST_HD void period_form(const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, bool mirror_image, Period<NPOL>& U) {
-  const double cA = A.a[0], cB = B.a[0];
+PST_HD void period_form(const BareLayer& A, const BareLayer& B, bool mirror_image, Period& U) {
+  const double cA = A.c, cB = B.c;
+  const double snA = A.sn, siA = A.si, snB = B.sn, siB = B.si;
   const double cc = cB * cA;
-#pragma unroll
-  for (int p = 0; p < NPOL; ++p) {
-    const double alA = A.a[1 + 2 * p], beA = A.a[2 + 2 * p], alB = B.a[1 + 2 * p], beB = B.a[2 + 2 * p];
-    double sum, dif;  // beB alA + alB beA = 2 cc - (u00 + u11);  alB beA - beB alA = u00 - u11
-    if (!mirror_image) {
-      const double m = beB * alA;
-      sum = fma(alB, beA, m);
-      dif = fma(alB, beA, -m);
-      U.u01[p] = fma(cB, beA, beB * cA);
-      U.u10[p] = fma(alB, cA, cB * alA);
-    } else {  // the same numbers as the call with A and B exchanged, w negated
-      const double m = beA * alB;
-      sum = fma(alA, beB, m);
-      dif = -fma(alA, beB, -m);
-      U.u01[p] = fma(cA, beB, beA * cB);
-      U.u10[p] = fma(alA, cB, cA * alB);
-    }
-    U.x[p] = fma(-0.5, sum, cc);
-    U.w[p] = 0.5 * dif;
-    U.s2[p] = fma(-U.w[p], U.w[p], U.u01[p] * U.u10[p]);
+  double sum, dif;  // siB snA + snB siA = 2 cc - (u00 + u11);  snB siA - siB snA = u00 - u11
+  if (!mirror_image) {
+    const double m = siB * snA;
+    sum = fma(snB, siA, m);
+    dif = fma(snB, siA, -m);
+    U.u01 = fma(cB, siA, siB * cA);
+    U.u10 = fma(snB, cA, cB * snA);
+  } else {  // the same numbers as the call with A and B exchanged, w negated
+    const double m = siA * snB;
+    sum = fma(snA, siB, m);
+    dif = -fma(snA, siB, -m);
+    U.u01 = fma(cA, siB, siA * cB);
+    U.u10 = fma(snA, cB, cA * snB);
   }
+  U.x = fma(-0.5, sum, cc);
+  U.w = 0.5 * dif;
+  U.s2 = fma(-U.w, U.w, U.u01 * U.u10);
+}
+template <int NPOL>
+PST_HD void period_form(const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, bool mirror_image, Period& U) {
+  period_form(BareLayer{A.a[0], A.a[5], A.a[6]}, BareLayer{B.a[0], B.a[5], B.a[6]}, mirror_image, U);
 }
 
-// (t_k, s_k) 2^ks with U^k = t_k I + s_k W.  `rescale` (block-uniform): pull an exact power of two out after every
-// bit -- needed when |eigenvalue|^k can leave the fp64 range (deep stop bands); without it the exponent stays 0.
-template <int NPOL>
+// (t_k, s_k) 2^ks with U^k = t_k I + s_k W.
 struct PairPower {
-  double t[NPOL], s[NPOL];
-  int ks[NPOL];
+  double t, s;
+  int ks;
 };
 
-template <int NPOL>
-PST_HD void pair_power_coeffs(const Period<NPOL>& U, int k, bool rescale, PairPower<NPOL>& S) {
-#pragma unroll
-  for (int p = 0; p < NPOL; ++p) {
-    S.t[p] = U.x[p];  // U^1
-    S.s[p] = 1.0;
-    S.ks[p] = 0;
+// One bit of the exponent: square, multiply by U when the bit is set (block-uniform), and -- RESCALE -- pull an exact
+// power of two out (needed when |eigenvalue|^k can leave the fp64 range: deep stop bands).
+template <bool RESCALE>
+PST_HD void pair_power_step(const Period& U, bool mul, PairPower& S) {
+  const double t = S.t, s = S.s;
+  double tn = fma(t, t, -((U.s2 * s) * s));  // (t, s)^2
+  double sn = (t + t) * s;
+  if (mul) {                                   // times U = (x, 1)
+    const double tm = fma(U.x, tn, -(U.s2 * sn));
+    sn = fma(U.x, sn, tn);
+    tn = tm;
   }
+  if (RESCALE) {
+    unsigned m = (unsigned)hi_word(tn) & 0x7fffffffu;
+    const unsigned h = (unsigned)hi_word(sn) & 0x7fffffffu;
+    m = h > m ? h : m;
+    int e = (int)(m >> 20) - 1023;
+    e = e > 1000 ? 1000 : (e < -1000 ? 0 : e);
+    const double f = from_words((1023 - e) << 20, 0);
+    tn *= f;
+    sn *= f;
+    S.ks = 2 * S.ks + e;
+  }
+  S.t = tn;
+  S.s = sn;
+}
+
+// Left-to-right binary exponentiation.  k is block-uniform (it comes from the program): the bits below the leading
+// one are dispatched through one switch into straight-line code (k < 8192), so nothing loop-carried moves between
+// registers; deeper stacks take the loop.
+template <bool RESCALE>
+PST_HD void pair_power_coeffs_t(const Period& U, int k, PairPower& S) {
+  S.t = U.x;  // U^1
+  S.s = 1.0;
+  S.ks = 0;
   int hb = 0;
   while ((k >> (hb + 1)) != 0) ++hb;
-  for (int bit = hb - 1; bit >= 0; --bit) {
-    const bool mul = (k >> bit) & 1;
-#pragma unroll
-    for (int p = 0; p < NPOL; ++p) {
-      const double t = S.t[p], s = S.s[p];
-      double tn = fma(t, t, -((U.s2[p] * s) * s));  // (t, s)^2
-      double sn = (t + t) * s;
-      if (mul) {                                      // times U = (x, 1)
-        const double tm = fma(U.x[p], tn, -(U.s2[p] * sn));
-        sn = fma(U.x[p], sn, tn);
-        tn = tm;
-      }
-      S.t[p] = tn;
-      S.s[p] = sn;
-    }
-    if (rescale) {
-#pragma unroll
-      for (int p = 0; p < NPOL; ++p) {
-        unsigned m = (unsigned)hi_word(S.t[p]) & 0x7fffffffu;
-        const unsigned h = (unsigned)hi_word(S.s[p]) & 0x7fffffffu;
-        m = h > m ? h : m;
-        int e = (int)(m >> 20) - 1023;
-        e = e > 1000 ? 1000 : (e < -1000 ? 0 : e);
-        const double f = from_words((1023 - e) << 20, 0);
-        S.t[p] *= f;
-        S.s[p] *= f;
-        S.ks[p] = 2 * S.ks[p] + e;
-      }
-    }
+  if (hb > 12) {
+    for (int bit = hb - 1; bit >= 12; --bit) pair_power_step<RESCALE>(U, (k >> bit) & 1, S);
+    hb = 12;
+  }
+  switch (hb) {
+    case 12: pair_power_step<RESCALE>(U, (k >> 11) & 1, S);  // fall through
+    case 11: pair_power_step<RESCALE>(U, (k >> 10) & 1, S);  // fall through
+    case 10: pair_power_step<RESCALE>(U, (k >> 9) & 1, S);   // fall through
+    case 9: pair_power_step<RESCALE>(U, (k >> 8) & 1, S);    // fall through
+    case 8: pair_power_step<RESCALE>(U, (k >> 7) & 1, S);    // fall through
+    case 7: pair_power_step<RESCALE>(U, (k >> 6) & 1, S);    // fall through
+    case 6: pair_power_step<RESCALE>(U, (k >> 5) & 1, S);    // fall through
+    case 5: pair_power_step<RESCALE>(U, (k >> 4) & 1, S);    // fall through
+    case 4: pair_power_step<RESCALE>(U, (k >> 3) & 1, S);    // fall through
+    case 3: pair_power_step<RESCALE>(U, (k >> 2) & 1, S);    // fall through
+    case 2: pair_power_step<RESCALE>(U, (k >> 1) & 1, S);    // fall through
+    case 1: pair_power_step<RESCALE>(U, k & 1, S);           // fall through
+    default: break;
   }
 }
 
-// Whether pair_power_coeffs must rescale: |t_k|, |s_k| <= k G^(2k) with G <= 2^lg the per-layer growth bound
-// (growth_log2).  Block-uniform by construction (lg is a warp/block maximum).  Without rescaling the entries of U^k
-// stay below 2^kPowerNoRescaleLog2.
+// Whether the powering must rescale: |t_k|, |s_k| <= k G^(2k) with G <= 2^lg the per-layer growth bound.  Block-uniform
+// by construction (lg is grid-wide, k comes from the program).  Without rescaling the entries of U^k stay below
+// 2^kPowerNoRescaleLog2.
 constexpr int kPowerNoRescaleLog2 = 440;
 PST_HD bool pair_power_needs_rescale(int k, int lg) { return 2 * lg * k + 40 > kPowerNoRescaleLog2; }
 
-// U^k = t I + s W as a matrix [[p00, -i p01], [-i p10, p11]] (real entries) times 2^ks
+PST_HD void pair_power_coeffs(const Period& U, int k, int lg, PairPower& S) {
+  if (pair_power_needs_rescale(k, lg)) pair_power_coeffs_t<true>(U, k, S);
+  else pair_power_coeffs_t<false>(U, k, S);
+}
+
+// U^k = t I + s W as a matrix [[p00, -i p01], [-i p10, p11]] (real entries) times 2^ks: the diagonal is shared by the
+// polarisations, the off-diagonal entries take the factors 1/g and g
 template <int NPOL>
 struct PairMatrix {
-  double p00[NPOL], p11[NPOL], p01[NPOL], p10[NPOL];
-  int ks[NPOL];
+  double p00, p11;
+  double p01[NPOL], p10[NPOL];
+  int ks;
 };
 
 template <int NPOL>
-PST_HD void pair_power_matrix(const Period<NPOL>& U, const PairPower<NPOL>& S, PairMatrix<NPOL>& P) {
+PST_HD void pair_power_matrix(const Period& U, const PairPower& S, double ct, double ict, int pol_first, PairMatrix<NPOL>& P) {
+  P.p00 = fma(S.s, U.w, S.t);
+  P.p11 = fma(-S.s, U.w, S.t);
+  const double b01 = S.s * U.u01, b10 = S.s * U.u10;
 #pragma unroll
   for (int p = 0; p < NPOL; ++p) {
-    P.p00[p] = fma(S.s[p], U.w[p], S.t[p]);
-    P.p11[p] = fma(-S.s[p], U.w[p], S.t[p]);
-    P.p01[p] = S.s[p] * U.u01[p];
-    P.p10[p] = S.s[p] * U.u10[p];
-    P.ks[p] = S.ks[p];
+    const bool is_s = pol_is_s<NPOL>(p, pol_first);
+    P.p01[p] = (is_s ? ict : ct) * b01;
+    P.p10[p] = (is_s ? ct : ict) * b10;
   }
+  P.ks = S.ks;
 }
 
 template <int NPOL, int NC>
@@ -362,24 +368,25 @@ PST_HD void apply_pair_matrix(ChainState<NPOL, NC>& st, const PairMatrix<NPOL>& 
     for (int c = 0; c < NC; ++c) {
       double* v = st.v[p][c];
       const double v0r = v[0], v0i = v[1], v1r = v[2], v1i = v[3];
-      v[0] = fma(P.p00[p], v0r, P.p01[p] * v1i);
-      v[1] = fma(P.p00[p], v0i, -(P.p01[p] * v1r));
-      v[2] = fma(P.p11[p], v1r, P.p10[p] * v0i);
-      v[3] = fma(P.p11[p], v1i, -(P.p10[p] * v0r));
+      v[0] = fma(P.p00, v0r, P.p01[p] * v1i);
+      v[1] = fma(P.p00, v0i, -(P.p01[p] * v1r));
+      v[2] = fma(P.p11, v1r, P.p10[p] * v0i);
+      v[3] = fma(P.p11, v1i, -(P.p10[p] * v0r));
     }
-    st.kexp[p] += P.ks[p];
+    st.kexp[p] += P.ks;
   }
 }
 
 // v <- U^k v with U = B A (A applied first); lg = growth bound of the two layers (growth_log2)
 template <int NPOL, int NC>
-PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, int k, int lg) {
-  Period<NPOL> U;
+PST_HD void apply_pair_power(ChainState<NPOL, NC>& st, const TypeRegs<NPOL>& A, const TypeRegs<NPOL>& B, int k, int lg,
+                             double ct, double ict, int pol_first) {
+  Period U;
   period_form<NPOL>(A, B, false, U);
-  PairPower<NPOL> S;
-  pair_power_coeffs<NPOL>(U, k, pair_power_needs_rescale(k, lg), S);
+  PairPower S;
+  pair_power_coeffs(U, k, lg, S);
   PairMatrix<NPOL> P;
-  pair_power_matrix<NPOL>(U, S, P);
+  pair_power_matrix<NPOL>(U, S, ct, ict, pol_first, P);
   apply_pair_matrix<NPOL, NC>(st, P);
 }
 
@@ -417,14 +424,17 @@ PST_HD void renormalise(ChainState<NPOL, NC>& st) {
   }
 }
 
-// lg >= log2 G with max|M v| <= G max|v| over a set of cached layer matrices, from the largest high word m_hi of
-// their entries (e = floor(log2 max|entry|)):
-//   lossless   G = 1 + max(|al|, |be|)                       <= 2 max(1, m)  ->  1 + max(e + 1, 0)
-//   absorbing  G = |c.re| + |c.im| + max(|m.re| + |m.im|)    <= 4 max(1, m)  ->  2 + max(e + 1, 0)
-PST_HD int growth_log2(unsigned m_hi, bool any_lossy) {
-  const int e = (int)(m_hi >> 20) - 1023;
-  return (e + 1 > 0 ? e + 1 : 0) + (any_lossy ? 2 : 1);
-}
+// lg >= log2 G with max|M v| <= G max|v| for every layer matrix of the grid.  E = e_n + e_g + 2 >= 0 with e_n, e_g the
+// exponents (floor(log2)) of the largest |n|, |1/n| entry and of the largest 1/cos(theta) of the grid (prep_kernel):
+// every al = g n sin(phi), be = sin(phi)/(n g) is below 2^E, and the entries of an absorbing layer's mantissa matrix
+// (cosh, sinh scaled into [1/2, 5/2]) below 2^(E + 3).
+//   lossless   G = 1 + max(|al|, |be|)                       <= 2 max(1, m)  ->  1 + E
+//   absorbing  G = |c.re| + |c.im| + max(|m.re| + |m.im|)    <= 4 max(1, m)  ->  2 + E + 3
+// Grid-wide, hence block-uniform; it only decides WHEN exact power-of-two rescalings happen, never a result bit.
+PST_HD int growth_log2(int E, bool any_lossy) { return E + (any_lossy ? 5 : 1); }
+// layout of the device word the typed kernel reads (prep_kernel writes it): bits 0..7 lossy bit per layer type,
+// bits 8..19 E, bit 31 some material absorbs
+PST_HD int growth_E_of_word(unsigned w) { return (int)((w >> 8) & 0xfffu); }
 
 // Exit-medium columns D_f[:, c]:  s: (1, +-n_f cos)   p: (cos, +-n_f)                       (tm.py:209,212)
 template <int NPOL, int NC>

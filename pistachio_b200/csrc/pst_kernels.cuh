@@ -118,21 +118,25 @@ struct TypedPlan {
   int sweep_type;           // type whose thickness is sweep_d[blockIdx.y]; -1: none
   int mat_first, mat_last;  // materials of the incidence and the exit medium
   int type_stride;          // bytes of layer-matrix cache per thread (odd multiple of 16: conflict-free LDS.128)
-  int shape;                // 1: the program is [power(A, B, k1), single C, power({A, B}, k2)] -- a spacer between two
-                            // periodic mirrors (DBR microcavity); the kernel then runs it as straight-line code
   int type_mat[kMaxTypes];
   double type_d[kMaxTypes];
   int4 ops[kMaxOps];        // (type A, type B or -1, repeat count, 0), in application order (exit side first)
-  // shape == 1: everything the straight-line program needs, resolved on the host so that the kernel's first loads do not
-  // wait on chains of dependent constant-bank reads (ops -> type -> material -> row address)
-  int fast_row[3];          // row offsets (in double2 units) of the materials of types A, B (mirror pair) and C (spacer)
-  int fast_row_last, fast_row_first;
-  unsigned fast_lossy_ab;   // bits of types A and B in the device's lossy-type word; fast_lossy_c: bit of type C
-  unsigned fast_lossy_c;
-  int fast_c_swept;         // 1: the spacer is the swept layer (thickness from sweep_d)
-  int fast_mirrored;        // 1: the second mirror applies (B, A) -- the mirror image of the first
-  double fast_d[3];         // thicknesses of A, B, C
-  const unsigned* lossy_types;  // device word, bit t: the material of type t absorbs somewhere on the grid (flag kernel)
+  const unsigned* lossy_types;  // device word (prep_kernel): bits 0..7 the material of type t absorbs somewhere on the
+                                // grid, bits 8..19 grid-wide growth bound E (pst_chain.cuh growth_log2), bit 31 any material
+};
+
+// The cavity kernel's program (by value): periodic mirror / spacer / periodic mirror over one pair of layer types --
+// [power(A, B, k1), single C, power(A, B | B, A, k2)] in application order (exit side first); a DBR microcavity.
+constexpr int kCavityRow = 23;  // staged values per wavelength: rows of A, B, C (6 each), n_exit (2), 1/n_in (2), d_C
+struct CavityPlan {
+  int src[kCavityRow - 1];  // offsets (in doubles) of those values inside the wavelength's block of the optical table
+  double d[3];              // thicknesses of A, B, C
+  int k1, k2;               // pair counts of the first and the second mirror applied
+  int mirrored;             // 1: the second mirror applies (B, A) -- the mirror image of the first
+  int c_swept;              // 1: the spacer is the swept layer (thickness from sweep_d)
+  unsigned lossy_a, lossy_ab, lossy_c;  // bits of type A, of types A | B and of type C in the device's lossy-type word
+  int tiles;                // theta tiles of 128 angles per block (row-mode launch)
+  const unsigned* lossy_types;
 };
 
 // ---------------------------------------------------------------------------------------------- K0
@@ -197,6 +201,8 @@ prep_kernel(const double* __restrict__ wl, const double* __restrict__ mat_n, con
             const double* __restrict__ cos_theta, int n_theta, double2* __restrict__ trig, int n_opt_blocks,
             const LayerEntry* __restrict__ layers, int n_layers, LayerEntry* __restrict__ layers_out, const TypeMats tm,
             unsigned* __restrict__ lossy_types, unsigned* __restrict__ ticket) {
+  // ticket[0]: arrival counter; ticket[1], ticket[2]: largest high word (sign cleared) of the |n|, |1/n| components and
+  // of 1/cos(theta) over the grid -- the grid-wide growth bound of pst_chain.cuh (growth_log2); zero between calls
   if ((int)blockIdx.x < n_opt_blocks) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < (long long)n_wl * n_mat) {
@@ -208,8 +214,16 @@ prep_kernel(const double* __restrict__ wl, const double* __restrict__ mat_n, con
       o[0] = make_double2(r.qr, r.nr);
       o[1] = make_double2(r.inr, r.ni);
       o[2] = make_double2(r.qi, r.ini);
-      // the material absorbs (or amplifies) somewhere on the grid: one atomic per warp and material at most
       const unsigned act = __activemask();
+      {
+        unsigned hw = (unsigned)hi_word(r.nr) & 0x7fffffffu;
+        hw = max(hw, (unsigned)hi_word(r.ni) & 0x7fffffffu);
+        hw = max(hw, (unsigned)hi_word(r.inr) & 0x7fffffffu);
+        hw = max(hw, (unsigned)hi_word(r.ini) & 0x7fffffffu);
+        hw = __reduce_max_sync(act, hw);
+        if ((threadIdx.x & 31) == __ffs(act) - 1 && hw > __ldcg(ticket + 1)) atomicMax(ticket + 1, hw);
+      }
+      // the material absorbs (or amplifies) somewhere on the grid: one atomic per warp and material at most
       const int m0 = __shfl_sync(act, m, __ffs(act) - 1);
       const bool any_here = __any_sync(act, nk != 0.0 && m == m0);
       if (m == m0) {
@@ -222,7 +236,11 @@ prep_kernel(const double* __restrict__ wl, const double* __restrict__ mat_n, con
     const int i = ((int)blockIdx.x - n_opt_blocks) * blockDim.x + threadIdx.x;
     if (i < n_theta) {
       const double c = cos_theta ? cos_theta[i] : cos(theta[i]);
-      trig[i] = make_double2(c, 1.0 / c);
+      const double ic = 1.0 / c;
+      trig[i] = make_double2(c, ic);
+      const unsigned act = __activemask();
+      const unsigned hw = __reduce_max_sync(act, (unsigned)hi_word(ic) & 0x7fffffffu);
+      if ((threadIdx.x & 31) == __ffs(act) - 1 && hw > __ldcg(ticket + 2)) atomicMax(ticket + 2, hw);
     }
   }
   // ---- the last block to arrive finishes the flag-dependent part
@@ -237,7 +255,9 @@ prep_kernel(const double* __restrict__ wl, const double* __restrict__ mat_n, con
     unsigned m = 0;
     for (int t = 0; t < tm.n; ++t) m |= (__ldcg(mat_flags + tm.mat[t]) != 0 ? 1u : 0u) << t;
     for (int i = 0; i < n_mat; ++i) m |= (__ldcg(mat_flags + i) != 0 ? 1u : 0u) << 31;
-    *lossy_types = m;
+    const int e_n = (int)(__ldcg(ticket + 1) >> 20) - 1023, e_g = (int)(__ldcg(ticket + 2) >> 20) - 1023;
+    const int E = min(max(e_n + e_g + 2, 0), 4095);
+    *lossy_types = m | ((unsigned)E << 8);
   }
   for (int j = threadIdx.x; j < n_layers; j += blockDim.x) {
     LayerEntry e = layers[j];
@@ -246,7 +266,7 @@ prep_kernel(const double* __restrict__ wl, const double* __restrict__ mat_n, con
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n_mat; i += blockDim.x) mat_flags[i] = 0;
-  if (threadIdx.x == 0) *ticket = 0u;
+  if (threadIdx.x == 0) { ticket[0] = 0u; ticket[1] = 0u; ticket[2] = 0u; }
 }
 
 // ------------------------------------------------------------------------------------ K1 / K2
@@ -518,103 +538,23 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
   }
   const int il = prm.il0 + il_loc;
   const double2* optp = reinterpret_cast<const double2*>(prm.opt + (size_t)il * prm.n_mat * 6);  // rows of 3 double2
-  // straight-line program (below): its table rows are requested before anything waits on a load
-  const bool shape1 = NCOL == 1 && tp.shape == 1 && !(prm.flags & (128u | 2048u));
-  double2 a0, a1, b0, b1, c0, c1, c2;
-  if (shape1) {
-    const double2* rA = optp + tp.fast_row[0];
-    const double2* rB = optp + tp.fast_row[1];
-    const double2* rC = optp + tp.fast_row[2];
-    a0 = __ldg(rA); a1 = __ldg(rA + 1); b0 = __ldg(rB); b1 = __ldg(rB + 1);
-    c0 = __ldg(rC); c1 = __ldg(rC + 1); c2 = __ldg(rC + 2);
-  }
   const double2 tr = __ldg(prm.trig + it);
-  const unsigned lossy_mask = __ldg(tp.lossy_types);
-  const double d_sweep = prm.sweep_d ? __ldg(prm.sweep_d + sweep_idx) : 0.0;
+  const unsigned lossy_mask = __ldg(tp.lossy_types);  // bits 0..7: lossy layer types, bits 8..19: growth bound, bit 31
   const double ct = tr.x, ict = tr.y;
-  const int row_last = shape1 ? tp.fast_row_last : tp.mat_last * 3;
+  const int row_last = tp.mat_last * 3;
   const double2 ex0 = __ldg(optp + row_last), ex1 = __ldg(optp + row_last + 1);
   const double nfr = ex0.y, nfi = ex1.y;
-  const double2* in_row = optp + (shape1 ? tp.fast_row_first : tp.mat_first * 3);  // incidence medium: 1/n for the epilogue
+  const double2* in_row = optp + tp.mat_first * 3;  // incidence medium: 1/n for the epilogue
   double2 in1, in2;
 
   ChainState<NPOL, NC> st;
   init_exit_columns<NPOL, NC>(st, nfr, nfi, ct, prm.pol_first);
 
-  // ---- straight-line form of the commonest program: periodic mirror / spacer / periodic mirror (tp.shape == 1, both
-  // mirror layers lossless).  Same functions in the same order as the interpreted form below, so the results are
-  // bit-identical (tested, PST_FLAG_NO_SHAPE_FASTPATH); what goes away is the interpretation: no type records in
-  // shared memory, no loops over types and ops, and the three layer matrices are built in one basic block so that
-  // their sincos chains interleave.
-  bool done = false;
-  if constexpr (NCOL == 1) {
-    if (shape1 && !(lossy_mask & tp.fast_lossy_ab)) {
-      const bool lossyC = (lossy_mask & tp.fast_lossy_c) != 0u;
-      const double dC = tp.fast_c_swept ? d_sweep : tp.fast_d[2];
-      const double xA = layer_phase(a0.x, ct, tp.fast_d[0]), xB = layer_phase(b0.x, ct, tp.fast_d[1]);
-      const double xC = layer_phase(c0.x, ct, dC);
-      double sA, cA, sB, cB, sC, cC;
-      if (sincos_in_fast_range(xA) && sincos_in_fast_range(xB) && sincos_in_fast_range(xC)) {
-        sincos_core(xA, sA, cA);
-        sincos_core(xB, sB, cB);
-        sincos_core(xC, sC, cC);
-      } else {
-        sincos_fast(xA, sA, cA);
-        sincos_fast(xB, sB, cB);
-        sincos_fast(xC, sC, cC);
-      }
-      TypeRegs<NPOL> A, B, C;
-      A.set_real(finish_real_layer<NPOL>(sA, cA, a0.y, a1.x, ct, ict, prm.pol_first));
-      B.set_real(finish_real_layer<NPOL>(sB, cB, b0.y, b1.x, ct, ict, prm.pol_first));
-      if (!lossyC) {
-        C.set_real(finish_real_layer<NPOL>(sC, cC, c0.y, c1.x, ct, ict, prm.pol_first));
-      } else {
-        OptRow o;
-        o.qr = c0.x; o.nr = c0.y; o.inr = c1.x; o.ni = c1.y; o.qi = c2.x; o.ini = c2.y;
-        C.set_cplx(finish_cplx_layer<NPOL>(sC, cC, layer_phase(o.qi, ct, dC), o, ct, ict, prm.pol_first));
-      }
-      unsigned mh = A.max_hi_dominant(false);
-      mh = max(mh, B.max_hi_dominant(false));
-      mh = max(mh, C.max_hi_dominant(lossyC));
-      const int lg = growth_log2(__reduce_max_sync(0xffffffffu, mh), lossyC);
-      if (lg <= 12) {
-        // No rescaling between the three ops: one power grows the state by < 2^(kPowerNoRescaleLog2 + 1) (rescaled
-        // coefficients: < 2^4), the spacer by 2^lg -- inside the fp64 range together.  The interpreted form rescales
-        // after every power; rescaling is exact, so the bits are the same.
-        const int k1 = tp.ops[0].z, k2 = tp.ops[2].z;
-        Period<NPOL> U;
-        period_form<NPOL>(A, B, false, U);
-        PairPower<NPOL> S;
-        pair_power_coeffs<NPOL>(U, k1, pair_power_needs_rescale(k1, lg), S);
-        PairMatrix<NPOL> P;
-        pair_power_matrix<NPOL>(U, S, P);
-        apply_pair_matrix<NPOL, NC>(st, P);
-        apply_type<NPOL, NC>(st, C, lossyC);
-        in1 = __ldg(in_row + 1);  // requested here (registers of C are free again), used in the epilogue
-        in2 = __ldg(in_row + 2);
-        if (k2 == k1) {
-          // both mirrors have the same number of pairs: one matrix serves both (exchanged diagonal when the second
-          // mirror is the mirror image: w -> -w), and the layer matrices and coefficients are dead from here on
-          if (tp.fast_mirrored) {
-#pragma unroll
-            for (int pp = 0; pp < NPOL; ++pp) { const double t = P.p00[pp]; P.p00[pp] = P.p11[pp]; P.p11[pp] = t; }
-          }
-        } else {
-          if (tp.fast_mirrored) period_form<NPOL>(B, A, false, U);  // new coefficients: a period of its own (see the op loop)
-          pair_power_coeffs<NPOL>(U, k2, pair_power_needs_rescale(k2, lg), S);
-          pair_power_matrix<NPOL>(U, S, P);
-        }
-        apply_pair_matrix<NPOL, NC>(st, P);
-        renormalise<NPOL, NC>(st);
-        done = true;
-      }
-    }
-  }
-  if (!done) {
+  {
     // ---- build each distinct layer matrix once
     unsigned char* my_types = smem_raw + (size_t)threadIdx.x * tp.type_stride;
     int* my_sc = reinterpret_cast<int*>(my_types + tp.n_types * kTypeRecBytes);
-    unsigned m_hi = 0;
+    const double d_sweep = prm.sweep_d ? __ldg(prm.sweep_d + sweep_idx) : 0.0;
     {
       double2 ra = __ldg(optp + tp.type_mat[0] * 3);
       for (int t = 0; t < tp.n_types; ++t) {
@@ -632,13 +572,12 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
           o.qr = a.x; o.nr = a.y; o.inr = b.x; o.ni = b.y; o.qi = c.x; o.ini = c.y;
           tmp.set_cplx(build_cplx_layer<NPOL>(o, d, ct, ict, prm.pol_first));
         }
-        const unsigned h = tmp.max_hi(lossy);
-        m_hi = h > m_hi ? h : m_hi;
         double2* rec = reinterpret_cast<double2*>(my_types + t * kTypeRecBytes);
         if (!lossy) {
           rec[0] = make_double2(tmp.a[0], tmp.a[1]);
           rec[1] = make_double2(tmp.a[2], tmp.a[3]);
-          rec[2] = make_double2(tmp.a[4], 0.0);
+          rec[2] = make_double2(tmp.a[4], tmp.a[5]);
+          rec[3] = make_double2(tmp.a[6], 0.0);
         } else {
   #pragma unroll
           for (int k = 0; k < 5; ++k) rec[k] = make_double2(tmp.a[2 * k], tmp.a[2 * k + 1]);
@@ -650,7 +589,7 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
       const double2* rec = reinterpret_cast<const double2*>(my_types + t * kTypeRecBytes);
       if (!lossy) {
   #pragma unroll
-        for (int k = 0; k < 3; ++k) { const double2 v = rec[k]; out.a[2 * k] = v.x; out.a[2 * k + 1] = v.y; }
+        for (int k = 0; k < 4; ++k) { const double2 v = rec[k]; out.a[2 * k] = v.x; out.a[2 * k + 1] = v.y; }
         out.sc = 0;
       } else {
   #pragma unroll
@@ -659,15 +598,14 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
       }
     };
 
-    // Rescaling interval from the growth bound: after a rescale max|v| < 2 and n layers multiply it by at most G^n,
-    // so n <= 900 / log2 G layers cannot overflow.  Warp-uniform (maximum over the lanes): it sets loop trip counts.
+    // Rescaling interval from the grid-wide growth bound (prep_kernel): after a rescale max|v| < 2 and n layers multiply
+    // it by at most G^n, so n <= 900 / log2 G layers cannot overflow.  Block-uniform: it sets loop trip counts.
     // Ordinary mirrors need no rescale inside the chain at all.
-    const int lg = growth_log2(__reduce_max_sync(0xffffffffu, m_hi), lossy_mask != 0);
+    const int lg = growth_log2(growth_E_of_word(lossy_mask), (lossy_mask & 0xffu) != 0u);
     const int every = max(2, min(1024, __float2int_rz(899.5f * __frcp_rn((float)lg)))) & ~1;  // <= 900 / lg, no division
 
-    PairPower<NPOL> S;
-  #pragma unroll
-    for (int pp = 0; pp < NPOL; ++pp) { S.t[pp] = 1.0; S.s[pp] = 0.0; S.ks[pp] = 0; }
+    PairPower S;
+    S.t = 1.0; S.s = 0.0; S.ks = 0;
     int s_lo = -1, s_hi = -1, s_k = -1;  // the period S belongs to
     int s_first = -1;                   // the layer type applied first when S was computed (orientation of its sums)
     int since = 0;                      // layers applied since the last rescale
@@ -692,17 +630,17 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
         // could leave the fp64 range
         if (since * lg > 1000 - kPowerNoRescaleLog2 - 20) renormalise<NPOL, NC>(st);
         const int t_lo = min(o.x, o.y), t_hi = max(o.x, o.y);
-        Period<NPOL> U;
+        Period U;
         if (t_lo != s_lo || t_hi != s_hi || o.z != s_k) {  // else: same or mirrored period, same (x, s2), same power
           period_form<NPOL>(A, B, false, U);
-          pair_power_coeffs<NPOL>(U, o.z, pair_power_needs_rescale(o.z, lg), S);
+          pair_power_coeffs(U, o.z, lg, S);
           s_lo = t_lo; s_hi = t_hi; s_k = o.z;
           s_first = o.x;
         } else {
           period_form<NPOL>(A, B, o.x != s_first, U);  // a mirror image rounds like the period it mirrors
         }
         PairMatrix<NPOL> P;
-        pair_power_matrix<NPOL>(U, S, P);
+        pair_power_matrix<NPOL>(U, S, ct, ict, prm.pol_first, P);
         apply_pair_matrix<NPOL, NC>(st, P);
         renormalise<NPOL, NC>(st);
         since = 0;
@@ -739,6 +677,201 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
         mo[0] = make_double4(r.M[0], r.M[1], r.M[2], r.M[3]);
         mo[1] = make_double4(r.M[4], r.M[5], r.M[6], r.M[7]);
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ K1 cavity (straight line)
+// The commonest typed program -- periodic mirror / spacer / periodic mirror over one pair of layer types (a DBR
+// microcavity, BASELINE configs[1]) -- as straight-line code: no type records, no op loop.  It evaluates the same
+// functions in the same order as tmm_typed_kernel's interpreter, so the results are bit-identical
+// (PST_FLAG_NO_SHAPE_FASTPATH routes the same stack through the interpreter; tested).
+//
+// Row-mode launch (ROW): a block owns ONE wavelength and cp.tiles consecutive tiles of 128 angles.  Everything the
+// program needs from the optical table -- the rows of the three layer types, the exit index, the incidence 1/n, the
+// spacer thickness: 23 doubles -- is block-uniform; 23 threads fetch it into shared memory once, and every tile reads
+// it back with broadcast LDS at the point of use (volatile: the compiler must not hoist 46 registers' worth of loads
+// out of the tile loop -- that was what spilled in round 1's tile loop).  The only per-thread global load of a tile is
+// its (cos, 1/cos) pair, requested one tile ahead.  So the L2 round trip that every warp of the round-1 kernel paid
+// before its first instruction (13 global loads per thread, 12 % of a warp's life) is paid once per block.
+//
+// Register diet (80 -> 6 blocks/SM): the mirror layers are only ever needed through their polarisation-independent parts
+// (cos phi, n sin phi, sin phi / n: pst_chain.cuh BareLayer) because the period is formed from those; the two mirror
+// sincos chains interleave, the period is powered and turned into the matrix P (6 doubles) before the spacer is even
+// built, and the spacer's matrix dies before the second application of P.
+//
+// Absorbing mirror layers (cold path): the same kernel applies the pairs one by one -- no closed form exists for them.
+template <int NPOL>
+__device__ __noinline__ void cavity_lossy_mirrors(const double* rv, double dA, double dB, int k1, int k2, bool mirrored,
+                                                  bool lossyA, bool lossyB, bool lossyC, double ct, double ict, int pol_first,
+                                                  unsigned flags, double* res /* [NPOL][3] = R, T, A */) {
+  // self-contained (own state, own epilogue): the hot path's state must never have its address taken
+  ChainState<NPOL, 1> st;
+  init_exit_columns<NPOL, 1>(st, rv[18], rv[19], ct, pol_first);
+  TypeRegs<NPOL> A, B, C;
+  auto build = [&](int base, double d, bool lossy, TypeRegs<NPOL>& out) {
+    OptRow o;
+    o.qr = rv[base]; o.nr = rv[base + 1]; o.inr = rv[base + 2]; o.ni = rv[base + 3]; o.qi = rv[base + 4]; o.ini = rv[base + 5];
+    if (!lossy) out.set_real(build_real_layer<NPOL>(o.qr, o.nr, o.inr, d, ct, ict, pol_first));
+    else out.set_cplx(build_cplx_layer<NPOL>(o, d, ct, ict, pol_first));
+  };
+  build(0, dA, lossyA, A);
+  build(6, dB, lossyB, B);
+  build(12, rv[kCavityRow - 1], lossyC, C);
+  for (int i = 0; i < k1; ++i) {
+    apply_type<NPOL, 1>(st, A, lossyA);
+    apply_type<NPOL, 1>(st, B, lossyB);
+    renormalise<NPOL, 1>(st);
+  }
+  apply_type<NPOL, 1>(st, C, lossyC);
+  renormalise<NPOL, 1>(st);
+  for (int i = 0; i < k2; ++i) {
+    apply_type<NPOL, 1>(st, mirrored ? B : A, mirrored ? lossyB : lossyA);
+    apply_type<NPOL, 1>(st, mirrored ? A : B, mirrored ? lossyA : lossyB);
+    renormalise<NPOL, 1>(st);
+  }
+#pragma unroll
+  for (int pp = 0; pp < NPOL; ++pp) {
+    const PointOut r = finish_point<NPOL, 1>(st, pp, rv[20], rv[21], rv[18], rv[19], ict, pol_first, flags);
+    res[3 * pp] = r.R; res[3 * pp + 1] = r.T; res[3 * pp + 2] = r.A;
+  }
+}
+
+template <int NPOL, int MINB, bool ROW>
+__global__ void __launch_bounds__(128, MINB)
+tmm_cavity_kernel(const GridParams prm, const CavityPlan cp) {
+  __shared__ double s_row[kCavityRow + 1];
+  const unsigned npts = (unsigned)prm.points, nth = (unsigned)prm.n_theta;
+  const unsigned sweep_idx = ROW ? blockIdx.z : blockIdx.y;
+  const unsigned lossy_mask = __ldg(cp.lossy_types);
+  const int n_tiles = ROW ? cp.tiles : 1;
+  const unsigned tile0 = ROW ? blockIdx.x * (unsigned)n_tiles : 0u;
+  const double* optr = nullptr;  // !ROW: this thread's block of the optical table
+  unsigned p = 0;
+  int it = 0;
+  bool valid = true;
+  if constexpr (ROW) {
+    const double* row = prm.opt + (size_t)(prm.il0 + (int)blockIdx.y) * prm.n_mat * 6;
+    if (threadIdx.x < kCavityRow - 1) s_row[threadIdx.x] = __ldg(row + cp.src[threadIdx.x]);
+    if (threadIdx.x == kCavityRow - 1) s_row[kCavityRow - 1] = cp.c_swept ? __ldg(prm.sweep_d + sweep_idx) : cp.d[2];
+    __syncthreads();
+  } else {
+    const unsigned praw = blockIdx.x * 128u + threadIdx.x;
+    valid = praw < npts;
+    p = valid ? praw : npts - 1u;  // tail lanes shadow the last point
+    const int il_loc = (int)(p / nth);
+    it = (int)(p - (unsigned)il_loc * nth);
+    optr = prm.opt + (size_t)(prm.il0 + il_loc) * prm.n_mat * 6;
+  }
+  // value i of the staged record (layout: A 0..5, B 6..11, C 12..17 as OptRow; n_exit 18, 19; 1/n_in 20, 21; d_C 22)
+  auto val = [&](int i) -> double {
+    if constexpr (ROW) return *reinterpret_cast<const volatile double*>(s_row + i);
+    else return i == kCavityRow - 1 ? (cp.c_swept ? __ldg(prm.sweep_d + sweep_idx) : cp.d[2]) : __ldg(optr + cp.src[i]);
+  };
+  auto opt_row_at = [&](int base) {
+    OptRow o;
+    o.qr = val(base); o.nr = val(base + 1); o.inr = val(base + 2); o.ni = val(base + 3); o.qi = val(base + 4); o.ini = val(base + 5);
+    return o;
+  };
+  const bool lossyAB = (lossy_mask & cp.lossy_ab) != 0u;
+  const bool lossyC = (lossy_mask & cp.lossy_c) != 0u;
+  // Rescaling schedule from the grid-wide growth bound (prep_kernel; block-uniform).  One power grows the state by
+  // < 2^(kPowerNoRescaleLog2 + 1) (rescaled coefficients: < 2^4), the spacer by 2^lg: up to lg = 100 the three ops fit the
+  // fp64 range without a rescale in between.  The interpreter rescales after every power; rescaling is exact, so the
+  // bits are the same.
+  const int lg = growth_log2(growth_E_of_word(lossy_mask), lossyC || lossyAB);
+  const bool mid_rescale = lg > 100;
+
+  const size_t plane = (size_t)prm.points;
+  const size_t out_base = (size_t)sweep_idx * (size_t)(NPOL << prm.pol_dup) * plane;
+  double2 tr_next;
+  if constexpr (ROW) tr_next = __ldg(prm.trig + min(tile0 * 128u + threadIdx.x, nth - 1u));
+  else tr_next = __ldg(prm.trig + it);
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    if constexpr (ROW) {
+      const unsigned itr = (tile0 + (unsigned)tile) * 128u + threadIdx.x;
+      if ((tile0 + (unsigned)tile) * 128u >= nth) break;  // block-uniform: ragged last block
+      valid = itr < nth;
+      it = (int)(valid ? itr : nth - 1u);  // tail lanes shadow the last angle
+      p = blockIdx.y * nth + (unsigned)it;
+    }
+    const double ct = tr_next.x, ict = tr_next.y;
+    if constexpr (ROW) {
+      if (tile + 1 < n_tiles) tr_next = __ldg(prm.trig + min((tile0 + (unsigned)tile + 1u) * 128u + threadIdx.x, nth - 1u));
+    }
+    double outR[NPOL], outT[NPOL], outA[NPOL];
+    if (!lossyAB) {
+      ChainState<NPOL, 1> st;
+      init_exit_columns<NPOL, 1>(st, val(18), val(19), ct, prm.pol_first);
+      // ---- first mirror: the two sincos chains interleave in one basic block
+      PairMatrix<NPOL> P;
+      Period U;
+      {
+        const double xA = layer_phase(val(0), ct, cp.d[0]), xB = layer_phase(val(6), ct, cp.d[1]);
+        double sA, cA, sB, cB;
+        if (sincos_in_fast_range(xA) && sincos_in_fast_range(xB)) {
+          sincos_core(xA, sA, cA);
+          sincos_core(xB, sB, cB);
+        } else {
+          sincos_fast(xA, sA, cA);
+          sincos_fast(xB, sB, cB);
+        }
+        const BareLayer A = finish_bare_layer(sA, cA, val(1), val(2)), B = finish_bare_layer(sB, cB, val(7), val(8));
+        period_form(A, B, false, U);
+        PairPower S;
+        pair_power_coeffs(U, cp.k1, lg, S);
+        pair_power_matrix<NPOL>(U, S, ct, ict, prm.pol_first, P);
+        // a second mirror with another pair count has a power of its own (see the interpreter's op loop); its period
+        // rounds in the order its own first layer dictates and is formed now, while A and B are live
+        if (cp.k2 != cp.k1 && cp.mirrored) period_form(B, A, false, U);
+      }
+      apply_pair_matrix<NPOL, 1>(st, P);
+      if (mid_rescale) renormalise<NPOL, 1>(st);
+      // ---- spacer
+      {
+        const double dC = val(22);
+        double sC, cC;
+        sincos_fast(layer_phase(val(12), ct, dC), sC, cC);
+        if (!lossyC) {
+          apply_real_layer<NPOL, 1>(st, finish_real_layer<NPOL>(sC, cC, val(13), val(14), ct, ict, prm.pol_first));
+        } else {
+          const OptRow o = opt_row_at(12);
+          apply_cplx_layer<NPOL, 1>(st, finish_cplx_layer<NPOL>(sC, cC, layer_phase(o.qi, ct, dC), o, ct, ict, prm.pol_first));
+        }
+      }
+      if (mid_rescale) renormalise<NPOL, 1>(st);
+      // ---- second mirror: the same matrix (exchanged diagonal for the mirror image: w -> -w) when the pair counts agree
+      if (cp.k2 == cp.k1) {
+        if (cp.mirrored) { const double t = P.p00; P.p00 = P.p11; P.p11 = t; }
+      } else {
+        PairPower S2;  // powered only now: cheaper than holding a second matrix across the spacer
+        pair_power_coeffs(U, cp.k2, lg, S2);
+        pair_power_matrix<NPOL>(U, S2, ct, ict, prm.pol_first, P);
+      }
+      apply_pair_matrix<NPOL, 1>(st, P);
+      renormalise<NPOL, 1>(st);
+      {
+        const double in0r = val(20), in0i = val(21), nfr = val(18), nfi = val(19);
+#pragma unroll
+        for (int pp = 0; pp < NPOL; ++pp) {
+          const PointOut r = finish_point<NPOL, 1>(st, pp, in0r, in0i, nfr, nfi, ict, prm.pol_first, prm.flags);
+          outR[pp] = r.R; outT[pp] = r.T; outA[pp] = r.A;
+        }
+      }
+    } else {
+      // ---- absorbing mirror layers (cold, out of line: its three full layer matrices must not cost the hot path
+      // registers): layer by layer, the interpreter's matrices in the interpreter's order
+      double rv[kCavityRow], res[3 * NPOL];
+#pragma unroll 1
+      for (int i = 0; i < kCavityRow; ++i) rv[i] = val(i);
+      cavity_lossy_mirrors<NPOL>(rv, cp.d[0], cp.d[1], cp.k1, cp.k2, cp.mirrored != 0, (lossy_mask & cp.lossy_a) != 0u,
+                                 (lossy_mask & (cp.lossy_ab & ~cp.lossy_a)) != 0u, lossyC, ct, ict, prm.pol_first, prm.flags, res);
+#pragma unroll
+      for (int pp = 0; pp < NPOL; ++pp) { outR[pp] = res[3 * pp]; outT[pp] = res[3 * pp + 1]; outA[pp] = res[3 * pp + 2]; }
+    }
+    if (valid) {
+#pragma unroll
+      for (int pp = 0; pp < NPOL; ++pp) store_point<false>(prm, out_base + (size_t)pp * plane + (size_t)p, outR[pp], outT[pp], outA[pp]);
     }
   }
 }

@@ -26,8 +26,11 @@ angle (PST_FLAG_SNELL).
 """
 from __future__ import annotations
 
+import argparse
 import csv
 import os
+import sys
+import time
 
 import numpy as np
 
@@ -449,9 +452,31 @@ class Structure:
             print("Layer {} :".format(i), layer.material, "| d = " + str(int(layer.thickness * 10 ** 3)) + " nm")
 
 
-def write_tmm_results(theta, wavelengths, trans, refl, output_dir):
-    """CSV `Wavelength,Transmittance,Reflectance`, file name '<theta>deg_.csv' (tm.py:687-726)."""
-    path = os.path.join(output_dir, str(theta) + "deg_.csv")
+    def make_sim_dir(self, out_path, sim_name=None):
+        """Path of the output directory of an angle-resolved run (tm.py:648-684).  With sim_name = None the name is
+        built from the structure as the reference intends: the layers' materials joined by '_', then
+        '<theta_i>--<theta_f>deg_<lambda_i>--<lambda_f>lambda/' with the angles rounded to whole degrees.
+        The reference's version cannot run (`sim_name` is never bound, tm.py:669, and the else-branch joins a None,
+        tm.py:682); this is that function with `sim_name` as the keyword argument its docstring describes.
+        Returns the path; creating the directory is the caller's job, as in tm.py:791-793."""
+        if sim_name is None:
+            sim_name = ""
+            for layer in self.layers:
+                sim_name += layer.material + "_"
+            theta_i = np.round(np.rad2deg(self.theta[0]))
+            theta_f = np.round(np.rad2deg(self.theta[-1]))
+            lmbda_i = self.wavelengths[0]
+            lmbda_f = self.wavelengths[-1]
+            sim_name += str(theta_i) + "--" + str(theta_f) + "deg_" + str(lmbda_i) + "--" + str(lmbda_f) + "lambda/"
+        return os.path.join(out_path, sim_name)
+
+
+def write_tmm_results(theta, wavelengths, trans, refl, output_dir, notebook_names=False):
+    """CSV `Wavelength,Transmittance,Reflectance`, file name '<theta>deg_.csv' (tm.py:687-726).
+    notebook_names = True writes 'deg<theta in degrees, two decimals>_.csv' instead, the 'deg##.##_' pattern the
+    reference's analysis notebooks look for (Polariton Peak Analysis.ipynb, cell 3), with theta taken in radians."""
+    name = "deg{:05.2f}_.csv".format(float(np.rad2deg(theta))) if notebook_names else str(theta) + "deg_.csv"
+    path = os.path.join(output_dir, name)
     with open(path, "w", encoding="utf-8", newline="") as fh:
         w = csv.writer(fh, delimiter=",")
         w.writerow(["Wavelength", "Transmittance", "Reflectance"])
@@ -472,3 +497,47 @@ def fresnel(n1, n2, k1x, k2x):
 def transmission_matrix(r_ij, t_ij):
     """Interface matrix (1/t)[[1, r], [r, 1]] (tm.py:746-751)."""
     return _to_numpy(_eng().interface_matrices(r_ij, t_ij)[0])
+
+
+# ---- command line (tm.py:755-805) ---------------------------------------------------------------------------------
+def parse_arguments(argv=None):
+    """`structure output [-p | -s]`, the reference's arguments (tm.py:755-767)."""
+    parser = argparse.ArgumentParser(prog="python -m pistachio_b200")
+    parser.add_argument("structure", help="Path for a yaml file from config_files describing a multilayered structure.")
+    parser.add_argument("output", help="Directory for transfer matrix results.")
+    parser.add_argument("-p", "--pwave", help="Boolean. Incident wave is p-wave.", action="store_true")
+    parser.add_argument("-s", "--swave", help="Boolean. Incident was is s-wave.", action="store_true")
+    parser.add_argument("--notebook-names", action="store_true",
+                        help="name the per-angle files deg##.##_.csv (degrees) as the reference's notebooks expect")
+    return parser.parse_args(argv)
+
+
+def main(args):
+    """Load the YAML structure, evaluate every angle, write one CSV per angle into make_sim_dir(output)
+    (tm.py:770-799; there the run always dies in make_sim_dir after computing).  Like the reference it exits
+    silently when neither -p nor -s is given (tm.py:779-780)."""
+    print("Loading structure parameters from {}".format(args.structure))
+    if args.pwave:
+        wave_type = P_WAVE
+    elif args.swave:
+        wave_type = S_WAVE
+    else:
+        sys.exit()
+    s = Structure()
+    s.load_struct_from_config(args.structure)
+    start_time = time.time()
+    results = s.angle_resolved_spectra(wave_type)
+    elapsed_time = np.round(time.time() - start_time, 4)
+    print("Calculation time: {} seconds".format(elapsed_time))
+    out_path = s.make_sim_dir(args.output)
+    if not os.path.exists(out_path):
+        os.makedirs(out_path)
+    for i, (t_results, r_results) in enumerate(results):
+        write_tmm_results(s.theta[i], s.wavelengths, t_results, r_results, out_path,
+                          notebook_names=getattr(args, "notebook_names", False))
+    print("Wrote results to {}".format(out_path))
+    return out_path
+
+
+if __name__ == "__main__":
+    main(parse_arguments())

@@ -15,7 +15,8 @@ __global__ void __launch_bounds__(256) mix_kernel(int iters, double seed, int is
 #pragma unroll
   for (int i = 0; i < NF; ++i) a[i] = seed + i;
 #pragma unroll
-  for (int i = 0; i < NI; ++i) { b[i] = iseed + i; f[i] = (float)seed + i; }
+  for (int i = 0; i < NI; ++i) { b[i] = iseed + i + (int)threadIdx.x; f[i] = (float)seed + i + threadIdx.x; }  // per-thread values: keeps the chains off the uniform datapath
+  const int tsel = threadIdx.x & 1 ? 0x55555555 : 0x33333333;
   const double m = 0.9999999, c = 1e-9;
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
@@ -25,9 +26,11 @@ __global__ void __launch_bounds__(256) mix_kernel(int iters, double seed, int is
       for (int i = 0; i < (NF > NI ? NF : NI); ++i) {
         if (i < NF) a[i] = fma(a[i], m, c);
         if (i < NI) {
-          if (KIND == 0) b[i] = b[i] * iseed + 12345;          // IMAD
+          if (KIND == 0) b[i] = b[i] * tsel + 12345;            // IMAD
           else if (KIND == 1) f[i] = fmaf(f[i], 0.999f, 1e-3f);  // FFMA
-          else b[i] = (b[i] ^ iseed) & 0x7fffffff | (b[i] >> 3);  // LOP3 / SHF
+          else if (KIND == 2) b[i] = (b[i] ^ tsel) & (b[i] | 0x0f0f0f0f);  // LOP3 (one three-input op)
+          else if (KIND == 3) b[i] = b[i] + tsel + i;           // IADD3
+          else b[i] = (b[i] > tsel) ? (b[i] - tsel) : (b[i] + 77);  // ISETP + SEL / VIADD
         }
       }
     }
@@ -76,8 +79,14 @@ int main() {
   run<8, 4, 1>("ffma", sink, cyc);
   run<8, 8, 1>("ffma", sink, cyc);
   run<8, 16, 1>("ffma", sink, cyc);
+  run<0, 8, 2>("lop3", sink, cyc);
   run<8, 8, 2>("lop3", sink, cyc);
   run<8, 16, 2>("lop3", sink, cyc);
+  run<0, 8, 3>("iadd3", sink, cyc);
+  run<8, 8, 3>("iadd3", sink, cyc);
+  run<8, 16, 3>("iadd3", sink, cyc);
+  run<0, 8, 4>("setp+sel", sink, cyc);
+  run<8, 8, 4>("setp+sel", sink, cyc);
   run<4, 8, 0>("imad", sink, cyc);
   run<4, 8, 1>("ffma", sink, cyc);
   return 0;

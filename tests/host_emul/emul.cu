@@ -17,6 +17,20 @@ static void run(int n_wl, int n_theta, int L, const double* wl, const double* co
   for (int j = 0; j < L; ++j)
     for (int il = 0; il < n_wl; ++il)
       if (n_im[(size_t)j * n_wl + il] != 0.0) lossless[j] = 0;
+  // grid-wide growth bound as prep_kernel forms it: exponents of the largest |n|, |1/n| component and 1/cos(theta)
+  int growth_E = 0;
+  {
+    unsigned hn = 0, hg = 0;
+    auto up = [](unsigned& m, double x) { const unsigned h = (unsigned)hi_word(x) & 0x7fffffffu; m = h > m ? h : m; };
+    for (int j = 0; j < L; ++j)
+      for (int il = 0; il < n_wl; ++il) {
+        const OptRow r = make_opt_row(wl[il], n_re[(size_t)j * n_wl + il], n_im[(size_t)j * n_wl + il]);
+        up(hn, r.nr); up(hn, r.ni); up(hn, r.inr); up(hn, r.ini);
+      }
+    for (int it = 0; it < n_theta; ++it) up(hg, 1.0 / cos_theta[it]);
+    const int E = (int)(hn >> 20) - 1023 + (int)(hg >> 20) - 1023 + 2;
+    growth_E = E < 0 ? 0 : (E > 4095 ? 4095 : E);
+  }
   for (int il = 0; il < n_wl; ++il) {
     std::vector<OptRow> rows(L);
     for (int j = 0; j < L; ++j) rows[j] = make_opt_row(wl[il], n_re[(size_t)j * n_wl + il], n_im[(size_t)j * n_wl + il]);
@@ -70,9 +84,7 @@ static void run(int n_wl, int n_theta, int L, const double* wl, const double* co
             const TypeRegs<NPOL> A = build(ta), B = build(tb);
             if (lossless[ta] && lossless[tb] && k >= 3) {
               renormalise<NPOL, NCOL>(fin);
-              unsigned mh = A.max_hi(false), mb = B.max_hi(false);
-              mh = mb > mh ? mb : mh;
-              apply_pair_power<NPOL, NCOL>(fin, A, B, k, growth_log2(mh, false));
+              apply_pair_power<NPOL, NCOL>(fin, A, B, k, growth_log2(growth_E, false), ct, ict, pol_first);
             } else {
               for (int r = 0; r < k; ++r) {
                 apply_type<NPOL, NCOL>(fin, A, !lossless[ta]);

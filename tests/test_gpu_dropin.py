@@ -238,3 +238,35 @@ def test_print_structure_and_csv_export(tm, tmp_path, capsys):
     tm.write_tmm_results(0.5, [1.0, 2.0], [0.9, 0.8], [0.1, 0.2], str(tmp_path))
     text = (tmp_path / "0.5deg_.csv").read_text().splitlines()
     assert text[0] == "Wavelength,Transmittance,Reflectance" and text[1] == "1.0,0.9,0.1"
+
+
+def test_command_line_writes_one_csv_per_angle(tm, tmp_path, capsys):
+    """`python -m pistachio_b200 structure.yaml out -s` (tm.py:755-805): the YAML is loaded, every angle evaluated and one
+    `Wavelength,Transmittance,Reflectance` file per angle written into make_sim_dir(out); the files read back to the
+    values angle_resolved_spectra returns."""
+    import csv
+
+    import yaml
+    import importlib.resources as pkg_resources
+    from pistachio_b200 import default
+
+    cfg = yaml.safe_load((pkg_resources.files(default) / "Au_thin_layer.yaml").read_text())
+    cfg["wave"]["theta_f"], cfg["wave"]["num_angles"] = 40.0, 3
+    path = tmp_path / "structure.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    out_dir = tm.main(tm.parse_arguments([str(path), str(tmp_path), "-s"]))
+    printed = capsys.readouterr().out
+    assert "Loading structure parameters from" in printed and "Calculation time:" in printed and "Wrote results to" in printed
+    s = tm.Structure()
+    s.load_struct_from_config(str(path))
+    expect = s.angle_resolved_spectra("s-wave")
+    assert os.path.isdir(out_dir) and out_dir == s.make_sim_dir(str(tmp_path))
+    files = sorted(os.listdir(out_dir))
+    assert files == sorted(str(th) + "deg_.csv" for th in s.theta)
+    for th, (T, R) in zip(s.theta, expect):
+        with open(os.path.join(out_dir, str(th) + "deg_.csv")) as fh:
+            rows = list(csv.reader(fh))
+        assert rows[0] == ["Wavelength", "Transmittance", "Reflectance"] and len(rows) == 1 + len(s.wavelengths)
+        got = np.array(rows[1:], dtype=np.float64)
+        assert np.array_equal(got[:, 0], s.wavelengths) and np.array_equal(got[:, 1], T) and np.array_equal(got[:, 2], R)
+    assert not np.array_equal(expect[0][0], expect[2][0])  # the angles really differ (the reference's would not)

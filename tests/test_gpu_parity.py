@@ -344,6 +344,37 @@ def test_period_power_against_mpmath_truth(eng):
         assert err_p < 2e-12 and err_p < 3 * err_s + 2e-14, (pairs, err_p, err_s)
 
 
+def test_handle_scratch_is_ordered_across_streams(eng):
+    """the handle's scratch (optical table, angle table, layer lists, flag words) is shared by all calls.
+    Calls on different streams -- and pst_eval_grid_host, which runs on the library's own streams -- must queue behind
+    the work that still reads it.  Two different stacks are evaluated alternately on two torch streams and through the
+    host-buffer call with no synchronisation in between; every result must equal the serial one bit for bit."""
+    from pistachio_b200 import workloads
+
+    wa = workloads.c2_dbr_cavity(n_wl=1024, n_theta=512, pairs=20)   # ~ 30 us of kernel per call: overlaps are likely
+    wb = workloads.c2_dbr_cavity(n_wl=1024, n_theta=512, pairs=7)    # other layer list, other types
+    wb.wl = wb.wl * 1.1
+    pa, pb = eng.prepare_workload(wa), eng.prepare_workload(wb)
+    ref_a, ref_b = eng.eval_prepared(pa).numpy(), eng.eval_prepared(pb).numpy()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for i in range(6):
+        st, prep = ((s1, pa) if i % 2 == 0 else (s2, pb))
+        with torch.cuda.stream(st):
+            outs.append((i % 2, eng.eval_prepared(prep)))
+    host = eng.eval_grid_host(wb.wl, wb.theta, pb["mat_n"].cpu(), pb["mat_k"].cpu(), pb["layer_mat"], pb["layer_d"])
+    with torch.cuda.stream(s1):
+        last = eng.eval_prepared(pa)
+    torch.cuda.synchronize()
+    for which, res in outs:
+        ref = ref_b if which else ref_a
+        got = res.numpy()
+        assert np.array_equal(got["R"], ref["R"]) and np.array_equal(got["T"], ref["T"]), which
+    assert np.array_equal(host["R"], ref_b["R"]) and np.array_equal(host["T"], ref_b["T"])
+    assert np.array_equal(last.numpy()["R"], ref_a["R"])
+
+
 def test_cavity_shape_fast_path_is_bit_identical(eng):
     """Mirror / spacer / mirror programs run as straight-line code in the typed kernel; PST_FLAG_NO_SHAPE_FASTPATH sends
     them through the general op interpreter.  Same functions in the same order: the results must be equal bit for bit

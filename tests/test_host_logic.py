@@ -146,6 +146,28 @@ def test_csv_loading_and_yaml_parsing_without_gpu(tmp_path, monkeypatch):
     assert cfg["num_points"] == 10000 and len(cfg["layers"]) == 5 and float(cfg["layers"]["layer1"]["thickness"]) == 0.01
 
 
+def test_cli_arguments_and_sim_dir_naming(tmp_path):
+    """The command line of tm.py:755-805 and a make_sim_dir that runs (the reference's raises UnboundLocalError at
+    tm.py:669): name = materials joined by '_' + '<theta_i>--<theta_f>deg_<lambda_i>--<lambda_f>lambda/'."""
+    from pistachio_b200 import transfer_matrix as tm
+
+    a = tm.parse_arguments(["struct.yaml", "out", "-p"])
+    assert a.structure == "struct.yaml" and a.output == "out" and a.pwave and not a.swave
+    a = tm.parse_arguments(["struct.yaml", "out", "--swave"])
+    assert a.swave and not a.pwave
+    with pytest.raises(SystemExit):  # neither -p nor -s: the reference exits silently (tm.py:779-780)
+        tm.main(tm.parse_arguments(["struct.yaml", "out"]))
+    s = tm.Structure()
+    for name in ("CaF2", "Au", "Air"):
+        s.add_layer(tm.Layer(material=name))
+    s.theta = np.deg2rad(np.linspace(0.0, 30.0, 4))
+    s.wavelengths = np.linspace(2.0, 6.0, 5)
+    assert s.make_sim_dir(str(tmp_path)) == os.path.join(str(tmp_path), "CaF2_Au_Air_0.0--30.0deg_2.0--6.0lambda/")
+    assert s.make_sim_dir(str(tmp_path), sim_name="run7") == os.path.join(str(tmp_path), "run7")
+    tm.write_tmm_results(np.deg2rad(12.5), [1.0], [0.5], [0.25], str(tmp_path), notebook_names=True)
+    assert (tmp_path / "deg12.50_.csv").read_text().splitlines()[1] == "1.0,0.5,0.25"
+
+
 def test_workload_shapes():
     from pistachio_b200 import workloads as wk
 
