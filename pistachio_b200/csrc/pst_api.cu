@@ -413,19 +413,20 @@ bool cavity_shape(pst_handle_t h, const pst_grid_args* a, CavityPlan* cp) {
     if (h->type_layer[t] == a->sweep_layer) sweep_type = t;
   if (sweep_type == o0.x || sweep_type == o0.y) return false;  // a swept mirror layer is not a periodic mirror
   std::memset(cp, 0, sizeof(*cp));
-  const int t3[3] = {o0.x, o0.y, o1.x};
-  for (int i = 0; i < 3; ++i) {
-    const int j = h->type_layer[t3[i]];
-    for (int f = 0; f < 6; ++f) cp->src[6 * i + f] = a->layer_mat[j] * 6 + f;  // OptRow order: qr nr inr ni qi ini
-    cp->d[i] = a->layer_d[j];
-  }
-  const int m_last = a->layer_mat[a->n_layers - 1], m_first = a->layer_mat[0];
-  cp->src[18] = m_last * 6 + 1;   // n_exit
-  cp->src[19] = m_last * 6 + 3;
-  cp->src[20] = m_first * 6 + 2;  // 1 / n_incidence
-  cp->src[21] = m_first * 6 + 5;
+  // staged record layout: see CavityPlan (pst_kernels.cuh); optical row of a material: qr nr inr ni qi ini
+  const int jA = h->type_layer[o0.x], jB = h->type_layer[o0.y], jC = h->type_layer[o1.x];
+  const int mA = a->layer_mat[jA] * 6, mB = a->layer_mat[jB] * 6, mC = a->layer_mat[jC] * 6;
+  const int m_last = a->layer_mat[a->n_layers - 1] * 6, m_first = a->layer_mat[0] * 6;
+  const int src[kCavityRow] = {mA + 0, mB + 0, mA + 1, mA + 2, mB + 1, mB + 2, mC + 0, -1,     mC + 1,     mC + 2,      mC + 3, mC + 4,
+                               mC + 5, -1,     m_last + 1, m_last + 3,  m_first + 2, m_first + 5, mA + 3, mA + 4, mA + 5, mB + 3, mB + 4, mB + 5};
+  for (int i = 0; i < kCavityRow; ++i) cp->src[i] = src[i];
+  cp->d[0] = a->layer_d[jA];
+  cp->d[1] = a->layer_d[jB];
+  cp->d[2] = a->layer_d[jC];
   cp->k1 = o0.z;
   cp->k2 = o2.z;
+  cp->hb1 = log2_floor(cp->k1);
+  cp->hb2 = log2_floor(cp->k2);
   cp->mirrored = (o2.x == o0.x) ? 0 : 1;
   cp->c_swept = (o1.x == sweep_type) ? 1 : 0;
   cp->lossy_a = 1u << o0.x;

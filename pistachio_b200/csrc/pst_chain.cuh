@@ -13,6 +13,10 @@
 
 namespace pst {
 
+// Exponent pulled out by a rescale: [-1022, 1000] keeps 2^-e a normal number (a zero or denormal state is scaled by
+// 2^1022, harmlessly; inf/nan stay what they are)
+PST_HD int clamp_exp(int e) { return e > 1000 ? 1000 : (e < -1022 ? -1022 : e); }
+
 // State per polarisation and column: v = (v0.re, v0.im, v1.re, v1.im); true value = v * 2^kexp.
 template <int NPOL, int NC>
 struct ChainState {
@@ -285,7 +289,7 @@ PST_HD void pair_power_step(const Period& U, bool mul, PairPower& S) {
     const unsigned h = (unsigned)hi_word(sn) & 0x7fffffffu;
     m = h > m ? h : m;
     int e = (int)(m >> 20) - 1023;
-    e = e > 1000 ? 1000 : (e < -1000 ? 0 : e);
+    e = clamp_exp(e);
     const double f = from_words((1023 - e) << 20, 0);
     tn *= f;
     sn *= f;
@@ -298,13 +302,17 @@ PST_HD void pair_power_step(const Period& U, bool mul, PairPower& S) {
 // Left-to-right binary exponentiation.  k is block-uniform (it comes from the program): the bits below the leading
 // one are dispatched through one switch into straight-line code (k < 8192), so nothing loop-carried moves between
 // registers; deeper stacks take the loop.
+PST_HD int log2_floor(int k) {
+  int hb = 0;
+  while ((k >> (hb + 1)) != 0) ++hb;
+  return hb;
+}
+// hb = log2_floor(k): callers that know it (the host resolves it for the cavity kernel) pass it in
 template <bool RESCALE>
-PST_HD void pair_power_coeffs_t(const Period& U, int k, PairPower& S) {
+PST_HD void pair_power_coeffs_t(const Period& U, int k, int hb, PairPower& S) {
   S.t = U.x;  // U^1
   S.s = 1.0;
   S.ks = 0;
-  int hb = 0;
-  while ((k >> (hb + 1)) != 0) ++hb;
   if (hb > 12) {
     for (int bit = hb - 1; bit >= 12; --bit) pair_power_step<RESCALE>(U, (k >> bit) & 1, S);
     hb = 12;
@@ -333,8 +341,8 @@ constexpr int kPowerNoRescaleLog2 = 440;
 PST_HD bool pair_power_needs_rescale(int k, int lg) { return 2 * lg * k + 40 > kPowerNoRescaleLog2; }
 
 PST_HD void pair_power_coeffs(const Period& U, int k, int lg, PairPower& S) {
-  if (pair_power_needs_rescale(k, lg)) pair_power_coeffs_t<true>(U, k, S);
-  else pair_power_coeffs_t<false>(U, k, S);
+  if (pair_power_needs_rescale(k, lg)) pair_power_coeffs_t<true>(U, k, log2_floor(k), S);
+  else pair_power_coeffs_t<false>(U, k, log2_floor(k), S);
 }
 
 // U^k = t I + s W as a matrix [[p00, -i p01], [-i p10, p11]] (real entries) times 2^ks: the diagonal is shared by the
@@ -414,7 +422,7 @@ PST_HD void renormalise(ChainState<NPOL, NC>& st) {
         m = h > m ? h : m;
       }
     int e = (int)(m >> 20) - 1023;  // floor(log2 max|v|); -1023 for zero/denormal, 1024 for inf/nan
-    e = e > 1000 ? 1000 : (e < -1000 ? 0 : e);
+    e = clamp_exp(e);
     const double s = from_words((1023 - e) << 20, 0);
 #pragma unroll
     for (int c = 0; c < NC; ++c)
@@ -521,7 +529,7 @@ PST_HD PointOut finish_point_det(const ChainState<NPOL, NCOL>& fin, int p, doubl
   PointOut out;
   const double den = fma(m[0][0].re, m[0][0].re, m[0][0].im * m[0][0].im);  // |M00|^2 (scaled by 2^-2kexp)
   const double num = fma(m[0][1].re, m[0][1].re, m[0][1].im * m[0][1].im);  // |M10|^2
-  const double iden = 1.0 / den;
+  const double iden = recip_nr(den);
   out.R = num * iden;
   out.T = scale_sq(det_re * iden, (NCOL == 2 ? 0 : 1) - fin.kexp[p]);
   if constexpr (NCOL == 2) {

@@ -18,6 +18,8 @@
 //   M   = D_0^-1 (M_1 ... M_{N-2}) D_{N-1},   t = 1/M00, r = M10/M00, R = |r|^2, T = Re(det M |t|^2).
 // Only the columns of M that are asked for are propagated: v <- M_j v from the exit side.
 #pragma once
+#include <type_traits>
+
 #include "pst_bulk.cuh"
 #include "pst_chain.cuh"
 
@@ -127,11 +129,17 @@ struct TypedPlan {
 
 // The cavity kernel's program (by value): periodic mirror / spacer / periodic mirror over one pair of layer types --
 // [power(A, B, k1), single C, power(A, B | B, A, k2)] in application order (exit side first); a DBR microcavity.
-constexpr int kCavityRow = 23;  // staged values per wavelength: rows of A, B, C (6 each), n_exit (2), 1/n_in (2), d_C
+// Staged record per wavelength (doubles; pairs that are used together sit 16-byte aligned -> one 128-bit LDS):
+//    0 q_A      1 q_B     |  2 n_A      3 1/n_A   |  4 n_B      5 1/n_B   |  6 q_C.re   7 d_C
+//    8 n_C.re   9 1/n_C.re| 10 n_C.im  11 q_C.im  | 12 1/n_C.im 13 -      | 14 n_exit.re 15 n_exit.im
+//   16 1/n_in.re 17 1/n_in.im | absorbing mirror layers only: 18..20 n_A.im q_A.im 1/n_A.im, 21..23 the same of B
+constexpr int kCavityRow = 24;
 struct CavityPlan {
-  int src[kCavityRow - 1];  // offsets (in doubles) of those values inside the wavelength's block of the optical table
+  int src[kCavityRow];      // offsets (in doubles) of those values inside the wavelength's block of the optical table;
+                            // -1: not from the table (d_C, padding)
   double d[3];              // thicknesses of A, B, C
   int k1, k2;               // pair counts of the first and the second mirror applied
+  int hb1, hb2;             // floor(log2 k1), floor(log2 k2)
   int mirrored;             // 1: the second mirror applies (B, A) -- the mirror image of the first
   int c_swept;              // 1: the spacer is the swept layer (thickness from sweep_d)
   unsigned lossy_a, lossy_ab, lossy_c;  // bits of type A, of types A | B and of type C in the device's lossy-type word
@@ -382,8 +390,7 @@ tmm_chain_kernel(const GridParams prm) {
           mh = max(mh, (unsigned)hi_word(w[pp]) & 0x7fffffffu);
           mh = max(mh, (unsigned)hi_word(u[pp]) & 0x7fffffffu);
           mh = max(mh, (unsigned)hi_word(b[pp]) & 0x7fffffffu);
-          int e = (int)(mh >> 20) - 1023;
-          e = e > 1000 ? 1000 : (e < -1000 ? 0 : e);
+          int e = clamp_exp((int)(mh >> 20) - 1023);
           const double sc = from_words((1023 - e) << 20, 0);
           a[pp] *= sc; w[pp] *= sc; u[pp] *= sc; b[pp] *= sc;
           ke[pp] += e;
@@ -689,35 +696,35 @@ tmm_typed_kernel(const GridParams prm, const TypedPlan tp) {
 //
 // Row-mode launch (ROW): a block owns ONE wavelength and cp.tiles consecutive tiles of 128 angles.  Everything the
 // program needs from the optical table -- the rows of the three layer types, the exit index, the incidence 1/n, the
-// spacer thickness: 23 doubles -- is block-uniform; 23 threads fetch it into shared memory once, and every tile reads
-// it back with broadcast LDS at the point of use (volatile: the compiler must not hoist 46 registers' worth of loads
-// out of the tile loop -- that was what spilled in round 1's tile loop).  The only per-thread global load of a tile is
-// its (cos, 1/cos) pair, requested one tile ahead.  So the L2 round trip that every warp of the round-1 kernel paid
-// before its first instruction (13 global loads per thread, 12 % of a warp's life) is paid once per block.
+// spacer thickness: 24 doubles -- is block-uniform; 24 threads fetch it into shared memory once, and every tile reads
+// it back with broadcast 128-bit LDS at the point of use (asm volatile: the compiler must not hoist 40 registers' worth
+// of loads out of the tile loop -- that was what spilled in round 1's tile loop).  The only per-thread global load of
+// a tile is its (cos, 1/cos) pair, requested one tile ahead.  So the L2 round trip that every warp of the round-1
+// kernel paid before its first instruction (13 global loads per thread, 12 % of a warp's life) is paid once per block.
 //
 // Register diet (80 -> 6 blocks/SM): the mirror layers are only ever needed through their polarisation-independent parts
 // (cos phi, n sin phi, sin phi / n: pst_chain.cuh BareLayer) because the period is formed from those; the two mirror
 // sincos chains interleave, the period is powered and turned into the matrix P (6 doubles) before the spacer is even
-// built, and the spacer's matrix dies before the second application of P.
+// built, and the spacer's matrix dies before the second application of P.  What is block-uniform and decided by
+// device data (absorbing spacer? rescaled powering?) selects one of four compiled tile loops up front, so the loop
+// bodies test nothing.
 //
-// Absorbing mirror layers (cold path): the same kernel applies the pairs one by one -- no closed form exists for them.
+// Absorbing mirror layers (cold, out of line): the same kernel applies the pairs one by one -- no closed form exists.
 template <int NPOL>
 __device__ __noinline__ void cavity_lossy_mirrors(const double* rv, double dA, double dB, int k1, int k2, bool mirrored,
                                                   bool lossyA, bool lossyB, bool lossyC, double ct, double ict, int pol_first,
                                                   unsigned flags, double* res /* [NPOL][3] = R, T, A */) {
   // self-contained (own state, own epilogue): the hot path's state must never have its address taken
   ChainState<NPOL, 1> st;
-  init_exit_columns<NPOL, 1>(st, rv[18], rv[19], ct, pol_first);
+  init_exit_columns<NPOL, 1>(st, rv[14], rv[15], ct, pol_first);
   TypeRegs<NPOL> A, B, C;
-  auto build = [&](int base, double d, bool lossy, TypeRegs<NPOL>& out) {
-    OptRow o;
-    o.qr = rv[base]; o.nr = rv[base + 1]; o.inr = rv[base + 2]; o.ni = rv[base + 3]; o.qi = rv[base + 4]; o.ini = rv[base + 5];
+  auto build = [&](const OptRow& o, double d, bool lossy, TypeRegs<NPOL>& out) {
     if (!lossy) out.set_real(build_real_layer<NPOL>(o.qr, o.nr, o.inr, d, ct, ict, pol_first));
     else out.set_cplx(build_cplx_layer<NPOL>(o, d, ct, ict, pol_first));
   };
-  build(0, dA, lossyA, A);
-  build(6, dB, lossyB, B);
-  build(12, rv[kCavityRow - 1], lossyC, C);
+  build(OptRow{rv[0], rv[2], rv[3], rv[18], rv[19], rv[20]}, dA, lossyA, A);
+  build(OptRow{rv[1], rv[4], rv[5], rv[21], rv[22], rv[23]}, dB, lossyB, B);
+  build(OptRow{rv[6], rv[8], rv[9], rv[10], rv[11], rv[12]}, rv[7], lossyC, C);
   for (int i = 0; i < k1; ++i) {
     apply_type<NPOL, 1>(st, A, lossyA);
     apply_type<NPOL, 1>(st, B, lossyB);
@@ -732,30 +739,24 @@ __device__ __noinline__ void cavity_lossy_mirrors(const double* rv, double dA, d
   }
 #pragma unroll
   for (int pp = 0; pp < NPOL; ++pp) {
-    const PointOut r = finish_point<NPOL, 1>(st, pp, rv[20], rv[21], rv[18], rv[19], ict, pol_first, flags);
+    const PointOut r = finish_point<NPOL, 1>(st, pp, rv[16], rv[17], rv[14], rv[15], ict, pol_first, flags);
     res[3 * pp] = r.R; res[3 * pp + 1] = r.T; res[3 * pp + 2] = r.A;
   }
 }
 
-template <int NPOL, int MINB, bool ROW>
-__global__ void __launch_bounds__(128, MINB)
-tmm_cavity_kernel(const GridParams prm, const CavityPlan cp) {
-  __shared__ double s_row[kCavityRow + 1];
+// MODE: 0 lossless spacer, 1 absorbing spacer, 2 absorbing mirror layers (cold);  RESC: rescaled powering
+template <int NPOL, bool ROW, int MODE, bool RESC>
+__device__ __forceinline__ void cavity_tiles(const GridParams& prm, const CavityPlan& cp, unsigned s_base, unsigned lossy_mask,
+                                             bool mid_rescale) {
   const unsigned npts = (unsigned)prm.points, nth = (unsigned)prm.n_theta;
   const unsigned sweep_idx = ROW ? blockIdx.z : blockIdx.y;
-  const unsigned lossy_mask = __ldg(cp.lossy_types);
   const int n_tiles = ROW ? cp.tiles : 1;
   const unsigned tile0 = ROW ? blockIdx.x * (unsigned)n_tiles : 0u;
   const double* optr = nullptr;  // !ROW: this thread's block of the optical table
   unsigned p = 0;
   int it = 0;
   bool valid = true;
-  if constexpr (ROW) {
-    const double* row = prm.opt + (size_t)(prm.il0 + (int)blockIdx.y) * prm.n_mat * 6;
-    if (threadIdx.x < kCavityRow - 1) s_row[threadIdx.x] = __ldg(row + cp.src[threadIdx.x]);
-    if (threadIdx.x == kCavityRow - 1) s_row[kCavityRow - 1] = cp.c_swept ? __ldg(prm.sweep_d + sweep_idx) : cp.d[2];
-    __syncthreads();
-  } else {
+  if constexpr (!ROW) {
     const unsigned praw = blockIdx.x * 128u + threadIdx.x;
     valid = praw < npts;
     p = valid ? praw : npts - 1u;  // tail lanes shadow the last point
@@ -763,34 +764,33 @@ tmm_cavity_kernel(const GridParams prm, const CavityPlan cp) {
     it = (int)(p - (unsigned)il_loc * nth);
     optr = prm.opt + (size_t)(prm.il0 + il_loc) * prm.n_mat * 6;
   }
-  // value i of the staged record (layout: A 0..5, B 6..11, C 12..17 as OptRow; n_exit 18, 19; 1/n_in 20, 21; d_C 22)
-  auto val = [&](int i) -> double {
-    if constexpr (ROW) return *reinterpret_cast<const volatile double*>(s_row + i);
-    else return i == kCavityRow - 1 ? (cp.c_swept ? __ldg(prm.sweep_d + sweep_idx) : cp.d[2]) : __ldg(optr + cp.src[i]);
+  // values i, i + 1 of the staged record (i even)
+  auto val2 = [&](auto I) -> double2 {
+    constexpr int i = decltype(I)::value;
+    if constexpr (ROW) {
+      double2 v;
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(s_base), "n"(i * 8));
+      return v;
+    } else {
+      double2 v;
+      v.x = (i == 6 || cp.src[i] >= 0) ? __ldg(optr + cp.src[i]) : 0.0;
+      if (i + 1 == 7) v.y = cp.c_swept ? __ldg(prm.sweep_d + sweep_idx) : cp.d[2];
+      else v.y = cp.src[i + 1] >= 0 ? __ldg(optr + cp.src[i + 1]) : 0.0;
+      return v;
+    }
   };
-  auto opt_row_at = [&](int base) {
-    OptRow o;
-    o.qr = val(base); o.nr = val(base + 1); o.inr = val(base + 2); o.ni = val(base + 3); o.qi = val(base + 4); o.ini = val(base + 5);
-    return o;
-  };
-  const bool lossyAB = (lossy_mask & cp.lossy_ab) != 0u;
-  const bool lossyC = (lossy_mask & cp.lossy_c) != 0u;
-  // Rescaling schedule from the grid-wide growth bound (prep_kernel; block-uniform).  One power grows the state by
-  // < 2^(kPowerNoRescaleLog2 + 1) (rescaled coefficients: < 2^4), the spacer by 2^lg: up to lg = 100 the three ops fit the
-  // fp64 range without a rescale in between.  The interpreter rescales after every power; rescaling is exact, so the
-  // bits are the same.
-  const int lg = growth_log2(growth_E_of_word(lossy_mask), lossyC || lossyAB);
-  const bool mid_rescale = lg > 100;
-
+#define PST_V2(i) val2(std::integral_constant<int, i>{})
   const size_t plane = (size_t)prm.points;
   const size_t out_base = (size_t)sweep_idx * (size_t)(NPOL << prm.pol_dup) * plane;
+
   double2 tr_next;
   if constexpr (ROW) tr_next = __ldg(prm.trig + min(tile0 * 128u + threadIdx.x, nth - 1u));
   else tr_next = __ldg(prm.trig + it);
   for (int tile = 0; tile < n_tiles; ++tile) {
     if constexpr (ROW) {
-      const unsigned itr = (tile0 + (unsigned)tile) * 128u + threadIdx.x;
-      if ((tile0 + (unsigned)tile) * 128u >= nth) break;  // block-uniform: ragged last block
+      const unsigned t128 = (tile0 + (unsigned)tile) * 128u;
+      if (t128 >= nth) break;  // block-uniform: ragged last block
+      const unsigned itr = t128 + threadIdx.x;
       valid = itr < nth;
       it = (int)(valid ? itr : nth - 1u);  // tail lanes shadow the last angle
       p = blockIdx.y * nth + (unsigned)it;
@@ -800,14 +800,16 @@ tmm_cavity_kernel(const GridParams prm, const CavityPlan cp) {
       if (tile + 1 < n_tiles) tr_next = __ldg(prm.trig + min((tile0 + (unsigned)tile + 1u) * 128u + threadIdx.x, nth - 1u));
     }
     double outR[NPOL], outT[NPOL], outA[NPOL];
-    if (!lossyAB) {
+    if constexpr (MODE != 2) {
+      const double2 nf = PST_V2(14);
       ChainState<NPOL, 1> st;
-      init_exit_columns<NPOL, 1>(st, val(18), val(19), ct, prm.pol_first);
+      init_exit_columns<NPOL, 1>(st, nf.x, nf.y, ct, prm.pol_first);
       // ---- first mirror: the two sincos chains interleave in one basic block
       PairMatrix<NPOL> P;
       Period U;
       {
-        const double xA = layer_phase(val(0), ct, cp.d[0]), xB = layer_phase(val(6), ct, cp.d[1]);
+        const double2 q = PST_V2(0);
+        const double xA = layer_phase(q.x, ct, cp.d[0]), xB = layer_phase(q.y, ct, cp.d[1]);
         double sA, cA, sB, cB;
         if (sincos_in_fast_range(xA) && sincos_in_fast_range(xB)) {
           sincos_core(xA, sA, cA);
@@ -816,10 +818,11 @@ tmm_cavity_kernel(const GridParams prm, const CavityPlan cp) {
           sincos_fast(xA, sA, cA);
           sincos_fast(xB, sB, cB);
         }
-        const BareLayer A = finish_bare_layer(sA, cA, val(1), val(2)), B = finish_bare_layer(sB, cB, val(7), val(8));
+        const double2 na = PST_V2(2), nb = PST_V2(4);
+        const BareLayer A = finish_bare_layer(sA, cA, na.x, na.y), B = finish_bare_layer(sB, cB, nb.x, nb.y);
         period_form(A, B, false, U);
         PairPower S;
-        pair_power_coeffs(U, cp.k1, lg, S);
+        pair_power_coeffs_t<RESC>(U, cp.k1, cp.hb1, S);
         pair_power_matrix<NPOL>(U, S, ct, ict, prm.pol_first, P);
         // a second mirror with another pair count has a power of its own (see the interpreter's op loop); its period
         // rounds in the order its own first layer dictates and is formed now, while A and B are live
@@ -829,14 +832,15 @@ tmm_cavity_kernel(const GridParams prm, const CavityPlan cp) {
       if (mid_rescale) renormalise<NPOL, 1>(st);
       // ---- spacer
       {
-        const double dC = val(22);
+        const double2 qd = PST_V2(6), nc = PST_V2(8);
         double sC, cC;
-        sincos_fast(layer_phase(val(12), ct, dC), sC, cC);
-        if (!lossyC) {
-          apply_real_layer<NPOL, 1>(st, finish_real_layer<NPOL>(sC, cC, val(13), val(14), ct, ict, prm.pol_first));
+        sincos_fast(layer_phase(qd.x, ct, qd.y), sC, cC);
+        if constexpr (MODE == 0) {
+          apply_real_layer<NPOL, 1>(st, finish_real_layer<NPOL>(sC, cC, nc.x, nc.y, ct, ict, prm.pol_first));
         } else {
-          const OptRow o = opt_row_at(12);
-          apply_cplx_layer<NPOL, 1>(st, finish_cplx_layer<NPOL>(sC, cC, layer_phase(o.qi, ct, dC), o, ct, ict, prm.pol_first));
+          const double2 c2 = PST_V2(10), c3 = PST_V2(12);
+          const OptRow o = {qd.x, nc.x, nc.y, c2.x, c2.y, c3.x};
+          apply_cplx_layer<NPOL, 1>(st, finish_cplx_layer<NPOL>(sC, cC, layer_phase(o.qi, ct, qd.y), o, ct, ict, prm.pol_first));
         }
       }
       if (mid_rescale) renormalise<NPOL, 1>(st);
@@ -845,35 +849,85 @@ tmm_cavity_kernel(const GridParams prm, const CavityPlan cp) {
         if (cp.mirrored) { const double t = P.p00; P.p00 = P.p11; P.p11 = t; }
       } else {
         PairPower S2;  // powered only now: cheaper than holding a second matrix across the spacer
-        pair_power_coeffs(U, cp.k2, lg, S2);
+        pair_power_coeffs_t<RESC>(U, cp.k2, cp.hb2, S2);
         pair_power_matrix<NPOL>(U, S2, ct, ict, prm.pol_first, P);
       }
       apply_pair_matrix<NPOL, 1>(st, P);
       renormalise<NPOL, 1>(st);
       {
-        const double in0r = val(20), in0i = val(21), nfr = val(18), nfi = val(19);
+        const double2 in0 = PST_V2(16), nf2 = PST_V2(14);
 #pragma unroll
         for (int pp = 0; pp < NPOL; ++pp) {
-          const PointOut r = finish_point<NPOL, 1>(st, pp, in0r, in0i, nfr, nfi, ict, prm.pol_first, prm.flags);
+          const PointOut r = finish_point<NPOL, 1>(st, pp, in0.x, in0.y, nf2.x, nf2.y, ict, prm.pol_first, prm.flags);
           outR[pp] = r.R; outT[pp] = r.T; outA[pp] = r.A;
         }
       }
     } else {
-      // ---- absorbing mirror layers (cold, out of line: its three full layer matrices must not cost the hot path
-      // registers): layer by layer, the interpreter's matrices in the interpreter's order
       double rv[kCavityRow], res[3 * NPOL];
-#pragma unroll 1
-      for (int i = 0; i < kCavityRow; ++i) rv[i] = val(i);
+      {
+        const double2 v0 = PST_V2(0), v1 = PST_V2(2), v2 = PST_V2(4), v3 = PST_V2(6), v4 = PST_V2(8), v5 = PST_V2(10);
+        const double2 v6 = PST_V2(12), v7 = PST_V2(14), v8 = PST_V2(16), v9 = PST_V2(18), v10 = PST_V2(20), v11 = PST_V2(22);
+        const double2 all[12] = {v0, v1, v2, v3, v4, v5, v6, v7, v8, v9, v10, v11};
+        for (int i = 0; i < 12; ++i) { rv[2 * i] = all[i].x; rv[2 * i + 1] = all[i].y; }
+      }
       cavity_lossy_mirrors<NPOL>(rv, cp.d[0], cp.d[1], cp.k1, cp.k2, cp.mirrored != 0, (lossy_mask & cp.lossy_a) != 0u,
-                                 (lossy_mask & (cp.lossy_ab & ~cp.lossy_a)) != 0u, lossyC, ct, ict, prm.pol_first, prm.flags, res);
+                                 (lossy_mask & (cp.lossy_ab & ~cp.lossy_a)) != 0u, (lossy_mask & cp.lossy_c) != 0u, ct, ict,
+                                 prm.pol_first, prm.flags, res);
 #pragma unroll
       for (int pp = 0; pp < NPOL; ++pp) { outR[pp] = res[3 * pp]; outT[pp] = res[3 * pp + 1]; outA[pp] = res[3 * pp + 2]; }
     }
     if (valid) {
+      const size_t o = out_base + (size_t)p;
+      if (prm.plain_out) {  // the common call: three local arrays, no tests per value
+        double* pR = prm.R + o;
+        double* pT = prm.T + o;
+        double* pA = prm.A + o;
 #pragma unroll
-      for (int pp = 0; pp < NPOL; ++pp) store_point<false>(prm, out_base + (size_t)pp * plane + (size_t)p, outR[pp], outT[pp], outA[pp]);
+        for (int pp = 0; pp < NPOL; ++pp) {
+          pR[(size_t)pp * plane] = outR[pp];
+          pT[(size_t)pp * plane] = outT[pp];
+          pA[(size_t)pp * plane] = outA[pp];
+        }
+      } else {
+#pragma unroll
+        for (int pp = 0; pp < NPOL; ++pp) store_point<false>(prm, o + (size_t)pp * plane, outR[pp], outT[pp], outA[pp]);
+      }
     }
   }
+#undef PST_V2
+}
+
+template <int NPOL, int MINB, bool ROW>
+__global__ void __launch_bounds__(128, MINB)
+tmm_cavity_kernel(const GridParams prm, const CavityPlan cp) {
+  __shared__ __align__(16) double s_row[kCavityRow];
+  const unsigned lossy_mask = __ldg(cp.lossy_types);
+  unsigned s_base = 0;
+  if constexpr (ROW) {
+    if (threadIdx.x < kCavityRow) {
+      const int src = cp.src[threadIdx.x];
+      double v = 0.0;
+      if (src >= 0) v = __ldg(prm.opt + (size_t)(prm.il0 + (int)blockIdx.y) * prm.n_mat * 6 + src);
+      else if (threadIdx.x == 7) v = cp.c_swept ? __ldg(prm.sweep_d + blockIdx.z) : cp.d[2];
+      s_row[threadIdx.x] = v;
+    }
+    s_base = (unsigned)__cvta_generic_to_shared(s_row);
+    __syncthreads();
+  }
+  const bool lossyAB = (lossy_mask & cp.lossy_ab) != 0u;
+  const bool lossyC = (lossy_mask & cp.lossy_c) != 0u;
+  // Rescaling schedule from the grid-wide growth bound (prep_kernel; block-uniform).  One power grows the state by
+  // < 2^(kPowerNoRescaleLog2 + 1) (rescaled coefficients: < 2^4), the spacer by 2^lg: up to lg = 100 the three ops fit the
+  // fp64 range without a rescale in between.  The interpreter rescales after every power; rescaling is exact, so the
+  // bits are the same.
+  const int lg = growth_log2(growth_E_of_word(lossy_mask), lossyC || lossyAB);
+  const bool mid_rescale = lg > 100;
+  const bool resc = pair_power_needs_rescale(max(cp.k1, cp.k2), lg);
+  if (lossyAB) cavity_tiles<NPOL, ROW, 2, false>(prm, cp, s_base, lossy_mask, mid_rescale);
+  else if (!lossyC && !resc) cavity_tiles<NPOL, ROW, 0, false>(prm, cp, s_base, lossy_mask, mid_rescale);
+  else if (lossyC && !resc) cavity_tiles<NPOL, ROW, 1, false>(prm, cp, s_base, lossy_mask, mid_rescale);
+  else if (!lossyC) cavity_tiles<NPOL, ROW, 0, true>(prm, cp, s_base, lossy_mask, mid_rescale);
+  else cavity_tiles<NPOL, ROW, 1, true>(prm, cp, s_base, lossy_mask, mid_rescale);
 }
 
 // ------------------------------------------------------------------------------------ refraction mode
@@ -1070,7 +1124,7 @@ __device__ __forceinline__ void sweep_loop(const GridParams& prm, const SweepCon
       }
       const double den = fma(m00.re, m00.re, m00.im * m00.im);
       const double num = fma(m10.re, m10.re, m10.im * m10.im);
-      const double iden = 1.0 / den;
+      const double iden = recip_nr(den);
       const double R = num * iden;
       const double T = scale_sq(k.det_re * iden, -(k.kfix[pp] + sc));
       if constexpr (FAST) {

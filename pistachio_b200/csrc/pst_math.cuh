@@ -87,8 +87,13 @@ static const double h_exp[14] = PST_EXP_COEFS;
 #define PST_EC(i) h_exp[i]
 #endif
 PST_HD void exp_split(double y, double& even, double& odd, int& k) {
-  double kd = rint(y * PST_EC(0));
-  kd = fmin(fmax(kd, -1.0e9), 1.0e9);
+  // |y| >= 2^30 (not NaN) is clamped to +-2^30 on the high word: the power of two then saturates the caller's exponent
+  // bookkeeping instead of overflowing it (five integer instructions; fmin/fmax on doubles cost fifteen)
+  {
+    const int hy = hi_word(y);
+    if ((unsigned)((hy & 0x7fffffff) - 0x41d00000) < (unsigned)(0x7ff00000 - 0x41d00000)) y = from_words((hy & 0x80000000) | 0x41d00000, 0);
+  }
+  const double kd = rint(y * PST_EC(0));
   double r = fma(kd, PST_EC(1), y);
   r = fma(kd, PST_EC(2), r);
   k = (int)kd;
@@ -206,6 +211,22 @@ PST_HD void sincos_core(double x, double& s, double& c) {
   // sign flips as XOR on the high word (one integer op each instead of an FP64 negate + select)
   s = xor_sign(ss, (q & 2) << 30);
   c = xor_sign(cc, ((q + 1) & 2) << 30);
+}
+
+// 1/d for the epilogues: hardware seed (2^-23) and two Newton steps, every path the same function.  The compiler's 1.0/d
+// adds an exactly-rounded last step and a slow-path branch for denormal or huge operands (ten instructions more per
+// call); the operands here are |M00|^2 of a freshly rescaled state.  <= 1 ulp; the host emulation divides.
+PST_HD double recip_nr(double d) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+#else
+  return 1.0 / d;
+#endif
 }
 
 struct cplx {
