@@ -16,7 +16,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libpistachio_b200.so")
 SOURCES = [os.path.join(CSRC, "pst_api.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("pst_kernels.cuh", "pst_chain.cuh", "pst_math.cuh", "pst_bulk.cuh")] + [
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("pst_kernels.cuh", "pst_chain.cuh", "pst_math.cuh", "pst_bulk.cuh", "pst_f32.cuh")] + [
     os.path.join(ROOT, "include", "pistachio_b200.h")
 ]
 NVCC_FLAGS = [
@@ -24,8 +24,10 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "--fmad=true",            # FMA contraction on; the phase path opts out with __dmul_rn (pst_math.cuh)
     "-Xcompiler", "-fPIC", "-shared",
-    "--use_fast_math=false" if False else "-Xptxas", "-v" if False else "-O3",
+    "-Xptxas", "-O3",
 ]
+# fast-math must stay off: the phase path (mul_rn / div_rn, pst_math.cuh) and the table lookup rely on IEEE rounding
+EXTRA_FLAGS = os.environ.get("PST_NVCC_EXTRA", "").split()
 
 
 def nvcc_path() -> str:
@@ -45,7 +47,7 @@ def up_to_date() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-lcudart"]
+    cmd = [nvcc_path()] + NVCC_FLAGS + EXTRA_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-lcudart"]
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -222,7 +222,10 @@ ChainKernel pick_chain(int npol, int ncol, bool so, bool sl, bool seg) {
 using CavityKernel = void (*)(const GridParams, const CavityPlan);
 CavityKernel pick_cavity(int npol, bool row) {
   // 2 polarisations: 80 registers, 6 blocks/SM; 1 polarisation: 64 registers, 8 blocks/SM
-  if (npol == 2) return row ? tmm_cavity_kernel<2, 6, true> : tmm_cavity_kernel<2, 6, false>;
+#ifndef PST_CAV_MINB2
+#define PST_CAV_MINB2 6
+#endif
+  if (npol == 2) return row ? tmm_cavity_kernel<2, PST_CAV_MINB2, true> : tmm_cavity_kernel<2, PST_CAV_MINB2, false>;
   if (npol == 1) return row ? tmm_cavity_kernel<1, 8, true> : tmm_cavity_kernel<1, 8, false>;
   return nullptr;
 }
@@ -361,7 +364,7 @@ int run_prep(pst_handle_t h, const pst_grid_args* a, const double* wl, const dou
              const double* mat_n, const double* mat_k, cudaStream_t st) {
   const long long nm = (long long)a->n_wl * a->n_mat;
   PST_TRY(h->opt.ensure((size_t)nm * 6));
-  PST_TRY(h->trig.ensure(a->n_theta));
+  PST_TRY(h->trig.ensure((size_t)a->n_theta + kTrigPad));  // padded with copies of the last angle (prep_kernel)
   PST_TRY(h->layers_flagged.ensure(a->n_layers));
   PST_TRY(h->lossy_types.ensure(1));
   // flags and ticket are zero between calls (the kernel's last block clears them); zero them when (re)allocated
@@ -375,7 +378,7 @@ int run_prep(pst_handle_t h, const pst_grid_args* a, const double* wl, const dou
   tm.n = h->n_types;
   for (int t = 0; t < kMaxTypes; ++t) tm.mat[t] = t < h->n_types ? a->layer_mat[h->type_layer[t]] : 0;
   const int n_opt_blocks = (int)((nm + 255) / 256);
-  const int n_trig_blocks = (a->n_theta + 255) / 256;
+  const int n_trig_blocks = (a->n_theta + kTrigPad + 255) / 256;
   prep_kernel<<<(unsigned)(n_opt_blocks + n_trig_blocks), 256, 0, st>>>(
       wl, mat_n, mat_k, a->n_wl, a->n_mat, h->opt.p, h->mat_flags.p, theta, cos_theta, a->n_theta, h->trig.p, n_opt_blocks,
       h->layers_dev.p, a->n_layers, h->layers_flagged.p, tm, h->lossy_types.p, h->prep_ticket.p);
@@ -504,7 +507,7 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
       pl->fn_cavity = pick_cavity(pl->npol, pl->row);
       if (!pl->fn_cavity) return fail(PST_E_INVALID, "pst_eval_grid: no cavity kernel variant for this configuration");
       if (pl->row) {
-        const long long slots = (long long)h->sm_count * (pl->npol == 2 ? 6 : 8);
+        const long long slots = (long long)h->sm_count * (pl->npol == 2 ? PST_CAV_MINB2 : 8);
         for (int t : {8, 4, 2}) {
           if (t <= tiles && (long long)((tiles + t - 1) / t) * n_wl_launch * a->n_sweep >= 16 * slots) {
             pl->cp.tiles = t;

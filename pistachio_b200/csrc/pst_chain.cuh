@@ -279,9 +279,9 @@ PST_HD void pair_power_step(const Period& U, bool mul, PairPower& S) {
   const double t = S.t, s = S.s;
   double tn = fma(t, t, -((U.s2 * s) * s));  // (t, s)^2
   double sn = (t + t) * s;
-  if (mul) {                                   // times U = (x, 1)
-    const double tm = fma(U.x, tn, -(U.s2 * sn));
-    sn = fma(U.x, sn, tn);
+  if (__builtin_expect(mul, 0)) {  // times U = (x, 1).  `mul` is block-uniform; marked unlikely so that it compiles to
+    const double tm = fma(U.x, tn, -(U.s2 * sn));  // predicated instructions (issue slots only when the bit is clear)
+    sn = fma(U.x, sn, tn);                         // instead of three unconditional FP64 instructions and four selects
     tn = tm;
   }
   if (RESCALE) {

@@ -202,6 +202,7 @@ struct TypeMats {
   int n;
   int mat[kMaxTypes];
 };
+constexpr int kTrigPad = 1024;  // >= 128 * (largest cp.tiles)
 
 __global__ void __launch_bounds__(256)
 prep_kernel(const double* __restrict__ wl, const double* __restrict__ mat_n, const double* __restrict__ mat_k, int n_wl,
@@ -241,11 +242,13 @@ prep_kernel(const double* __restrict__ wl, const double* __restrict__ mat_n, con
       }
     }
   } else {
-    const int i = ((int)blockIdx.x - n_opt_blocks) * blockDim.x + threadIdx.x;
-    if (i < n_theta) {
+    // the angle table is padded by kTrigPad copies of the last angle: the cavity kernel's tile loop reads whole tiles
+    const int ip = ((int)blockIdx.x - n_opt_blocks) * blockDim.x + threadIdx.x;
+    if (ip < n_theta + kTrigPad) {
+      const int i = min(ip, n_theta - 1);
       const double c = cos_theta ? cos_theta[i] : cos(theta[i]);
       const double ic = 1.0 / c;
-      trig[i] = make_double2(c, ic);
+      trig[ip] = make_double2(c, ic);
       const unsigned act = __activemask();
       const unsigned hw = __reduce_max_sync(act, (unsigned)hi_word(ic) & 0x7fffffffu);
       if ((threadIdx.x & 31) == __ffs(act) - 1 && hw > __ldcg(ticket + 2)) atomicMax(ticket + 2, hw);
@@ -744,8 +747,9 @@ __device__ __noinline__ void cavity_lossy_mirrors(const double* rv, double dA, d
   }
 }
 
-// MODE: 0 lossless spacer, 1 absorbing spacer, 2 absorbing mirror layers (cold);  RESC: rescaled powering
-template <int NPOL, bool ROW, int MODE, bool RESC>
+// MODE: 0 lossless spacer, 1 absorbing spacer, 2 absorbing mirror layers (cold);  RESC: rescaled powering;
+// MIRRORED: the second mirror is the mirror image of the first (only looked at when the pair counts agree)
+template <int NPOL, bool ROW, int MODE, bool RESC, bool MIRRORED>
 __device__ __forceinline__ void cavity_tiles(const GridParams& prm, const CavityPlan& cp, unsigned s_base, unsigned lossy_mask,
                                              bool mid_rescale) {
   const unsigned npts = (unsigned)prm.points, nth = (unsigned)prm.n_theta;
@@ -782,22 +786,21 @@ __device__ __forceinline__ void cavity_tiles(const GridParams& prm, const Cavity
 #define PST_V2(i) val2(std::integral_constant<int, i>{})
   const size_t plane = (size_t)prm.points;
   const size_t out_base = (size_t)sweep_idx * (size_t)(NPOL << prm.pol_dup) * plane;
-
-  double2 tr_next;
-  if constexpr (ROW) tr_next = __ldg(prm.trig + min(tile0 * 128u + threadIdx.x, nth - 1u));
-  else tr_next = __ldg(prm.trig + it);
-  for (int tile = 0; tile < n_tiles; ++tile) {
+  // per-thread cursors, advanced by one tile (128 angles) per trip: the angle table is padded (kTrigPad), so tiles are
+  // read whole and only the stores are predicated
+  unsigned itr = ROW ? tile0 * 128u + threadIdx.x : 0u;
+  const double2* trp = prm.trig + (ROW ? itr : (unsigned)it);
+  size_t o = out_base + (ROW ? (size_t)blockIdx.y * nth + itr : (size_t)p);
+  double2 tr_next = __ldg(trp);
+  for (int tile = 0; tile < n_tiles; ++tile, itr += 128u, o += 128u) {
     if constexpr (ROW) {
-      const unsigned t128 = (tile0 + (unsigned)tile) * 128u;
-      if (t128 >= nth) break;  // block-uniform: ragged last block
-      const unsigned itr = t128 + threadIdx.x;
+      if (itr - threadIdx.x >= nth) break;  // block-uniform: ragged last block
       valid = itr < nth;
-      it = (int)(valid ? itr : nth - 1u);  // tail lanes shadow the last angle
-      p = blockIdx.y * nth + (unsigned)it;
     }
     const double ct = tr_next.x, ict = tr_next.y;
     if constexpr (ROW) {
-      if (tile + 1 < n_tiles) tr_next = __ldg(prm.trig + min((tile0 + (unsigned)tile + 1u) * 128u + threadIdx.x, nth - 1u));
+      trp += 128;
+      if (tile + 1 < n_tiles) tr_next = __ldg(trp);
     }
     double outR[NPOL], outT[NPOL], outA[NPOL];
     if constexpr (MODE != 2) {
@@ -846,7 +849,7 @@ __device__ __forceinline__ void cavity_tiles(const GridParams& prm, const Cavity
       if (mid_rescale) renormalise<NPOL, 1>(st);
       // ---- second mirror: the same matrix (exchanged diagonal for the mirror image: w -> -w) when the pair counts agree
       if (cp.k2 == cp.k1) {
-        if (cp.mirrored) { const double t = P.p00; P.p00 = P.p11; P.p11 = t; }
+        if constexpr (MIRRORED) { const double t = P.p00; P.p00 = P.p11; P.p11 = t; }
       } else {
         PairPower S2;  // powered only now: cheaper than holding a second matrix across the spacer
         pair_power_coeffs_t<RESC>(U, cp.k2, cp.hb2, S2);
@@ -877,7 +880,6 @@ __device__ __forceinline__ void cavity_tiles(const GridParams& prm, const Cavity
       for (int pp = 0; pp < NPOL; ++pp) { outR[pp] = res[3 * pp]; outT[pp] = res[3 * pp + 1]; outA[pp] = res[3 * pp + 2]; }
     }
     if (valid) {
-      const size_t o = out_base + (size_t)p;
       if (prm.plain_out) {  // the common call: three local arrays, no tests per value
         double* pR = prm.R + o;
         double* pT = prm.T + o;
@@ -912,6 +914,7 @@ tmm_cavity_kernel(const GridParams prm, const CavityPlan cp) {
       s_row[threadIdx.x] = v;
     }
     s_base = (unsigned)__cvta_generic_to_shared(s_row);
+    asm volatile("" : "+r"(s_base));  // opaque: held in a register instead of being rebuilt from the window base per load
     __syncthreads();
   }
   const bool lossyAB = (lossy_mask & cp.lossy_ab) != 0u;
@@ -923,11 +926,17 @@ tmm_cavity_kernel(const GridParams prm, const CavityPlan cp) {
   const int lg = growth_log2(growth_E_of_word(lossy_mask), lossyC || lossyAB);
   const bool mid_rescale = lg > 100;
   const bool resc = pair_power_needs_rescale(max(cp.k1, cp.k2), lg);
-  if (lossyAB) cavity_tiles<NPOL, ROW, 2, false>(prm, cp, s_base, lossy_mask, mid_rescale);
-  else if (!lossyC && !resc) cavity_tiles<NPOL, ROW, 0, false>(prm, cp, s_base, lossy_mask, mid_rescale);
-  else if (lossyC && !resc) cavity_tiles<NPOL, ROW, 1, false>(prm, cp, s_base, lossy_mask, mid_rescale);
-  else if (!lossyC) cavity_tiles<NPOL, ROW, 0, true>(prm, cp, s_base, lossy_mask, mid_rescale);
-  else cavity_tiles<NPOL, ROW, 1, true>(prm, cp, s_base, lossy_mask, mid_rescale);
+  const bool mir = cp.mirrored != 0;
+#define PST_CT(MODE, RESC, MIR) cavity_tiles<NPOL, ROW, MODE, RESC, MIR>(prm, cp, s_base, lossy_mask, mid_rescale)
+  if (lossyAB) PST_CT(2, false, false);
+  else if (!resc) {
+    if (!lossyC) { if (mir) PST_CT(0, false, true); else PST_CT(0, false, false); }
+    else { if (mir) PST_CT(1, false, true); else PST_CT(1, false, false); }
+  } else {
+    if (!lossyC) { if (mir) PST_CT(0, true, true); else PST_CT(0, true, false); }
+    else { if (mir) PST_CT(1, true, true); else PST_CT(1, true, false); }
+  }
+#undef PST_CT
 }
 
 // ------------------------------------------------------------------------------------ refraction mode

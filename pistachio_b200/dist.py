@@ -108,24 +108,37 @@ class AssembledResult:
                         copy comes back through the switch as well, so every GPU receives the WHOLE array
       mode "nccl"       compute into the local slab, then the in-place NCCL all-gather (two passes; the baseline)
 
+    `root` = None assembles on EVERY GPU; `root` = r assembles on rank r only (north_star: "a final gather only when
+    results must be assembled on one device"): every rank stores its slab into rank r's copy and nowhere else, so one
+    link receives and the other GPUs' links and memory stay free for their next chunk (NCCL mode: dist.gather).
+    `keys` selects the arrays that cross the links -- ("T", "R") by default: A = (1 - R) - T exactly (it is computed
+    that way, pst_chain.cuh finish_point_det), so whoever needs A recomputes it from the assembled T and R
+    (`absorptance()`), and a third of the wire bytes never travel.
+
     `finish()` orders the devices (stream sync + symmetric-memory barrier) before anyone reads `full[...]`.
     """
 
-    def __init__(self, n_slow: int, plane_shape, rank: int, world: int, device, group=None, mode: str = "unicast"):
+    def __init__(self, n_slow: int, plane_shape, rank: int, world: int, device, group=None, mode: str = "unicast",
+                 root: int | None = None, keys=("T", "R")):
         import torch.distributed._symmetric_memory as symm
 
         if n_slow % world:
             raise ValueError("AssembledResult needs equal slabs (slow axis divisible by the world size)")
         if mode not in ("unicast", "multicast", "nccl"):
             raise ValueError("mode must be 'unicast', 'multicast' or 'nccl'")
+        if root is not None and not (0 <= root < world):
+            raise ValueError("root must be a rank of the group")
+        if mode == "multicast" and root is not None:
+            raise ValueError("multicast stores reach every GPU of the mapping: use mode='unicast' with a root")
         self.rank, self.world, self.per = rank, world, n_slow // world
+        self.root, self.keys = root, tuple(keys)
         self.group = group if group is not None else dist.group.WORLD
         self.shape = (n_slow,) + tuple(plane_shape)
         self.plane_elems = 1
         for s in plane_shape:
             self.plane_elems *= int(s)
         self.full, self.handles = {}, {}
-        for k in ("R", "T", "A"):
+        for k in self.keys:
             t = symm.empty(self.shape, dtype=torch.float64, device=device)
             self.full[k] = t
             self.handles[k] = symm.rendezvous(t, self.group)
@@ -147,8 +160,12 @@ class AssembledResult:
     def peer_ptrs(self) -> dict:
         """This rank's slab inside every GPU's copy, rotated so that each rank starts with its right-hand neighbour
         (at any instant the ranks then target different destinations)."""
-        order = [(self.rank + 1 + i) % self.world for i in range(self.world)]
+        order = [(self.rank + 1 + i) % self.world for i in range(self.world)] if self.root is None else [self.root]
         return {k: [int(h.buffer_ptrs[i]) + self._slab_offset for i in order] for k, h in self.handles.items()}
+
+    def absorptance(self) -> torch.Tensor:
+        """A = (1 - R) - T of the assembled arrays: bit for bit what the kernels compute per point."""
+        return (1.0 - self.full["R"]) - self.full["T"]
 
     def eval_into(self, eng, prep_slab: dict, pols, flags: int = 0):
         """Evaluate this rank's slab (a prepared dict whose sweep_d holds this rank's `per` thicknesses)."""
@@ -158,12 +175,16 @@ class AssembledResult:
             return eng.eval_prepared(prep_slab, pols=pols, out_ptrs=self.multicast_ptrs(), flags=flags | FLAG_MULTICAST_OUT)
         if self.mode == "unicast":
             return eng.eval_prepared(prep_slab, pols=pols, out_ptrs=self.peer_ptrs(), flags=flags)
-        return eng.eval_prepared(prep_slab, pols=pols, out={k: self.local_slab(k) for k in ("R", "T", "A")}, flags=flags)
+        return eng.eval_prepared(prep_slab, pols=pols, want=self.keys, out={k: self.local_slab(k) for k in self.keys}, flags=flags)
 
     def finish(self):
         if self.mode == "nccl":
-            for k in ("R", "T", "A"):
-                dist.all_gather_into_tensor(self.full[k], self.local_slab(k), group=self.group)
+            for k in self.keys:
+                if self.root is None:
+                    dist.all_gather_into_tensor(self.full[k], self.local_slab(k), group=self.group)
+                else:
+                    slabs = [self.full[k][r * self.per:(r + 1) * self.per] for r in range(self.world)] if self.rank == self.root else None
+                    dist.gather(self.local_slab(k), gather_list=slabs, dst=self.root, group=self.group)
             return
         torch.cuda.current_stream().synchronize()
-        self.handles["R"].barrier()
+        self.handles[self.keys[0]].barrier()

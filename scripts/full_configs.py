@@ -165,7 +165,7 @@ def main() -> None:
             fused = {}
             for mode in ("unicast", "multicast"):
                 try:
-                    asm = pdist.AssembledResult(n_d, (2, 8192, 256), rank, world, eng.device, mode=mode)
+                    asm = pdist.AssembledResult(n_d, (2, 8192, 256), rank, world, eng.device, mode=mode, keys=("R", "T", "A"))
 
                     def fused_step():
                         asm.eval_into(eng, p, pols)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence for the bench command: launch list + one full capture of the chain kernel.
 mkdir -p gpurun_out
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline ${BENCH_ARGS:-}"
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-configs --no-sustained --no-ablation ${BENCH_ARGS:-}"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 &&
