@@ -532,7 +532,10 @@ int plan_chain(pst_handle_t h, const pst_grid_args* a, int n_wl_launch, ChainPla
   const size_t lay_bytes = (size_t)a->n_layers * sizeof(LayerEntry);
   const size_t opt_bytes = (size_t)pl->tl_rows * pl->opt_row_bytes;
   pl->sl = lay_bytes <= 64 * 1024 && seg_bytes + type_bytes + lay_bytes <= budget;
-  size_t used = seg_bytes + type_bytes + (pl->sl ? lay_bytes : 0);
+  // deep stacks whose layer list does not fit: every warp streams its segments' slices through a double-buffered window
+  // of 32 layers per segment (tmm_chain_kernel, STREAM): 2 x 32 x 16 bytes per segment
+  const size_t stream_bytes = (pl->seg && !pl->sl) ? (size_t)W * 1024 : 0;
+  size_t used = seg_bytes + type_bytes + stream_bytes + (pl->sl ? lay_bytes : 0);
   pl->so = !(a->flags & PST_FLAG_NO_SMEM_STAGING) && used + opt_bytes <= std::min<size_t>(budget, std::max<size_t>(96 * 1024, used + 16 * 1024));
   used += pl->so ? opt_bytes : 0;
   if (used > budget) return fail(PST_E_INVALID, "pst_eval_grid: shared-memory plan exceeds the device limit");

@@ -74,6 +74,24 @@ PST_HD RealLayer<NPOL> finish_real_layer(double sx, double cx, double nr, double
   return m;
 }
 
+// the same with the polarisation factors resolved by the caller (g = cos for s, 1/cos for p; gi = 1/g): loops over many
+// layers hoist the selection
+template <int NPOL>
+PST_HD RealLayer<NPOL> finish_real_layer_g(double sx, double cx, double nr, double inr, const double (&g)[NPOL],
+                                           const double (&gi)[NPOL]) {
+  const double sn = sx * nr, si = sx * inr;
+  RealLayer<NPOL> m;
+  m.c = cx;
+  m.sn = sn;
+  m.si = si;
+#pragma unroll
+  for (int p = 0; p < NPOL; ++p) {
+    m.al[p] = g[p] * sn;
+    m.be[p] = gi[p] * si;
+  }
+  return m;
+}
+
 template <int NPOL>
 PST_HD CplxLayer<NPOL> finish_cplx_layer(double sx, double cx, double y, const OptRow& o, double ct, double ict,
                                          int pol_first) {

@@ -35,6 +35,16 @@ constexpr int kMaxTypes = 8;        // distinct (material, thickness) pairs the 
 constexpr int kTypeRecBytes = 80;   // one cached layer matrix: 10 doubles (complex form) or 5 (real form); the
                                     // power-of-two exponents of all types follow the records as ints
 constexpr int kRenormEvery = 16;
+// deep-stack kernel: layers whose transcendental parts share a basic block, and groups per unrolled loop trip
+// (measured on BASELINE configs[3]: 1/1 0.672 ms, 2/1 0.582, 2/2 0.569, 2/8 0.594 -- instruction cache --, 4/1 0.567 with
+// 208 bytes of spills at the 72-register cap, 4/4 0.620)
+#ifndef PST_K2_GROUP
+#define PST_K2_GROUP 2
+#endif
+#ifndef PST_K2_UNROLL
+#define PST_K2_UNROLL 2
+#endif
+constexpr int kK2Group = PST_K2_GROUP, kK2Unroll = PST_K2_UNROLL;
 constexpr int kMaxOps = 24;         // run-length ops the typed kernel takes by value (longer programs use K1 untyped)
 
 struct GridParams {
@@ -286,8 +296,9 @@ prep_kernel(const double* __restrict__ wl, const double* __restrict__ mat_n, con
 //   STAGE_OPT / STAGE_LAYERS  optical table window and layer list staged in shared memory once per block
 //   SEG    blockDim.y ordered layer segments per point, combined in order through shared memory (deep stacks)
 template <int NPOL, int NCOL, bool STAGE_OPT, bool STAGE_LAYERS, bool SEG>
-__global__ void __launch_bounds__(SEG ? 512 : 256, (SEG && NPOL == 1) ? 2 : 1)  // deep-stack kernel: 64 registers, 8 x 128-thread blocks per SM
-tmm_chain_kernel(const GridParams prm) {
+__global__ void __launch_bounds__(SEG ? 512 : 256)
+__maxnreg__(SEG ? (NPOL == 1 ? 72 : 128) : 255)  // deep-stack kernel, one polarisation: 72 registers = 28 warps per SM, what
+tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384 points x 8 segments) needs to be resident at once
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NC = SEG ? 2 : NCOL;  // a segment product needs both columns
   const int PB = blockDim.x;          // points per block
@@ -308,6 +319,13 @@ tmm_chain_kernel(const GridParams prm) {
   LayerEntry* s_layers = reinterpret_cast<LayerEntry*>(smem_raw + off);
   off += STAGE_LAYERS ? (size_t)L * sizeof(LayerEntry) : 0;
   double* s_seg = reinterpret_cast<double*>(smem_raw + off);
+  // SEG without a staged layer list (deep stacks: the list does not fit): every warp streams its segments' slices of the
+  // list through a double-buffered shared-memory window with the bulk-copy engine (below)
+  constexpr bool STREAM = SEG && !STAGE_LAYERS;
+  constexpr int kStreamChunk = 32;  // layers per chunk and segment (512 bytes)
+  off += SEG ? (size_t)W * NPOL * 9 * PB * sizeof(double) : 0;
+  LayerEntry* s_stream = reinterpret_cast<LayerEntry*>(smem_raw + off);  // [warp][2][segments per warp][kStreamChunk]
+  __shared__ __align__(8) uint64_t s_sbar[16][2];                        // one mbarrier per warp and buffer
 
   // the block's wavelength window of the [wl][mat][6] table is one contiguous global range; rows are re-pitched
   // to opt_row_bytes so that lanes on different wavelengths hit different 16-byte bank groups (pst_bulk.cuh)
@@ -358,6 +376,75 @@ tmm_chain_kernel(const GridParams prm) {
   if constexpr (SEG) init_identity<NPOL>(st);
   else init_exit_columns<NPOL, NC>(st, exit_row.nr, exit_row.ni, ct, prm.pol_first);
 
+  // ---- iteration over this thread's layers j_hi-1 .. j_lo: apply(entry, j) per layer, rescale() every kRenormEvery layers
+  auto for_each_layer = [&](auto UNROLLED, auto&& apply, auto&& apply2, auto&& rescale) {
+    if constexpr (!STREAM) {
+      int j = j_hi - 1;
+      while (j >= j_lo) {
+        const int j_stop = max(j - kRenormEvery, j_lo - 1);
+        for (; j - 1 > j_stop; j -= 2) apply2(lay + j, j, std::integral_constant<int, 2>{});  // layers j, j - 1
+        if (j > j_stop) {
+          apply(lay[j], j);
+          --j;
+        }
+        rescale();
+      }
+    } else {
+      // A warp holds SW = 32 / PB consecutive segments (lane = segment-in-warp * PB + point).  Chunk k of a segment is the
+      // kStreamChunk layers below j_hi - k kStreamChunk: one contiguous, 16-byte aligned range of the global list -> one
+      // cp.async.bulk per segment and chunk, completing on the warp's mbarrier of that buffer; chunk k + 1 is in flight
+      // while chunk k is multiplied.  The per-layer global load (and its L2 round trip on the dependent path: 1.4
+      // long-scoreboard stalls per issue in round 1's capture) becomes one broadcast LDS.128, and full batches of
+      // kRenormEvery layers run unrolled: no loop counter, no index arithmetic per layer.
+      const int lane = tid & 31, warp = tid >> 5;
+      const int SWs = 32 / PB, segw = lane / PB;
+      LayerEntry* wbuf = s_stream + (size_t)warp * 2 * SWs * kStreamChunk;
+      if (lane == 0) {
+        mbar_init(&s_sbar[warp][0], 1);
+        mbar_init(&s_sbar[warp][1], 1);
+      }
+      __syncwarp();
+      const int n_mine = j_hi - j_lo;
+      const int n_chunks = (seg_q + (seg_r ? 1 : 0) + kStreamChunk - 1) / kStreamChunk;  // block-uniform upper bound
+      const bool leader = (lane - segw * PB) == 0;
+      auto issue = [&](int k) {
+        // all segments of the warp copy [lo, hi) with lo = max(j_hi - (k + 1) CH, 0): the bytes are summed over the
+        // warp's segment leaders (lanes with point index 0) for the transaction count
+        const int hi = j_hi - k * kStreamChunk, lo = max(hi - kStreamChunk, 0);
+        const int bytes = (leader && hi > lo) ? (hi - lo) * (int)sizeof(LayerEntry) : 0;
+        const int total = __reduce_add_sync(0xffffffffu, bytes);
+        if (lane == 0) mbar_expect_tx(&s_sbar[warp][k & 1], (uint32_t)total);
+        __syncwarp();
+        // the copy is ascending in j and lands at slots [CH - (hi - lo), CH): layer hi - 1 - i sits at slot CH - 1 - i
+        if (bytes > 0)
+          bulk_g2s(wbuf + ((size_t)(k & 1) * SWs + segw) * kStreamChunk + (kStreamChunk - (hi - lo)), prm.layers + lo,
+                   (uint32_t)bytes, &s_sbar[warp][k & 1]);
+      };
+      issue(0);
+      for (int k = 0; k < n_chunks; ++k) {
+        if (k + 1 < n_chunks) issue(k + 1);
+        mbar_wait(&s_sbar[warp][k & 1], (uint32_t)((k >> 1) & 1));
+        const LayerEntry* top = wbuf + ((size_t)(k & 1) * SWs + segw) * kStreamChunk + (kStreamChunk - 1);  // slot of layer j_top
+        const int j_top = j_hi - 1 - k * kStreamChunk;
+        const int left = n_mine - k * kStreamChunk;  // layers of this lane not yet applied (may be <= 0)
+#pragma unroll
+        for (int b0 = 0; b0 < kStreamChunk; b0 += kRenormEvery) {
+          if (decltype(UNROLLED)::value && left >= b0 + kRenormEvery) {
+#pragma unroll kK2Unroll
+            for (int i = 0; i < kRenormEvery; i += kK2Group)  // kK2Group layers at a time: their sincos chains interleave
+              apply2(top - (b0 + i), j_top - (b0 + i), std::integral_constant<int, kK2Group>{});
+            rescale();
+          } else if (left > b0) {
+            const int end = min(left, b0 + kRenormEvery);
+            for (int i = b0; i < end; ++i) apply(top[-i], j_top - i);
+            rescale();
+          }
+        }
+        __syncwarp();  // every lane is done with this buffer before chunk k + 2 overwrites it
+      }
+    }
+  };
+
   bool done = false;
   if constexpr (SEG) {
     if (!(__ldg(prm.lossy_word) >> 31)) {
@@ -369,36 +456,72 @@ tmm_chain_kernel(const GridParams prm) {
       int ke[NPOL];
 #pragma unroll
       for (int pp = 0; pp < NPOL; ++pp) { a[pp] = 1.0; w[pp] = 0.0; u[pp] = 0.0; b[pp] = 1.0; ke[pp] = 0; }
-      int j = j_hi - 1;
-      while (j >= j_lo) {
-        const int j_stop = max(j - kRenormEvery, j_lo - 1);
-        for (; j > j_stop; --j) {
-          const LayerEntry le = lay[j];
-          const double d = (j == prm.sweep_layer) ? d_sweep : le.d;
-          double qr, nr, inr;
-          opt_row_real(le.mat, qr, nr, inr);
-          const RealLayer<NPOL> m = build_real_layer<NPOL>(qr, nr, inr, d, ct, ict, prm.pol_first);
+      double g[NPOL], gi[NPOL];
 #pragma unroll
-          for (int pp = 0; pp < NPOL; ++pp) {
-            const double a0 = a[pp], w0 = w[pp], u0 = u[pp], b0 = b[pp];
-            a[pp] = fma(m.c, a0, m.be[pp] * w0);
-            w[pp] = fma(m.c, w0, -(m.al[pp] * a0));
-            u[pp] = fma(m.c, u0, -(m.be[pp] * b0));
-            b[pp] = fma(m.c, b0, m.al[pp] * u0);
-          }
-        }
-#pragma unroll
-        for (int pp = 0; pp < NPOL; ++pp) {  // exact power-of-two rescale, as renormalise()
-          unsigned mh = (unsigned)hi_word(a[pp]) & 0x7fffffffu;
-          mh = max(mh, (unsigned)hi_word(w[pp]) & 0x7fffffffu);
-          mh = max(mh, (unsigned)hi_word(u[pp]) & 0x7fffffffu);
-          mh = max(mh, (unsigned)hi_word(b[pp]) & 0x7fffffffu);
-          int e = clamp_exp((int)(mh >> 20) - 1023);
-          const double sc = from_words((1023 - e) << 20, 0);
-          a[pp] *= sc; w[pp] *= sc; u[pp] *= sc; b[pp] *= sc;
-          ke[pp] += e;
-        }
+      for (int pp = 0; pp < NPOL; ++pp) {
+        const bool is_s = pol_is_s<NPOL>(pp, prm.pol_first);
+        g[pp] = is_s ? ct : ict;
+        gi[pp] = is_s ? ict : ct;
       }
+      const int sweep_j = prm.sweep_d ? prm.sweep_layer : -1;
+      auto phase_of = [&](const LayerEntry& le, int j, double& nr, double& inr) {
+        const double d = (j == sweep_j) ? d_sweep : le.d;
+        double qr;
+        opt_row_real(le.mat, qr, nr, inr);
+        return layer_phase(qr, ct, d);
+      };
+      auto step = [&](double sx, double cx, double nr, double inr) {
+        const RealLayer<NPOL> m = finish_real_layer_g<NPOL>(sx, cx, nr, inr, g, gi);
+#pragma unroll
+        for (int pp = 0; pp < NPOL; ++pp) {
+          const double a0 = a[pp], w0 = w[pp], u0 = u[pp], b0 = b[pp];
+          a[pp] = fma(m.c, a0, m.be[pp] * w0);
+          w[pp] = fma(m.c, w0, -(m.al[pp] * a0));
+          u[pp] = fma(m.c, u0, -(m.be[pp] * b0));
+          b[pp] = fma(m.c, b0, m.al[pp] * u0);
+        }
+      };
+      for_each_layer(
+          std::true_type{},
+          [&](const LayerEntry& le, int j) {
+            double nr, inr, sx, cx;
+            sincos_fast(phase_of(le, j, nr, inr), sx, cx);
+            step(sx, cx, nr, inr);
+          },
+          [&](const LayerEntry* first, int j_first, auto N_) {
+            // the transcendental parts of N consecutive layers (first[0], first[-1], ...) in one basic block with one joint
+            // range test, then the N ordered steps
+            constexpr int N = decltype(N_)::value;
+            double nr[N], inr[N], x[N], sx[N], cx[N];
+            bool fast = true;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              x[i] = phase_of(first[-i], j_first - i, nr[i], inr[i]);
+              fast = fast && sincos_in_fast_range(x[i]);
+            }
+            if (fast) {
+#pragma unroll
+              for (int i = 0; i < N; ++i) sincos_core(x[i], sx[i], cx[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < N; ++i) sincos_fast(x[i], sx[i], cx[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) step(sx[i], cx[i], nr[i], inr[i]);
+          },
+          [&]() {
+#pragma unroll
+            for (int pp = 0; pp < NPOL; ++pp) {  // exact power-of-two rescale, as renormalise()
+              unsigned mh = (unsigned)hi_word(a[pp]) & 0x7fffffffu;
+              mh = max(mh, (unsigned)hi_word(w[pp]) & 0x7fffffffu);
+              mh = max(mh, (unsigned)hi_word(u[pp]) & 0x7fffffffu);
+              mh = max(mh, (unsigned)hi_word(b[pp]) & 0x7fffffffu);
+              const int e = clamp_exp((int)(mh >> 20) - 1023);
+              const double sc = from_words((1023 - e) << 20, 0);
+              a[pp] *= sc; w[pp] *= sc; u[pp] *= sc; b[pp] *= sc;
+              ke[pp] += e;
+            }
+          });
 #pragma unroll
       for (int pp = 0; pp < NPOL; ++pp) {
         st.v[pp][0][0] = a[pp]; st.v[pp][0][1] = 0.0; st.v[pp][0][2] = 0.0; st.v[pp][0][3] = w[pp];
@@ -409,23 +532,45 @@ tmm_chain_kernel(const GridParams prm) {
     }
   }
   if (!done) {
-    int j = j_hi - 1;
-    while (j >= j_lo) {
-      const int j_stop = max(j - kRenormEvery, j_lo - 1);
-      for (; j > j_stop; --j) {
-        const LayerEntry le = lay[j];
-        const double d = (j == prm.sweep_layer) ? d_sweep : le.d;
-        const int lossy = le.type;  // untyped launches get the flagged layer list (prep_kernel)
-        if (lossy == 0) {
-          double qr, nr, inr;
-          opt_row_real(le.mat, qr, nr, inr);
-          apply_real_layer<NPOL, NC>(st, build_real_layer<NPOL>(qr, nr, inr, d, ct, ict, prm.pol_first));
-        } else {
-          apply_cplx_layer<NPOL, NC>(st, build_cplx_layer<NPOL>(opt_row(le.mat), d, ct, ict, prm.pol_first));
-        }
-      }
-      renormalise<NPOL, NC>(st);
-    }
+    auto apply_any = [&](const LayerEntry& le, int j) {
+          const double d = (j == prm.sweep_layer) ? d_sweep : le.d;
+          const int lossy = le.type;  // untyped launches get the flagged layer list (prep_kernel)
+          if (lossy == 0) {
+            double qr, nr, inr;
+            opt_row_real(le.mat, qr, nr, inr);
+            apply_real_layer<NPOL, NC>(st, build_real_layer<NPOL>(qr, nr, inr, d, ct, ict, prm.pol_first));
+          } else {
+            apply_cplx_layer<NPOL, NC>(st, build_cplx_layer<NPOL>(opt_row(le.mat), d, ct, ict, prm.pol_first));
+          }
+        };
+    for_each_layer(std::false_type{}, apply_any,
+                   [&](const LayerEntry* first, int j_first, auto N_) {
+                     constexpr int N = decltype(N_)::value;
+                     if constexpr (N == 2) {
+                       // two lossless neighbours (block-uniform: the flag is the material's): their sincos chains share a
+                       // basic block under one joint range test, then the two ordered steps
+                       const LayerEntry le0 = first[0], le1 = first[-1];
+                       if (le0.type == 0 && le1.type == 0) {
+                         double q0, n0, in0, q1, n1, in1, sx0, cx0, sx1, cx1;
+                         opt_row_real(le0.mat, q0, n0, in0);
+                         opt_row_real(le1.mat, q1, n1, in1);
+                         const double x0 = layer_phase(q0, ct, (j_first == prm.sweep_layer) ? d_sweep : le0.d);
+                         const double x1 = layer_phase(q1, ct, (j_first - 1 == prm.sweep_layer) ? d_sweep : le1.d);
+                         if (sincos_in_fast_range(x0) && sincos_in_fast_range(x1)) {
+                           sincos_core(x0, sx0, cx0);
+                           sincos_core(x1, sx1, cx1);
+                         } else {
+                           sincos_fast(x0, sx0, cx0);
+                           sincos_fast(x1, sx1, cx1);
+                         }
+                         apply_real_layer<NPOL, NC>(st, finish_real_layer<NPOL>(sx0, cx0, n0, in0, ct, ict, prm.pol_first));
+                         apply_real_layer<NPOL, NC>(st, finish_real_layer<NPOL>(sx1, cx1, n1, in1, ct, ict, prm.pol_first));
+                         return;
+                       }
+                     }
+                     for (int i = 0; i < N; ++i) apply_any(first[-i], j_first - i);
+                   },
+        [&]() { renormalise<NPOL, NC>(st); });
   }
 
   ChainState<NPOL, NCOL> fin;
