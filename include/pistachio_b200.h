@@ -252,6 +252,21 @@ int pst_polariton_branches(pst_handle_t h, const double* y /*[dev]*/, int n_oute
                            const double* peak_height /*[dev]*/, const int* peak_count /*[dev]*/, int max_peaks,
                            double* out /*[dev] n_outer*n_inner*6*/, void* stream);
 
+/* Joint two-Lorentzian least-squares fit per spectrum: the fit the reference's notebooks/Polariton Peak Analysis.ipynb
+ * runs per angle (cells 8-14: lmfit `LorentzianModel(prefix='l1_') + LorentzianModel(prefix='l2_')`, six parameters,
+ * Levenberg-Marquardt) and whose two centers are the lower and upper polariton (cell 17).  lmfit's line shape:
+ *   f(x; amplitude, center, sigma) = (amplitude / pi) sigma / ((x - center)^2 + sigma^2).
+ * y, n_outer, n_pts, n_inner, reverse, axis as in pst_find_peaks; seed[s][6] = the rows pst_polariton_branches wrote
+ * (centers, half widths, peak heights of the two highest peaks; a NaN / non-positive half width is replaced by sigma0);
+ * the fit uses samples [i_lo, i_hi) of the scan order (the notebook's wavenumber mask).  Levenberg-Marquardt with
+ * Marquardt scaling, at most max_iter evaluations of the misfit, one pass over the window per evaluation.
+ * out[s][8] = (center_lower, center_upper, sigma_lower, sigma_upper, amplitude_lower, amplitude_upper, chi^2, evaluations;
+ * negative evaluations = tolerance not met within max_iter).  NaN rows for spectra whose seed is NaN (fewer than two
+ * peaks).  Pinned against scipy.optimize.curve_fit (MINPACK Levenberg-Marquardt, what lmfit calls) in tests/test_peaks.py. */
+int pst_fit_two_lorentzians(pst_handle_t h, const double* y /*[dev]*/, int n_outer, int n_pts, int n_inner, int reverse,
+                            const double* axis /*[dev] n_pts*/, const double* seed /*[dev] n_outer*n_inner*6*/, int i_lo,
+                            int i_hi, double sigma0, int max_iter, double* out /*[dev] n_outer*n_inner*8*/, void* stream);
+
 /* ---- measurement helpers ------------------------------------------------------------------------------ */
 /* Independent-DFMA micro-benchmark: the measured FP64 (non-tensor) peak used as the roofline denominator.
  * Runs `iters` dependent FMAs on 8 independent chains per thread over a full-chip grid, returns TFLOP/s. */

@@ -101,3 +101,37 @@ def polariton_branches(x, y, height=None, distance=None):
     a, b = lorentzian_three_point(x, y, peaks[j1]), lorentzian_three_point(x, y, peaks[j2])
     lo, hi = (a, b) if a[0] <= b[0] else (b, a)
     return lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]
+
+
+# --------------------------------------------------------------------------- joint two-Lorentzian fit
+def lorentzian(x, amplitude, center, sigma):
+    """lmfit's LorentzianModel line shape (lmfit.lineshapes.lorentzian; lmfit is what the reference's notebook imports,
+    "Polariton Peak Analysis" cell 2, and is not part of the reference repository)."""
+    return (amplitude / np.pi) * sigma / ((x - center) ** 2 + sigma ** 2)
+
+
+def two_lorentzians(x, a1, c1, s1, a2, c2, s2):
+    return lorentzian(x, a1, c1, s1) + lorentzian(x, a2, c2, s2)
+
+
+def fit_two_lorentzians(x, y, seed, sigma0=None):
+    """The notebook's fit (cells 8-14): `LorentzianModel(prefix='l1_') + LorentzianModel(prefix='l2_')` least-squares
+    fitted to one spectrum -- here with scipy.optimize.curve_fit (MINPACK's Levenberg-Marquardt, the minimiser lmfit
+    calls by default), tolerances at machine level so that the minimum itself is the oracle.  `seed` = (center_lower,
+    center_upper, hwhm_lower, hwhm_upper, height_lower, height_upper), the row pst_polariton_branches produces.
+    Returns (center_lower, center_upper, sigma_lower, sigma_upper, amplitude_lower, amplitude_upper, chi2)."""
+    from scipy import optimize
+
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    c1, c2, g1, g2, h1, h2 = (float(v) for v in seed)
+    if sigma0 is not None:
+        g1 = g1 if g1 > 0 else sigma0
+        g2 = g2 if g2 > 0 else sigma0
+    p0 = [np.pi * g1 * h1, c1, g1, np.pi * g2 * h2, c2, g2]
+    p, _ = optimize.curve_fit(two_lorentzians, x, y, p0=p0, method="lm", ftol=1e-15, xtol=1e-15, gtol=1e-15, maxfev=20000)
+    p = [float(v) for v in p]
+    p[2], p[5] = abs(p[2]), abs(p[5])  # the model is even in sigma up to the sign of the amplitude
+    lo, hi = (p[:3], p[3:]) if p[1] <= p[4] else (p[3:], p[:3])
+    chi2 = float(np.sum((y - two_lorentzians(x, *p)) ** 2))
+    return lo[1], hi[1], lo[2], hi[2], abs(lo[0]), abs(hi[0]), chi2

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libpistachio_b200.so")
 SOURCES = [os.path.join(CSRC, "pst_api.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("pst_kernels.cuh", "pst_chain.cuh", "pst_math.cuh", "pst_bulk.cuh", "pst_f32.cuh")] + [
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("pst_kernels.cuh", "pst_chain.cuh", "pst_math.cuh", "pst_bulk.cuh", "pst_f32.cuh", "pst_fit.cuh")] + [
     os.path.join(ROOT, "include", "pistachio_b200.h")
 ]
 NVCC_FLAGS = [

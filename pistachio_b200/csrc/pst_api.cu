@@ -1067,6 +1067,24 @@ extern "C" int pst_polariton_branches(pst_handle_t h, const double* y, int n_out
   return PST_OK;
 }
 
+extern "C" int pst_fit_two_lorentzians(pst_handle_t h, const double* y, int n_outer, int n_pts, int n_inner, int reverse,
+                                       const double* axis, const double* seed, int i_lo, int i_hi, double sigma0, int max_iter,
+                                       double* out, void* stream) {
+  if (!h) return fail(PST_E_INVALID, "pst_fit_two_lorentzians: NULL handle");
+  if (!y || !axis || !seed || !out || n_outer <= 0 || n_pts < 6 || n_inner <= 0)
+    return fail(PST_E_INVALID, "pst_fit_two_lorentzians: bad argument");
+  if (i_lo < 0 || i_hi > n_pts || i_hi - i_lo < 6)
+    return fail(PST_E_INVALID, "pst_fit_two_lorentzians: the window [i_lo, i_hi) needs at least 6 samples inside the spectrum");
+  if (max_iter < 2 || !(sigma0 > 0.0)) return fail(PST_E_INVALID, "pst_fit_two_lorentzians: max_iter >= 2 and sigma0 > 0");
+  DeviceGuard g(h->device);
+  const long long n_spec = (long long)n_outer * n_inner;
+  fit_two_lorentzians_kernel<<<(unsigned)((n_spec + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      y, n_outer, n_pts, n_inner, reverse, axis, seed, i_lo, i_hi, sigma0, max_iter, out);
+  PST_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PST_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ measurement
 extern "C" int pst_fp64_peak_probe(pst_handle_t h, int iters, double* tflops_out, void* stream) {
   if (!h || !tflops_out || iters <= 0) return fail(PST_E_INVALID, "pst_fp64_peak_probe: bad argument");

@@ -22,6 +22,7 @@
 
 #include "pst_bulk.cuh"
 #include "pst_chain.cuh"
+#include "pst_fit.cuh"
 
 namespace pst {
 
@@ -1737,6 +1738,33 @@ __global__ void polariton_branches_kernel(const double* __restrict__ y, int n_ou
   o[0] = res[lo][0]; o[1] = res[hi][0];
   o[2] = res[lo][1]; o[3] = res[hi][1];
   o[4] = res[lo][2]; o[5] = res[hi][2];
+}
+
+// Joint two-Lorentzian fit per spectrum (pst_fit.cuh; the reference's "Polariton Peak Analysis" notebook, cells 8-17): one
+// thread per spectrum, lanes on adjacent `inner` (theta) so that every pass over the window is coalesced loads; seeds are
+// the rows pst_polariton_branches wrote.  The window [i_lo, i_hi) counts samples in scan order (`reverse` as in
+// find_peaks_kernel).  out[s][8] = (center_lower, center_upper, sigma_lower, sigma_upper, amplitude_lower,
+// amplitude_upper, chi^2, evaluations) in lmfit's LorentzianModel convention.
+__global__ void __launch_bounds__(128)
+fit_two_lorentzians_kernel(const double* __restrict__ y, int n_outer, int n_pts, int n_inner, int reverse,
+                           const double* __restrict__ axis, const double* __restrict__ seed, int i_lo, int i_hi, double sigma0,
+                           int max_iter, double* __restrict__ out) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= (long long)n_outer * n_inner) return;
+  const int outer = (int)(s / n_inner), inner = (int)(s - (long long)outer * n_inner);
+  const int m0 = reverse ? n_pts - 1 - i_lo : i_lo;  // memory index of the window's first sample
+  FitProblem pb;
+  pb.y = y + ((size_t)outer * n_pts + m0) * n_inner + inner;
+  pb.y_stride = reverse ? -(long long)n_inner : (long long)n_inner;
+  pb.x = axis + m0;
+  pb.x_stride = reverse ? -1 : 1;
+  pb.n = i_hi - i_lo;
+  double sd[6], res[8];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) sd[k] = seed[s * 6 + k];
+  fit_two_lorentzians(pb, sd, sigma0, max_iter, res);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) out[s * 8 + k] = res[k];
 }
 
 // ------------------------------------------------------------------------------ measurement helpers

@@ -437,6 +437,29 @@ class TMMEngine:
               "pst_polariton_branches")
         return out
 
+    def fit_two_lorentzians(self, y, seeds, axis, reverse=False, window=None, sigma0=None, max_iter=200):
+        """Joint two-Lorentzian least-squares fit of every spectrum of y[..., n_wl, n_theta] (pst_fit_two_lorentzians),
+        seeded by the rows `polariton_branches` returned for the same `y`, `axis` and `reverse`.  `window` = (i_lo, i_hi)
+        in samples of the scan order (default: the whole spectrum).  Returns a device tensor [..., n_theta, 8] =
+        (center_lower, center_upper, sigma_lower, sigma_upper, amplitude_lower, amplitude_upper, chi2, evaluations) in
+        lmfit's LorentzianModel convention (amplitude = area, sigma = half width at half maximum)."""
+        y = y.contiguous()
+        n_pts, n_inner = y.shape[-2], y.shape[-1]
+        lead = tuple(y.shape[:-2])
+        n_outer = int(np.prod(lead)) if lead else 1
+        ax_d = _dev_f64(axis, self.device)
+        if ax_d.numel() != n_pts:
+            raise ValueError("axis must have one value per wavelength")
+        i_lo, i_hi = (0, n_pts) if window is None else (int(window[0]), int(window[1]))
+        if sigma0 is None:
+            sigma0 = 4.0 * float((ax_d.max() - ax_d.min()).item()) / max(n_pts - 1, 1)
+        seeds = seeds.contiguous()
+        out = torch.empty(lead + (n_inner, 8), dtype=torch.float64, device=self.device)
+        check(self.lib.pst_fit_two_lorentzians(self.handle.raw, _ptr(y), n_outer, n_pts, n_inner, 1 if reverse else 0, _ptr(ax_d),
+                                               _ptr(seeds), i_lo, i_hi, float(sigma0), int(max_iter), _ptr(out), self._stream()),
+              "pst_fit_two_lorentzians")
+        return out
+
     # ------------------------------------------------------------------ measurement
     def fp64_peak_tflops(self, iters: int = 4096) -> float:
         out = C.c_double(0.0)

@@ -412,15 +412,22 @@ class Structure:
         return out
 
     def polariton_dispersion(self, theta=None, pol=S_WAVE, height=None, distance=None, sweep_layer=-1, sweep_d=None,
-                             max_peaks=64):
+                             max_peaks=64, fit="joint", window=None, max_iter=200):
         """Additive API: the dispersion step of the reference's "Polariton Peak Analysis"
         notebook (cells 8-17: a two-Lorentzian fit per angle whose centres are the lower and upper polariton) fused
         behind the spectrum.  Transmittance spectra are evaluated on the device for every angle (and swept thickness),
         the two highest peaks on the wavenumber axis nu = 1e4/lambda[um] are located (find_peaks semantics, `height`
-        as a fraction, `distance` in samples) and refined by the closed-form three-point Lorentzian, and only
-        (LP, UP, widths, amplitudes) per spectrum leave the GPU.  Returns a dict of arrays shaped (n_theta,) or
-        (n_sweep, n_theta): `theta`, `LP`, `UP`, `splitting` = UP - LP, `hwhm_LP`, `hwhm_UP`, `amp_LP`, `amp_UP`, and
-        `min_splitting` (the Rabi-splitting estimate: the smallest UP - LP over the angles) with its `theta_at_min`."""
+        as a fraction, `distance` in samples), estimated by the closed-form three-point Lorentzian and -- fit="joint",
+        the default -- refined by the notebook's own fit: the sum of two lmfit-style Lorentzians least-squares fitted
+        to the spectrum over `window` = (nu_lo, nu_hi) in cm^-1 (default: the whole grid; the notebook masks 500..8000),
+        Levenberg-Marquardt on the device (pst_fit_two_lorentzians).  fit="three-point" keeps the closed-form estimates.
+        Only (LP, UP, widths, amplitudes) per spectrum leave the GPU.  Returns a dict of arrays shaped (n_theta,) or
+        (n_sweep, n_theta): `theta`, `LP`, `UP`, `splitting` = UP - LP, `hwhm_LP`, `hwhm_UP`, `amp_LP`, `amp_UP`
+        (peak heights for "three-point", lmfit amplitudes = areas for "joint", which also returns `chi2` and
+        `evaluations`), and `min_splitting` (the Rabi-splitting estimate: the smallest UP - LP over the angles) with its
+        `theta_at_min`."""
+        if fit not in ("joint", "three-point"):
+            raise ValueError("fit must be 'joint' or 'three-point'")
         theta = np.atleast_1d(np.asarray(self.theta if theta is None else theta, dtype=np.float64))
         wl, mat_n, mat_k, layer_mat, layer_d = self._stack_on_grid()
         eng = _eng()
@@ -430,11 +437,21 @@ class Structure:
         rev = bool(wl.size > 1 and wl[0] < wl[-1])
         T = res.T[:, 0]
         idx, hts, cnt, _ = eng.find_peaks(T, height=height, distance=distance, max_peaks=max_peaks, axis=nu, reverse=rev)
-        br = _to_numpy(eng.polariton_branches(T, idx, hts, cnt, nu, reverse=rev))
         if (_to_numpy(cnt) < 0).any():
             raise ValueError("more peaks than max_peaks in at least one spectrum")
+        seeds = eng.polariton_branches(T, idx, hts, cnt, nu, reverse=rev)
+        br = _to_numpy(seeds)
+        extra = {}
+        if fit == "joint":
+            win = None
+            if window is not None:  # wavenumber bounds -> sample window of the scan order (ascending wavenumber)
+                order = nu[::-1] if rev else nu
+                lo, hi = np.searchsorted(order, [float(window[0]), float(window[1])], side="left")
+                win = (int(lo), int(max(hi, lo + 6)))
+            br = _to_numpy(eng.fit_two_lorentzians(T, seeds, nu, reverse=rev, window=win, max_iter=max_iter))
+            extra = {"chi2": br[..., 6], "evaluations": br[..., 7]}
         out = {"theta": theta, "LP": br[..., 0], "UP": br[..., 1], "splitting": br[..., 1] - br[..., 0],
-               "hwhm_LP": br[..., 2], "hwhm_UP": br[..., 3], "amp_LP": br[..., 4], "amp_UP": br[..., 5]}
+               "hwhm_LP": br[..., 2], "hwhm_UP": br[..., 3], "amp_LP": br[..., 4], "amp_UP": br[..., 5], **extra}
         with np.errstate(invalid="ignore"):
             spl = np.where(np.isnan(out["splitting"]), np.inf, out["splitting"])
         k = spl.argmin(axis=-1)

@@ -5,6 +5,7 @@
 // libpistachio_b200.so and never reachable from the pistachio_b200 package.
 #include <vector>
 #include "../../pistachio_b200/csrc/pst_chain.cuh"
+#include "../../pistachio_b200/csrc/pst_fit.cuh"
 
 using namespace pst;
 
@@ -163,4 +164,12 @@ extern "C" void emul_sincos(int n, const double* x, double* s, double* c) {
 }
 extern "C" void emul_cosh_sinh(int n, const double* y, double* ch, double* sh, int* sc) {
   for (int i = 0; i < n; ++i) sc[i] = cosh_sinh_scaled(y[i], ch[i], sh[i]);
+}
+
+// ---- joint two-Lorentzian fit (pst_fit.cuh) on one contiguous spectrum, for the comparison with scipy's curve_fit
+extern "C" void emul_fit_two_lorentzians(int n, const double* x, const double* y, const double* seed, double sigma0, int max_iter,
+                                         double* out) {
+  FitProblem pb;
+  pb.y = y; pb.y_stride = 1; pb.x = x; pb.x_stride = 1; pb.n = n;
+  fit_two_lorentzians(pb, seed, sigma0, max_iter, out);
 }

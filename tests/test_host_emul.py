@@ -14,20 +14,28 @@ from tests import parity
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "host_emul", "emul.cu")
 OUT = os.path.join(HERE, "host_emul", "_build", "libemul.so")
-DEPS = [SRC] + [os.path.join(HERE, "..", "pistachio_b200", "csrc", f) for f in ("pst_chain.cuh", "pst_math.cuh")]
+DEPS = [SRC] + [os.path.join(HERE, "..", "pistachio_b200", "csrc", f) for f in ("pst_chain.cuh", "pst_math.cuh", "pst_fit.cuh")]
 
 
-@pytest.fixture(scope="module")
-def emul():
+def load_emul():
+    """Build (when stale) and load tests/host_emul/_build/libemul.so; None without nvcc."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
-        pytest.skip("nvcc not available")
+        return None
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC],
                        check=True)
     lib = C.CDLL(OUT)
     lib.emul_eval_grid.restype = C.c_int
+    return lib
+
+
+@pytest.fixture(scope="module")
+def emul():
+    lib = load_emul()
+    if lib is None:
+        pytest.skip("nvcc not available")
     return lib
 
 
