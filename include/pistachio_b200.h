@@ -66,10 +66,21 @@ extern "C" {
                                                  GPU of the mapping -- a sharded sweep is assembled on all devices
                                                  without an all-gather.  The caller synchronises the devices afterwards.
                                                  Not valid with M or with pst_eval_grid_host */
-#define PST_FLAG_FP32 (1u << 9)                /* optional fp32 mode (<= 1e-5): phase and its range reduction stay in fp64,
+#define PST_FLAG_FP32 (1u << 9)                /* optional fp32 mode: phase and its range reduction stay in fp64,
                                                  polynomials, layer matrices and the chain run in fp32 with the two
                                                  polarisations packed in f32x2 registers; inputs/outputs stay fp64.
-                                                 Point kernel without layer CSE; not valid with M */
+                                                 Accuracy: |dR|, |dT| <= 1e-5 OF FULL SCALE (R, T in [0, 1]), i.e. 1e-5
+                                                 relative only for values of order one; measured 3e-7 on few-layer
+                                                 stacks, 9e-6 on a 2 x 20-pair DBR cavity (its finesse amplifies fp32
+                                                 rounding).  Identical layers repeat their rounding error, so the error
+                                                 of a periodic stack grows linearly with its depth: measured 1.1e-7 of
+                                                 full scale per layer on low-contrast quarter-wave stacks (2.9e-5 at 256
+                                                 layers, 2.7e-4 at 10 000).  Stacks of more than PST_FP32_MAX_LAYERS
+                                                 interior layers -- where that growth reaches 1e-5 -- are refused with
+                                                 PST_E_INVALID.  Point kernel without layer CSE; not valid with M */
+#ifndef PST_FP32_MAX_LAYERS
+#define PST_FP32_MAX_LAYERS 88
+#endif
 #define PST_FLAG_POL_DEGENERATE (1u << 10)     /* opt-in: compute the s-wave chain only and write it to both polarisation
                                                  planes.  In the reference's model (same theta in every layer, tm.py:209,
                                                  212,270) the p-wave matrices are a similarity transform of the s-wave
@@ -232,9 +243,10 @@ int pst_field_amplitudes(pst_handle_t h, const pst_grid_args* a, double* amp /*[
  * reverse != 0 scans each spectrum from its last sample to its first (ascending wavenumber on an ascending
  * wavelength grid); indices then count from the end.  Outputs per spectrum s = outer * n_inner + inner:
  *   out_idx[s][max_peaks] (first out_count[s] entries valid), out_height[s][max_peaks] (may be NULL),
- *   out_count[s] (-1: more than max_peaks / 128 candidates), out_spacing[s] = mean difference of axis[] between
- *   consecutive peaks (NaN below two peaks; may be NULL; axis may be NULL) -- the notebook's `diff().mean()` from which
- *   the cavity length L = 1e4 / (2 n_eff spacing) follows (cells 5-6). */
+ *   out_count[s] (-1: more than max_peaks peaks -- candidates the distance condition removes do not count, however
+ *   many), out_spacing[s] = mean difference of axis[] between consecutive peaks (NaN below two peaks; may be NULL; axis
+ *   may be NULL) -- the notebook's `diff().mean()` from which the cavity length L = 1e4 / (2 n_eff spacing) follows
+ *   (cells 5-6). */
 int pst_find_peaks(pst_handle_t h, const double* y /*[dev]*/, int n_outer, int n_pts, int n_inner, double height,
                    int use_height, int distance, int max_peaks, int reverse, const double* axis /*[dev] n_pts or NULL*/,
                    int* out_idx /*[dev]*/, double* out_height /*[dev] or NULL*/, int* out_count /*[dev]*/,
@@ -259,13 +271,17 @@ int pst_polariton_branches(pst_handle_t h, const double* y /*[dev]*/, int n_oute
  * y, n_outer, n_pts, n_inner, reverse, axis as in pst_find_peaks; seed[s][6] = the rows pst_polariton_branches wrote
  * (centers, half widths, peak heights of the two highest peaks; a NaN / non-positive half width is replaced by sigma0);
  * the fit uses samples [i_lo, i_hi) of the scan order (the notebook's wavenumber mask).  Levenberg-Marquardt with
- * Marquardt scaling, at most max_iter evaluations of the misfit, one pass over the window per evaluation.
+ * Marquardt scaling, at most max_iter evaluations of the misfit, one pass over the window per evaluation; it stops at an
+ * accepted step that lowers chi^2 by <= tol chi^2 or moves no parameter by more than tol of its size (MINPACK's ftol /
+ * xtol; lmfit's default is 1.5e-8; clamped to >= 1e-15).  Steps that would take a centre more than one window span
+ * outside the window, or a width beyond four spans, are refused.
  * out[s][8] = (center_lower, center_upper, sigma_lower, sigma_upper, amplitude_lower, amplitude_upper, chi^2, evaluations;
  * negative evaluations = tolerance not met within max_iter).  NaN rows for spectra whose seed is NaN (fewer than two
  * peaks).  Pinned against scipy.optimize.curve_fit (MINPACK Levenberg-Marquardt, what lmfit calls) in tests/test_peaks.py. */
 int pst_fit_two_lorentzians(pst_handle_t h, const double* y /*[dev]*/, int n_outer, int n_pts, int n_inner, int reverse,
                             const double* axis /*[dev] n_pts*/, const double* seed /*[dev] n_outer*n_inner*6*/, int i_lo,
-                            int i_hi, double sigma0, int max_iter, double* out /*[dev] n_outer*n_inner*8*/, void* stream);
+                            int i_hi, double sigma0, double tol, int max_iter, double* out /*[dev] n_outer*n_inner*8*/,
+                            void* stream);
 
 /* ---- measurement helpers ------------------------------------------------------------------------------ */
 /* Independent-DFMA micro-benchmark: the measured FP64 (non-tensor) peak used as the roofline denominator.

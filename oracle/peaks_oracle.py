@@ -114,10 +114,11 @@ def two_lorentzians(x, a1, c1, s1, a2, c2, s2):
     return lorentzian(x, a1, c1, s1) + lorentzian(x, a2, c2, s2)
 
 
-def fit_two_lorentzians(x, y, seed, sigma0=None):
+def fit_two_lorentzians(x, y, seed, sigma0=None, tol=1e-15):
     """The notebook's fit (cells 8-14): `LorentzianModel(prefix='l1_') + LorentzianModel(prefix='l2_')` least-squares
     fitted to one spectrum -- here with scipy.optimize.curve_fit (MINPACK's Levenberg-Marquardt, the minimiser lmfit
-    calls by default), tolerances at machine level so that the minimum itself is the oracle.  `seed` = (center_lower,
+    calls by default), tolerances at machine level by default so that the minimum itself is the oracle (tol = 1.5e-8 is
+    lmfit's default ftol = xtol).  `seed` = (center_lower,
     center_upper, hwhm_lower, hwhm_upper, height_lower, height_upper), the row pst_polariton_branches produces.
     Returns (center_lower, center_upper, sigma_lower, sigma_upper, amplitude_lower, amplitude_upper, chi2)."""
     from scipy import optimize
@@ -129,7 +130,7 @@ def fit_two_lorentzians(x, y, seed, sigma0=None):
         g1 = g1 if g1 > 0 else sigma0
         g2 = g2 if g2 > 0 else sigma0
     p0 = [np.pi * g1 * h1, c1, g1, np.pi * g2 * h2, c2, g2]
-    p, _ = optimize.curve_fit(two_lorentzians, x, y, p0=p0, method="lm", ftol=1e-15, xtol=1e-15, gtol=1e-15, maxfev=20000)
+    p, _ = optimize.curve_fit(two_lorentzians, x, y, p0=p0, method="lm", ftol=tol, xtol=tol, gtol=min(tol, 1e-15), maxfev=20000)
     p = [float(v) for v in p]
     p[2], p[5] = abs(p[2]), abs(p[5])  # the model is even in sigma up to the sign of the amplitude
     lo, hi = (p[:3], p[3:]) if p[1] <= p[4] else (p[3:], p[:3])

@@ -97,7 +97,7 @@ SYMBOLS = {
     "pst_polariton_branches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "pst_fit_two_lorentzians": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                           C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
+                                           C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     "pst_fp64_peak_probe": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_void_p]),
     "pst_flush_l2": (C.c_int, [C.c_void_p, C.c_void_p]),
 }

@@ -275,6 +275,9 @@ int validate_grid(const pst_grid_args* a, const char* who) {
   if ((a->flags & PST_FLAG_POL_DEGENERATE) && (a->M || a->pol_mask != (PST_POL_S | PST_POL_P)))
     return fail(PST_E_INVALID, w + ": PST_FLAG_POL_DEGENERATE needs pol_mask = S | P and no matrix output");
   if ((a->flags & PST_FLAG_FP32) && a->M) return fail(PST_E_INVALID, w + ": PST_FLAG_FP32 does not cover the matrix output M");
+  if ((a->flags & PST_FLAG_FP32) && a->n_layers - 2 > PST_FP32_MAX_LAYERS)
+    return fail(PST_E_INVALID, w + ": PST_FLAG_FP32 is limited to PST_FP32_MAX_LAYERS interior layers (its error grows with the "
+                                   "layer count and would pass 1e-5 of full scale); use the fp64 default");
   if ((a->flags & PST_FLAG_SNELL) && (a->flags & (PST_FLAG_FP32 | PST_FLAG_POL_DEGENERATE | PST_FLAG_FORCE_DEEP_KERNEL)))
     return fail(PST_E_INVALID, w + ": PST_FLAG_SNELL excludes the fp32, polarisation-degenerate and deep-kernel flags");
   if ((a->flags & PST_FLAG_NUMERIC_DET) && !a->M) return fail(PST_E_INVALID, w + ": PST_FLAG_NUMERIC_DET needs the matrix output M");
@@ -1068,18 +1071,19 @@ extern "C" int pst_polariton_branches(pst_handle_t h, const double* y, int n_out
 }
 
 extern "C" int pst_fit_two_lorentzians(pst_handle_t h, const double* y, int n_outer, int n_pts, int n_inner, int reverse,
-                                       const double* axis, const double* seed, int i_lo, int i_hi, double sigma0, int max_iter,
-                                       double* out, void* stream) {
+                                       const double* axis, const double* seed, int i_lo, int i_hi, double sigma0, double tol,
+                                       int max_iter, double* out, void* stream) {
   if (!h) return fail(PST_E_INVALID, "pst_fit_two_lorentzians: NULL handle");
   if (!y || !axis || !seed || !out || n_outer <= 0 || n_pts < 6 || n_inner <= 0)
     return fail(PST_E_INVALID, "pst_fit_two_lorentzians: bad argument");
   if (i_lo < 0 || i_hi > n_pts || i_hi - i_lo < 6)
     return fail(PST_E_INVALID, "pst_fit_two_lorentzians: the window [i_lo, i_hi) needs at least 6 samples inside the spectrum");
-  if (max_iter < 2 || !(sigma0 > 0.0)) return fail(PST_E_INVALID, "pst_fit_two_lorentzians: max_iter >= 2 and sigma0 > 0");
+  if (max_iter < 2 || !(sigma0 > 0.0) || !(tol >= 0.0))
+    return fail(PST_E_INVALID, "pst_fit_two_lorentzians: max_iter >= 2, sigma0 > 0 and tol >= 0");
   DeviceGuard g(h->device);
   const long long n_spec = (long long)n_outer * n_inner;
   fit_two_lorentzians_kernel<<<(unsigned)((n_spec + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      y, n_outer, n_pts, n_inner, reverse, axis, seed, i_lo, i_hi, sigma0, max_iter, out);
+      y, n_outer, n_pts, n_inner, reverse, axis, seed, i_lo, i_hi, sigma0, tol, max_iter, out);
   PST_CUDA(cudaGetLastError());
   h->launches += 1;
   return PST_OK;

@@ -121,7 +121,13 @@ PST_HD bool fit_solve(const double (&N)[kFitTri], const double (&g)[kFitParams],
 // with X = peak height in the seed and X = lmfit's amplitude (area, pi sigma height) in the result; out[6] = chi^2,
 // out[7] = evaluations used (negative: stopped at max_iter without meeting the tolerance).  A seed width that is NaN or
 // not positive (the three-point estimate gives up on flat tops) is replaced by sigma0; other NaN seeds give NaN results.
-PST_HD void fit_two_lorentzians(const FitProblem& pb, const double* seed, double sigma0, int max_iter, double* out) {
+// Stopping rule (MINPACK's ftol / xtol, which lmfit sets to 1.5e-8): an accepted step that lowers chi^2 by no more than
+// tol chi^2, or moves no parameter by more than tol of its size; tol is clamped to >= 1e-15.  On spectra that ARE two
+// Lorentzians the misfit vanishes and convergence is quadratic, so a tight tol costs a few evaluations; on measured-like
+// spectra (model misfit) Levenberg-Marquardt converges linearly along flat valleys and the reference's own result is only
+// defined to lmfit's tolerance.  Steps that would carry a centre more than one window span outside the window, or a width
+// beyond four spans, are refused like uphill steps (the unbounded fit can otherwise run away on a window holding one line).
+PST_HD void fit_two_lorentzians(const FitProblem& pb, const double* seed, double sigma0, double tol, int max_iter, double* out) {
   const double nan = from_words(0x7ff80000, 0);
   double p[kFitParams] = {seed[4], seed[0], seed[2], seed[5], seed[1], seed[3]};
   if (!(p[2] > 0.0)) p[2] = sigma0;
@@ -134,6 +140,9 @@ PST_HD void fit_two_lorentzians(const FitProblem& pb, const double* seed, double
     for (int k = 0; k < 8; ++k) out[k] = nan;
     return;
   }
+  tol = fmax(tol, 1.0e-15);
+  const double xa = fit_ld(pb.x), xb = fit_ld(pb.x + (long long)(pb.n - 1) * pb.x_stride);
+  const double span = fabs(xb - xa), c_lo = fmin(xa, xb) - span, c_hi = fmax(xa, xb) + span, s_hi = 4.0 * span;
   double N[kFitTri], g[kFitParams], delta[kFitParams], trial[kFitParams], dummyN[kFitTri], dummyg[kFitParams];
   double chi2 = fit_eval<true>(pb, p, N, g);
   double lambda = 1.0e-3;
@@ -147,7 +156,10 @@ PST_HD void fit_two_lorentzians(const FitProblem& pb, const double* seed, double
     }
 #pragma unroll
     for (int k = 0; k < kFitParams; ++k) trial[k] = p[k] + delta[k];
-    if (!(trial[2] > 0.0) || !(trial[5] > 0.0)) {  // a width crossing zero: shorten the step
+    // the model is even in sigma (height parameterisation), so a width may cross zero freely -- as it may in the
+    // unbounded lmfit model, where (amplitude, sigma) -> (-amplitude, -sigma) is a symmetry; |sigma| is reported
+    if (!(fabs(trial[2]) <= s_hi && fabs(trial[5]) <= s_hi && trial[1] >= c_lo && trial[1] <= c_hi && trial[4] >= c_lo &&
+          trial[4] <= c_hi)) {  // a line leaving the window (or a NaN): shorten the step
       lambda *= 10.0;
       if (lambda > 1.0e12) break;
       continue;
@@ -166,8 +178,8 @@ PST_HD void fit_two_lorentzians(const FitProblem& pb, const double* seed, double
       chi2 = fit_eval<true>(pb, p, N, g);
       ++evals;
       lambda = fmax(lambda * 0.1, 1.0e-12);
-      // stop when neither the parameters (relative 1e-13) nor the misfit (relative 1e-15) still move
-      if (step < 1.0e-13 || gain <= 1.0e-15 * chi2) {
+      // stop when neither the parameters nor the misfit still move by more than tol (relative)
+      if (step <= tol || gain <= tol * chi2) {
         converged = true;
         break;
       }
@@ -183,10 +195,10 @@ PST_HD void fit_two_lorentzians(const FitProblem& pb, const double* seed, double
   const double kPi = 3.141592653589793;
   out[0] = p[lo + 1];
   out[1] = p[hi + 1];
-  out[2] = p[lo + 2];
-  out[3] = p[hi + 2];
-  out[4] = kPi * p[lo + 2] * p[lo];  // lmfit amplitude = area
-  out[5] = kPi * p[hi + 2] * p[hi];
+  out[2] = fabs(p[lo + 2]);
+  out[3] = fabs(p[hi + 2]);
+  out[4] = kPi * fabs(p[lo + 2]) * p[lo];  // lmfit amplitude = area
+  out[5] = kPi * fabs(p[hi + 2]) * p[hi];
   out[6] = chi2;
   out[7] = converged ? (double)evals : -(double)evals;
 }

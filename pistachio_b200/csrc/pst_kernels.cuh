@@ -46,6 +46,9 @@ constexpr int kRenormEvery = 16;
 #define PST_K2_UNROLL 2
 #endif
 constexpr int kK2Group = PST_K2_GROUP, kK2Unroll = PST_K2_UNROLL;
+#ifndef PST_K1_MAXREG
+#define PST_K1_MAXREG 80
+#endif
 constexpr int kMaxOps = 24;         // run-length ops the typed kernel takes by value (longer programs use K1 untyped)
 
 struct GridParams {
@@ -298,7 +301,7 @@ prep_kernel(const double* __restrict__ wl, const double* __restrict__ mat_n, con
 //   SEG    blockDim.y ordered layer segments per point, combined in order through shared memory (deep stacks)
 template <int NPOL, int NCOL, bool STAGE_OPT, bool STAGE_LAYERS, bool SEG>
 __global__ void __launch_bounds__(SEG ? 512 : 256)
-__maxnreg__(SEG ? (NPOL == 1 ? 72 : 128) : 255)  // deep-stack kernel, one polarisation: 72 registers = 28 warps per SM, what
+__maxnreg__(SEG ? (NPOL == 1 ? 72 : 128) : (NCOL == 1 ? PST_K1_MAXREG : 255))  // deep-stack kernel, one polarisation: 72 registers = 28 warps per SM, what
 tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384 points x 8 segments) needs to be resident at once
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NC = SEG ? 2 : NCOL;  // a segment product needs both columns
@@ -1617,8 +1620,9 @@ __global__ void find_peaks_kernel(const double* __restrict__ y, int n_outer, int
   // ---- local maxima with plateau midpoints, height filter.  One-sample-at-a-time state machine (a rise opens a
   // candidate plateau, a strict descent closes it as a peak at the plateau's midpoint; plateaus touching either end
   // never close, as in scipy's _local_maxima_1d), fed from batches of independent loads so that the scan is
-  // bandwidth- rather than latency-bound.
-  if (n_pts >= 3) {
+  // bandwidth- rather than latency-bound.  emit(index, height) is called per peak that passes the height filter.
+  auto scan = [&](auto&& emit) {
+    if (n_pts < 3) return;
     constexpr int kBatch = 16;
     double prev = at(0);
     bool rising = false;
@@ -1629,10 +1633,7 @@ __global__ void find_peaks_kernel(const double* __restrict__ y, int n_outer, int
     //   x < prev (or NaN)   closes it; a descent from an open plateau is a peak at the plateau's midpoint
     auto feed = [&](int i, double x) {
       const bool gt = x > prev, lt = x < prev, ne = x != prev;
-      if (lt && rising && (!use_height || prev >= height)) {
-        if (n < kPeakCap && n < max_peaks) { idx[n] = (start + i - 1) / 2; hh[n] = prev; keep[n] = 1; ++n; }
-        else overflow = true;
-      }
+      if (lt && rising && (!use_height || prev >= height)) emit((start + i - 1) / 2, prev);
       rising = gt || (rising && !ne);
       start = gt ? i : start;
       prev = x;
@@ -1646,9 +1647,41 @@ __global__ void find_peaks_kernel(const double* __restrict__ y, int n_outer, int
       for (int k = 0; k < kBatch; ++k) feed(i0 + k, buf[k]);
     }
     for (; i0 < n_pts; ++i0) feed(i0, at(i0));
-  }
-  // ---- distance condition: from the highest peak down, a kept peak removes neighbours closer than `distance`
-  if (distance > 1 && n > 1) {
+  };
+  // max_peaks bounds the peaks REPORTED; the candidates a distance condition thins out may be more (up to kPeakCap here)
+  const int cand_cap = distance > 1 ? kPeakCap : max_peaks;
+  scan([&](int i, double h) {
+    if (n < cand_cap) { idx[n] = i; hh[n] = h; keep[n] = 1; ++n; }
+    else overflow = true;
+  });
+  if (overflow && distance > 1) {
+    // More candidates than the buffer holds (a rippled spectrum) and a distance condition that may leave only a few:
+    // exact selection without a candidate list.  scipy visits candidates from the highest down (ties: the later one
+    // first, as below) and a visited candidate that is still alive removes its neighbours closer than `distance`; so
+    // the kept set is built by repeatedly taking the highest candidate not within `distance` of one already kept --
+    // one re-scan of the spectrum (L2-resident) per kept peak.  Cold path: only the overflowing threads run it.
+    n = 0;
+    overflow = false;
+    for (;;) {
+      int bi = -1;
+      double bh = 0.0;
+      scan([&](int i, double h) {
+        if (bi >= 0 && h < bh) return;
+        for (int k = 0; k < n; ++k)
+          if (abs(idx[k] - i) < distance) return;  // removed by (or is) a kept peak
+        bi = i;
+        bh = h;
+      });
+      if (bi < 0) break;
+      if (n == max_peaks) { overflow = true; break; }
+      int k = n++;  // kept peaks stay sorted by position
+      for (; k > 0 && idx[k - 1] > bi; --k) { idx[k] = idx[k - 1]; hh[k] = hh[k - 1]; }
+      idx[k] = bi;
+      hh[k] = bh;
+    }
+    for (int k = 0; k < n; ++k) keep[k] = 1;
+  } else if (distance > 1 && n > 1) {
+    // ---- distance condition: from the highest peak down, a kept peak removes neighbours closer than `distance`
     unsigned char done[kPeakCap];
     for (int k = 0; k < n; ++k) done[k] = 0;
     for (int it = 0; it < n; ++it) {
@@ -1665,6 +1698,7 @@ __global__ void find_peaks_kernel(const double* __restrict__ y, int n_outer, int
   int m = 0, first = -1, last = -1;
   for (int k = 0; k < n; ++k)
     if (keep[k]) {
+      if (m == max_peaks) { overflow = true; break; }
       out_idx[s * max_peaks + m] = idx[k];
       if (out_height) out_height[s * max_peaks + m] = hh[k];
       if (first < 0) first = idx[k];
@@ -1748,7 +1782,7 @@ __global__ void polariton_branches_kernel(const double* __restrict__ y, int n_ou
 __global__ void __launch_bounds__(128)
 fit_two_lorentzians_kernel(const double* __restrict__ y, int n_outer, int n_pts, int n_inner, int reverse,
                            const double* __restrict__ axis, const double* __restrict__ seed, int i_lo, int i_hi, double sigma0,
-                           int max_iter, double* __restrict__ out) {
+                           double tol, int max_iter, double* __restrict__ out) {
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= (long long)n_outer * n_inner) return;
   const int outer = (int)(s / n_inner), inner = (int)(s - (long long)outer * n_inner);
@@ -1762,7 +1796,7 @@ fit_two_lorentzians_kernel(const double* __restrict__ y, int n_outer, int n_pts,
   double sd[6], res[8];
 #pragma unroll
   for (int k = 0; k < 6; ++k) sd[k] = seed[s * 6 + k];
-  fit_two_lorentzians(pb, sd, sigma0, max_iter, res);
+  fit_two_lorentzians(pb, sd, sigma0, tol, max_iter, res);
 #pragma unroll
   for (int k = 0; k < 8; ++k) out[s * 8 + k] = res[k];
 }

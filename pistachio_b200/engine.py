@@ -437,12 +437,13 @@ class TMMEngine:
               "pst_polariton_branches")
         return out
 
-    def fit_two_lorentzians(self, y, seeds, axis, reverse=False, window=None, sigma0=None, max_iter=200):
+    def fit_two_lorentzians(self, y, seeds, axis, reverse=False, window=None, sigma0=None, max_iter=200, tol=1.5e-8):
         """Joint two-Lorentzian least-squares fit of every spectrum of y[..., n_wl, n_theta] (pst_fit_two_lorentzians),
         seeded by the rows `polariton_branches` returned for the same `y`, `axis` and `reverse`.  `window` = (i_lo, i_hi)
         in samples of the scan order (default: the whole spectrum).  Returns a device tensor [..., n_theta, 8] =
         (center_lower, center_upper, sigma_lower, sigma_upper, amplitude_lower, amplitude_upper, chi2, evaluations) in
-        lmfit's LorentzianModel convention (amplitude = area, sigma = half width at half maximum)."""
+        lmfit's LorentzianModel convention (amplitude = area, sigma = half width at half maximum).  `tol`: relative
+        stopping tolerance on chi2 and on the parameters (MINPACK's ftol = xtol; 1.5e-8 is lmfit's default)."""
         y = y.contiguous()
         n_pts, n_inner = y.shape[-2], y.shape[-1]
         lead = tuple(y.shape[:-2])
@@ -456,7 +457,8 @@ class TMMEngine:
         seeds = seeds.contiguous()
         out = torch.empty(lead + (n_inner, 8), dtype=torch.float64, device=self.device)
         check(self.lib.pst_fit_two_lorentzians(self.handle.raw, _ptr(y), n_outer, n_pts, n_inner, 1 if reverse else 0, _ptr(ax_d),
-                                               _ptr(seeds), i_lo, i_hi, float(sigma0), int(max_iter), _ptr(out), self._stream()),
+                                               _ptr(seeds), i_lo, i_hi, float(sigma0), float(tol), int(max_iter), _ptr(out),
+                                               self._stream()),
               "pst_fit_two_lorentzians")
         return out
 

@@ -412,7 +412,7 @@ class Structure:
         return out
 
     def polariton_dispersion(self, theta=None, pol=S_WAVE, height=None, distance=None, sweep_layer=-1, sweep_d=None,
-                             max_peaks=64, fit="joint", window=None, max_iter=200):
+                             max_peaks=64, fit="joint", window=None, max_iter=400, tol=1.5e-8):
         """Additive API: the dispersion step of the reference's "Polariton Peak Analysis"
         notebook (cells 8-17: a two-Lorentzian fit per angle whose centres are the lower and upper polariton) fused
         behind the spectrum.  Transmittance spectra are evaluated on the device for every angle (and swept thickness),
@@ -420,7 +420,9 @@ class Structure:
         as a fraction, `distance` in samples), estimated by the closed-form three-point Lorentzian and -- fit="joint",
         the default -- refined by the notebook's own fit: the sum of two lmfit-style Lorentzians least-squares fitted
         to the spectrum over `window` = (nu_lo, nu_hi) in cm^-1 (default: the whole grid; the notebook masks 500..8000),
-        Levenberg-Marquardt on the device (pst_fit_two_lorentzians).  fit="three-point" keeps the closed-form estimates.
+        Levenberg-Marquardt on the device (pst_fit_two_lorentzians) stopped at lmfit's default tolerance `tol` (ftol =
+        xtol = 1.5e-8; `evaluations` < 0 marks spectra that used all `max_iter` evaluations first -- typically a window
+        that does not hold two lines).  fit="three-point" keeps the closed-form estimates.
         Only (LP, UP, widths, amplitudes) per spectrum leave the GPU.  Returns a dict of arrays shaped (n_theta,) or
         (n_sweep, n_theta): `theta`, `LP`, `UP`, `splitting` = UP - LP, `hwhm_LP`, `hwhm_UP`, `amp_LP`, `amp_UP`
         (peak heights for "three-point", lmfit amplitudes = areas for "joint", which also returns `chi2` and
@@ -448,7 +450,7 @@ class Structure:
                 order = nu[::-1] if rev else nu
                 lo, hi = np.searchsorted(order, [float(window[0]), float(window[1])], side="left")
                 win = (int(lo), int(max(hi, lo + 6)))
-            br = _to_numpy(eng.fit_two_lorentzians(T, seeds, nu, reverse=rev, window=win, max_iter=max_iter))
+            br = _to_numpy(eng.fit_two_lorentzians(T, seeds, nu, reverse=rev, window=win, max_iter=max_iter, tol=tol))
             extra = {"chi2": br[..., 6], "evaluations": br[..., 7]}
         out = {"theta": theta, "LP": br[..., 0], "UP": br[..., 1], "splitting": br[..., 1] - br[..., 0],
                "hwhm_LP": br[..., 2], "hwhm_UP": br[..., 3], "amp_LP": br[..., 4], "amp_UP": br[..., 5], **extra}

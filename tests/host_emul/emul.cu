@@ -167,9 +167,9 @@ extern "C" void emul_cosh_sinh(int n, const double* y, double* ch, double* sh, i
 }
 
 // ---- joint two-Lorentzian fit (pst_fit.cuh) on one contiguous spectrum, for the comparison with scipy's curve_fit
-extern "C" void emul_fit_two_lorentzians(int n, const double* x, const double* y, const double* seed, double sigma0, int max_iter,
-                                         double* out) {
+extern "C" void emul_fit_two_lorentzians(int n, const double* x, const double* y, const double* seed, double sigma0, double tol,
+                                         int max_iter, double* out) {
   FitProblem pb;
   pb.y = y; pb.y_stride = 1; pb.x = x; pb.x_stride = 1; pb.n = n;
-  fit_two_lorentzians(pb, seed, sigma0, max_iter, out);
+  fit_two_lorentzians(pb, seed, sigma0, tol, max_iter, out);
 }

@@ -635,6 +635,18 @@ def test_fp32_mode_fuzz_and_variants(eng, ref_cases):
     assert np.abs(f32["T"] - f64["T"]).max() <= 1e-6 and np.abs(f32["R"] - f64["R"]).max() <= 1e-6
     with pytest.raises(ValueError):
         eng.eval_grid(*args, flags=FP32, want_matrix=True)
+    # the mode's bound is 1e-5 of full scale up to PST_FP32_MAX_LAYERS (88) interior layers -- identical layers repeat
+    # their rounding error, 1.1e-7 per layer on this low-contrast quarter-wave stack; deeper stacks are refused
+    deep = [0] + [1, 2] * 45 + [0]
+    nn = np.array([1.0, 1.46, 1.45])[:, None] * np.ones((1, 64))
+    wl64 = np.linspace(0.9, 1.1, 64)
+    with pytest.raises(ValueError, match="PST_FP32_MAX_LAYERS"):
+        eng.eval_grid(wl64, [0.0, 0.4], nn, 0 * nn, deep, [0.0] + [0.17] * 90 + [0.0], POLS, flags=FP32)
+    args = (wl64, [0.0, 0.4], nn, 0 * nn, deep[:-3] + [0], [0.0] + [0.17] * 88 + [0.0], POLS)
+    ok, f64 = eng.eval_grid(*args, flags=FP32).numpy(), eng.eval_grid(*args).numpy()
+    worst = max(np.abs(ok["R"] - f64["R"]).max(), np.abs(ok["T"] - f64["T"]).max())
+    print(f"fp32, 88 layers: worst |d| = {worst:.2e}")
+    assert worst <= 1e-5
 
 
 def test_thick_absorber_and_deep_bragg_stay_finite(eng):
