@@ -352,6 +352,36 @@ PST_HD void pair_power_coeffs_t(const Period& U, int k, int hb, PairPower& S) {
   }
 }
 
+// Pair counts up to kPowerFixedMax: the bits of k resolved at COMPILE time.  k is block-uniform, so one jump selects a
+// straight-line chain of exactly the squarings and multiplications k needs (k = 20: 4 squarings + 1 multiplication =
+// 23 FP64 instructions, no bit tests, no predicated multiplications, no register moves between steps).  The operations
+// and their order are those of pair_power_coeffs_t<false>, so the two agree bit for bit (the interpreter keeps the
+// generic form; tests/test_gpu_parity.py::test_cavity_shape_fast_path_is_bit_identical compares them).
+constexpr int kPowerFixedMax = 40;
+template <int K>
+PST_HD void pair_power_fixed(const Period& U, PairPower& S) {
+  if constexpr (K <= 1) {
+    S.t = U.x;
+    S.s = 1.0;
+    S.ks = 0;
+  } else {
+    pair_power_fixed<K / 2>(U, S);
+    pair_power_step<false>(U, (K & 1) != 0, S);
+  }
+}
+// false: k is outside the compiled range (the caller takes the generic form)
+PST_HD bool pair_power_small(const Period& U, int k, PairPower& S) {
+#define PST_PPF(K) case K: pair_power_fixed<K>(U, S); return true;
+  switch (k) {
+    PST_PPF(1) PST_PPF(2) PST_PPF(3) PST_PPF(4) PST_PPF(5) PST_PPF(6) PST_PPF(7) PST_PPF(8) PST_PPF(9) PST_PPF(10)
+    PST_PPF(11) PST_PPF(12) PST_PPF(13) PST_PPF(14) PST_PPF(15) PST_PPF(16) PST_PPF(17) PST_PPF(18) PST_PPF(19) PST_PPF(20)
+    PST_PPF(21) PST_PPF(22) PST_PPF(23) PST_PPF(24) PST_PPF(25) PST_PPF(26) PST_PPF(27) PST_PPF(28) PST_PPF(29) PST_PPF(30)
+    PST_PPF(31) PST_PPF(32) PST_PPF(33) PST_PPF(34) PST_PPF(35) PST_PPF(36) PST_PPF(37) PST_PPF(38) PST_PPF(39) PST_PPF(40)
+    default: return false;
+  }
+#undef PST_PPF
+}
+
 // Whether the powering must rescale: |t_k|, |s_k| <= k G^(2k) with G <= 2^lg the per-layer growth bound.  Block-uniform
 // by construction (lg is grid-wide, k comes from the program).  Without rescaling the entries of U^k stay below
 // 2^kPowerNoRescaleLog2.
@@ -386,7 +416,9 @@ PST_HD void pair_power_matrix(const Period& U, const PairPower& S, double ct, do
   P.ks = S.ks;
 }
 
-template <int NPOL, int NC>
+// V0_REAL: the caller knows Im v0 = 0 exactly (the exit column straight from init_exit_columns); the two products with
+// that zero are left out -- the same values (finite operands), two FP64 instructions fewer per polarisation
+template <int NPOL, int NC, bool V0_REAL = false>
 PST_HD void apply_pair_matrix(ChainState<NPOL, NC>& st, const PairMatrix<NPOL>& P) {
 #pragma unroll
   for (int p = 0; p < NPOL; ++p) {
@@ -395,9 +427,14 @@ PST_HD void apply_pair_matrix(ChainState<NPOL, NC>& st, const PairMatrix<NPOL>& 
       double* v = st.v[p][c];
       const double v0r = v[0], v0i = v[1], v1r = v[2], v1i = v[3];
       v[0] = fma(P.p00, v0r, P.p01[p] * v1i);
-      v[1] = fma(P.p00, v0i, -(P.p01[p] * v1r));
-      v[2] = fma(P.p11, v1r, P.p10[p] * v0i);
       v[3] = fma(P.p11, v1i, -(P.p10[p] * v0r));
+      if constexpr (V0_REAL) {
+        v[1] = -(P.p01[p] * v1r);
+        v[2] = P.p11 * v1r;
+      } else {
+        v[1] = fma(P.p00, v0i, -(P.p01[p] * v1r));
+        v[2] = fma(P.p11, v1r, P.p10[p] * v0i);
+      }
     }
     st.kexp[p] += P.ks;
   }

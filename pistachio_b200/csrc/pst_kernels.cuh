@@ -900,7 +900,7 @@ __device__ __noinline__ void cavity_lossy_mirrors(const double* rv, double dA, d
 // MIRRORED: the second mirror is the mirror image of the first (only looked at when the pair counts agree)
 template <int NPOL, bool ROW, int MODE, bool RESC, bool MIRRORED>
 __device__ __forceinline__ void cavity_tiles(const GridParams& prm, const CavityPlan& cp, unsigned s_base, unsigned lossy_mask,
-                                             bool mid_rescale) {
+                                             bool mid_rescale, bool calm_skips_rescale) {
   const unsigned npts = (unsigned)prm.points, nth = (unsigned)prm.n_theta;
   const unsigned sweep_idx = ROW ? blockIdx.z : blockIdx.y;
   const int n_tiles = ROW ? cp.tiles : 1;
@@ -959,6 +959,7 @@ __device__ __forceinline__ void cavity_tiles(const GridParams& prm, const Cavity
       // ---- first mirror: the two sincos chains interleave in one basic block
       PairMatrix<NPOL> P;
       Period U;
+      bool calm = false;
       {
         const double2 q = PST_V2(0);
         const double xA = layer_phase(q.x, ct, cp.d[0]), xB = layer_phase(q.y, ct, cp.d[1]);
@@ -974,13 +975,19 @@ __device__ __forceinline__ void cavity_tiles(const GridParams& prm, const Cavity
         const BareLayer A = finish_bare_layer(sA, cA, na.x, na.y), B = finish_bare_layer(sB, cB, nb.x, nb.y);
         period_form(A, B, false, U);
         PairPower S;
-        pair_power_coeffs_t<RESC>(U, cp.k1, cp.hb1, S);
+        if constexpr (RESC) {
+          pair_power_coeffs_t<true>(U, cp.k1, cp.hb1, S);
+        } else {
+          if (!pair_power_small(U, cp.k1, S)) pair_power_coeffs_t<false>(U, cp.k1, cp.hb1, S);
+        }
         pair_power_matrix<NPOL>(U, S, ct, ict, prm.pol_first, P);
+        // |x| < 2 on every lane of the warp (tested on the high word; NaN fails): the Bloch eigenvalue is below 2 + sqrt 3
+        if constexpr (!RESC) calm = __all_sync(0xffffffffu, ((unsigned)hi_word(U.x) & 0x7fffffffu) < 0x40000000u) != 0;
         // a second mirror with another pair count has a power of its own (see the interpreter's op loop); its period
         // rounds in the order its own first layer dictates and is formed now, while A and B are live
         if (cp.k2 != cp.k1 && cp.mirrored) period_form(B, A, false, U);
       }
-      apply_pair_matrix<NPOL, 1>(st, P);
+      apply_pair_matrix<NPOL, 1, true>(st, P);
       if (mid_rescale) renormalise<NPOL, 1>(st);
       // ---- spacer
       {
@@ -1005,7 +1012,9 @@ __device__ __forceinline__ void cavity_tiles(const GridParams& prm, const Cavity
         pair_power_matrix<NPOL>(U, S2, ct, ict, prm.pol_first, P);
       }
       apply_pair_matrix<NPOL, 1>(st, P);
-      renormalise<NPOL, 1>(st);
+      // The epilogue squares the entries of M: the state is rescaled first unless the whole product provably stays far
+      // inside the fp64 range (warp-uniform; rescaling is exact, so the bits do not depend on the decision)
+      if (!(calm_skips_rescale && calm)) renormalise<NPOL, 1>(st);
       {
         const double2 in0 = PST_V2(16), nf2 = PST_V2(14);
 #pragma unroll
@@ -1076,7 +1085,14 @@ tmm_cavity_kernel(const GridParams prm, const CavityPlan cp) {
   const bool mid_rescale = lg > 100;
   const bool resc = pair_power_needs_rescale(max(cp.k1, cp.k2), lg);
   const bool mir = cp.mirrored != 0;
-#define PST_CT(MODE, RESC, MIR) cavity_tiles<NPOL, ROW, MODE, RESC, MIR>(prm, cp, s_base, lossy_mask, mid_rescale)
+  // Growth of the whole program when |x| < 2 at a point (x = half the period's trace): U^k = t I + s W with
+  // |t| <= mu^k, |s| <= k mu^(k-1), mu = |x| + sqrt(x^2 - 1) < 2^2, entries of W below 2^(2 lg)  ->  one mirror grows the
+  // state by < 2^(2 k + hb + 2 lg + 4), the spacer by 2^lg, exit column and D_0^-1 by 2^E each: when the sum of the
+  // exponents stays below 500 the squares |M00|^2, |M10|^2 cannot leave the fp64 range and the final rescaling is skipped
+  // for warps whose 32 points all have |x| < 2 (every pass band and every stop band of ordinary mirrors).
+  const int E = growth_E_of_word(lossy_mask);
+  const bool calm_skips = !mid_rescale && 2 * (cp.k1 + cp.k2) + cp.hb1 + cp.hb2 + 5 * lg + 2 * E + 9 <= 500;
+#define PST_CT(MODE, RESC, MIR) cavity_tiles<NPOL, ROW, MODE, RESC, MIR>(prm, cp, s_base, lossy_mask, mid_rescale, calm_skips)
   if (lossyAB) PST_CT(2, false, false);
   else if (!resc) {
     if (!lossyC) { if (mir) PST_CT(0, false, true); else PST_CT(0, false, false); }

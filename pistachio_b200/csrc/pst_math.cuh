@@ -179,16 +179,16 @@ PST_HD void sincos_core(double x, double& s, double& c) {
   const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
   const double t = fma(x, PST_SC(12), kMagic);
   const double kd = t - kMagic;
-  int q;
+  int q;  // low word of the magic sum = k mod 2^32 (read as a 32-bit register: the quadrant tests stay 32-bit compares)
+#ifdef __CUDA_ARCH__
+  q = __double2loint(t);
+#else
   {
     long long u;
-#ifdef __CUDA_ARCH__
-    u = __double_as_longlong(t);
-#else
     memcpy(&u, &t, 8);
-#endif
-    q = (int)u;  // low word of the magic sum = k mod 2^32
+    q = (int)u;
   }
+#endif
   // two-term Cody-Waite: kd * hi is exact in the FMA and the middle word carries pi/2 to 2^-107; the third word
   // (8.5e-32 kd < 6e-23 on the fast range) is below half an ulp of any result that is not itself below 1e-6
   double r = fma(kd, PST_SC(13), x);
