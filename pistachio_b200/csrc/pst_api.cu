@@ -571,6 +571,10 @@ int launch_chain(pst_handle_t h, const pst_grid_args* a, const ChainPlan& pl, in
   prm.lossy_word = h->lossy_types.p;
   prm.trig = h->trig.p;
   prm.layers = h->layers_flagged.p;  // `type` field = the material's lossy flag
+  for (int j = 0; j < a->n_layers; ++j) {
+    const double v = std::fabs(a->layer_d[j]);
+    if (!(v <= prm.d_max)) prm.d_max = (v == v) ? v : INFINITY;  // a NaN thickness: the kernels keep their range tests
+  }
   TypedPlan tp;
   std::memset(&tp, 0, sizeof(tp));
   if (pl.typed) {

@@ -37,15 +37,20 @@ constexpr int kTypeRecBytes = 80;   // one cached layer matrix: 10 doubles (comp
                                     // power-of-two exponents of all types follow the records as ints
 constexpr int kRenormEvery = 16;
 // deep-stack kernel: layers whose transcendental parts share a basic block, and groups per unrolled loop trip
-// (measured on BASELINE configs[3]: 1/1 0.672 ms, 2/1 0.582, 2/2 0.569, 2/8 0.594 -- instruction cache --, 4/1 0.567 with
-// 208 bytes of spills at the 72-register cap, 4/4 0.620)
+// (measured on BASELINE configs[3] with the range test hoisted out of the loops -- the kernel is bound by dependent-issue
+// latency at 7 warps per scheduler, so independent sincos chains per basic block pay: 2/1 0.550 ms, 2/2 0.579, 2/4 0.560,
+// 4/1 0.539, 4/2 0.526, 4/4 0.516, 8/1 0.527, 8/2 0.551; 4/2 at 80 registers 0.521, at 64 registers 0.531.
+// Before the hoist: 1/1 0.672, 2/2 0.569, 4/1 0.567)
 #ifndef PST_K2_GROUP
-#define PST_K2_GROUP 2
+#define PST_K2_GROUP 4
 #endif
 #ifndef PST_K2_UNROLL
-#define PST_K2_UNROLL 2
+#define PST_K2_UNROLL 4
 #endif
 constexpr int kK2Group = PST_K2_GROUP, kK2Unroll = PST_K2_UNROLL;
+#ifndef PST_K2_MAXREG
+#define PST_K2_MAXREG 72
+#endif
 #ifndef PST_K1_MAXREG
 #define PST_K1_MAXREG 80
 #endif
@@ -61,6 +66,7 @@ struct GridParams {
   int il0;           // first wavelength index of this launch (host pipeline launches wavelength windows)
   unsigned flags;
   int use_bulk;      // stage the tables with the bulk-copy engine (cp.async.bulk + mbarrier)
+  double d_max;      // largest |thickness| of the layer list (host; the swept values are looked at by the kernels)
   long long points;  // wavelengths of this launch * n_theta
   const double* opt;        // [n_wl][n_mat][6]: OptRow order qr nr inr ni qi ini
   const int* mat_flags;     // [n_mat] bit0: k != 0 at some wavelength
@@ -301,7 +307,7 @@ prep_kernel(const double* __restrict__ wl, const double* __restrict__ mat_n, con
 //   SEG    blockDim.y ordered layer segments per point, combined in order through shared memory (deep stacks)
 template <int NPOL, int NCOL, bool STAGE_OPT, bool STAGE_LAYERS, bool SEG>
 __global__ void __launch_bounds__(SEG ? 512 : 256)
-__maxnreg__(SEG ? (NPOL == 1 ? 72 : 128) : (NCOL == 1 ? PST_K1_MAXREG : 255))  // deep-stack kernel, one polarisation: 72 registers = 28 warps per SM, what
+__maxnreg__(SEG ? (NPOL == 1 ? PST_K2_MAXREG : 128) : (NCOL == 1 ? PST_K1_MAXREG : 255))  // deep-stack kernel, one polarisation: 72 registers = 28 warps per SM, what
 tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384 points x 8 segments) needs to be resident at once
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NC = SEG ? 2 : NCOL;  // a segment product needs both columns
@@ -349,6 +355,13 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
   const double ct = tr.x, ict = tr.y;
   const int sweep = blockIdx.y;
   const double d_sweep = prm.sweep_d ? __ldg(prm.sweep_d + sweep) : 0.0;
+  // a staged layer list takes the block's swept thickness in place: the layer loops then test nothing per layer
+  if constexpr (STAGE_LAYERS) {
+    if (prm.sweep_d) {
+      if (tid == 0) s_layers[prm.sweep_layer].d = d_sweep;
+      __syncthreads();
+    }
+  }
 
   // optical-table accessor for this thread's wavelength: 48-byte rows, three 16-byte loads
   const unsigned char* optp = STAGE_OPT ? (s_opt + (size_t)(il - l_lo) * prm.opt_row_bytes)
@@ -367,6 +380,20 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
     qr = a.x; nr = a.y; inr = o[1].x;
   };
   const OptRow exit_row = opt_row(lay[L - 1].mat);
+
+  // Every phase of this thread is |q cos(theta) d| <= max|q| |cos| max|d|.  When that bound is inside sincos' fast range
+  // for the whole warp, the layer loops below run without the per-layer range test (an FP64 compare, a branch and a
+  // convergence barrier per layer); otherwise the tested loops run.  Same functions on the same arguments either way.
+  bool warp_fast;
+  {
+    double qmax = 0.0;
+    for (int m = 0; m < prm.n_mat; ++m) {
+      const double2 a = reinterpret_cast<const double2*>(optp + (size_t)m * 48)[0];
+      qmax = fmax(qmax, fabs(a.x));
+    }
+    const double bound = qmax * fabs(ct) * fmax(prm.d_max, fabs(d_sweep));
+    warp_fast = __all_sync(0xffffffffu, bound < 536870912.0) != 0;  // 2^29: a factor two of slack for the roundings
+  }
 
   // ---- the ordered chain over this thread's segment of interior layers
   const int Li = L - 2;
@@ -469,7 +496,7 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
       }
       const int sweep_j = prm.sweep_d ? prm.sweep_layer : -1;
       auto phase_of = [&](const LayerEntry& le, int j, double& nr, double& inr) {
-        const double d = (j == sweep_j) ? d_sweep : le.d;
+        const double d = (!STAGE_LAYERS && j == sweep_j) ? d_sweep : le.d;
         double qr;
         opt_row_real(le.mat, qr, nr, inr);
         return layer_phase(qr, ct, d);
@@ -485,6 +512,7 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
           b[pp] = fma(m.c, b0, m.al[pp] * u0);
         }
       };
+      auto run = [&](auto NOTEST) {
       for_each_layer(
           std::true_type{},
           [&](const LayerEntry& le, int j) {
@@ -494,14 +522,14 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
           },
           [&](const LayerEntry* first, int j_first, auto N_) {
             // the transcendental parts of N consecutive layers (first[0], first[-1], ...) in one basic block with one joint
-            // range test, then the N ordered steps
+            // range test (none when the warp's phase bound already guarantees the range), then the N ordered steps
             constexpr int N = decltype(N_)::value;
             double nr[N], inr[N], x[N], sx[N], cx[N];
             bool fast = true;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
               x[i] = phase_of(first[-i], j_first - i, nr[i], inr[i]);
-              fast = fast && sincos_in_fast_range(x[i]);
+              if constexpr (!decltype(NOTEST)::value) fast = fast && sincos_in_fast_range(x[i]);
             }
             if (fast) {
 #pragma unroll
@@ -526,6 +554,9 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
               ke[pp] += e;
             }
           });
+      };
+      if (warp_fast) run(std::true_type{});
+      else run(std::false_type{});
 #pragma unroll
       for (int pp = 0; pp < NPOL; ++pp) {
         st.v[pp][0][0] = a[pp]; st.v[pp][0][1] = 0.0; st.v[pp][0][2] = 0.0; st.v[pp][0][3] = w[pp];
@@ -537,7 +568,7 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
   }
   if (!done) {
     auto apply_any = [&](const LayerEntry& le, int j) {
-          const double d = (j == prm.sweep_layer) ? d_sweep : le.d;
+          const double d = (!STAGE_LAYERS && j == prm.sweep_layer) ? d_sweep : le.d;
           const int lossy = le.type;  // untyped launches get the flagged layer list (prep_kernel)
           if (lossy == 0) {
             double qr, nr, inr;
@@ -547,6 +578,7 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
             apply_cplx_layer<NPOL, NC>(st, build_cplx_layer<NPOL>(opt_row(le.mat), d, ct, ict, prm.pol_first));
           }
         };
+    auto run = [&](auto NOTEST) {
     for_each_layer(std::false_type{}, apply_any,
                    [&](const LayerEntry* first, int j_first, auto N_) {
                      constexpr int N = decltype(N_)::value;
@@ -558,9 +590,9 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
                          double q0, n0, in0, q1, n1, in1, sx0, cx0, sx1, cx1;
                          opt_row_real(le0.mat, q0, n0, in0);
                          opt_row_real(le1.mat, q1, n1, in1);
-                         const double x0 = layer_phase(q0, ct, (j_first == prm.sweep_layer) ? d_sweep : le0.d);
-                         const double x1 = layer_phase(q1, ct, (j_first - 1 == prm.sweep_layer) ? d_sweep : le1.d);
-                         if (sincos_in_fast_range(x0) && sincos_in_fast_range(x1)) {
+                         const double x0 = layer_phase(q0, ct, (!STAGE_LAYERS && j_first == prm.sweep_layer) ? d_sweep : le0.d);
+                         const double x1 = layer_phase(q1, ct, (!STAGE_LAYERS && j_first - 1 == prm.sweep_layer) ? d_sweep : le1.d);
+                         if (decltype(NOTEST)::value || (sincos_in_fast_range(x0) && sincos_in_fast_range(x1))) {
                            sincos_core(x0, sx0, cx0);
                            sincos_core(x1, sx1, cx1);
                          } else {
@@ -575,6 +607,9 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
                      for (int i = 0; i < N; ++i) apply_any(first[-i], j_first - i);
                    },
         [&]() { renormalise<NPOL, NC>(st); });
+    };
+    if (warp_fast) run(std::true_type{});
+    else run(std::false_type{});
   }
 
   ChainState<NPOL, NCOL> fin;
