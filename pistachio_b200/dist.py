@@ -175,7 +175,12 @@ class AssembledResult:
             return eng.eval_prepared(prep_slab, pols=pols, out_ptrs=self.multicast_ptrs(), flags=flags | FLAG_MULTICAST_OUT)
         if self.mode == "unicast":
             return eng.eval_prepared(prep_slab, pols=pols, out_ptrs=self.peer_ptrs(), flags=flags)
-        return eng.eval_prepared(prep_slab, pols=pols, want=self.keys, out={k: self.local_slab(k) for k in self.keys}, flags=flags)
+        # the slab as the engine's [sweep][pol][wl][theta] view (a slab cut along the wavelength axis carries a leading 1)
+        def as_grid(t):
+            return t.view((-1,) + tuple(t.shape[-3:]))
+
+        return eng.eval_prepared(prep_slab, pols=pols, want=self.keys, out={k: as_grid(self.local_slab(k)) for k in self.keys},
+                                 flags=flags)
 
     def finish(self):
         if self.mode == "nccl":
