@@ -76,6 +76,10 @@ def main() -> None:
 
     tr = {"workload": a.workload, "kernel": inst[0][iname], "source": f"ncu --set full, profiles/{os.path.basename(raw_path)}",
           "dram_bytes_read": int(val("dram__bytes_read.sum", inst[0])), "dram_bytes_write": int(val("dram__bytes_write.sum", inst[0]))}
+    for key, name in (("fp64_pipe_pct", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                      ("issue_active_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active")):
+        if name in hdr:
+            tr[key] = float(inst[0][hdr.index(name)])  # bench.py copies fp64_pipe_pct into roofline.fp64.pipe_util_ncu_pct
     with open(os.path.join(prof, f"{a.tag}_traffic.json"), "w") as fh:
         json.dump(tr, fh, indent=1)
         fh.write("\n")
