@@ -390,7 +390,7 @@ PST_HD bool pair_power_needs_rescale(int k, int lg) { return 2 * lg * k + 40 > k
 
 PST_HD void pair_power_coeffs(const Period& U, int k, int lg, PairPower& S) {
   if (pair_power_needs_rescale(k, lg)) pair_power_coeffs_t<true>(U, k, log2_floor(k), S);
-  else pair_power_coeffs_t<false>(U, k, log2_floor(k), S);
+  else if (!pair_power_small(U, k, S)) pair_power_coeffs_t<false>(U, k, log2_floor(k), S);
 }
 
 // U^k = t I + s W as a matrix [[p00, -i p01], [-i p10, p11]] (real entries) times 2^ks: the diagonal is shared by the

@@ -158,6 +158,19 @@ extern "C" int emul_eval_grid(int n_wl, int n_theta, int L, const double* wl, co
   return 0;
 }
 
+// ---- period power (pst_chain.cuh): the compile-time chain of a pair count against the generic runtime bit loop
+// out = (t, s, 1 when the count is inside the compiled range)
+extern "C" void emul_pair_power(double x, double s2, int k, int fixed, double* out) {
+  Period U;
+  U.x = x; U.s2 = s2; U.w = 0.0; U.u01 = 0.0; U.u10 = 0.0;
+  PairPower S;
+  S.t = S.s = 0.0; S.ks = 0;
+  bool ok = true;
+  if (fixed) ok = pair_power_small(U, k, S);
+  else pair_power_coeffs_t<false>(U, k, log2_floor(k), S);
+  out[0] = S.t; out[1] = S.s; out[2] = ok ? 1.0 : 0.0;
+}
+
 // ---- elementary functions of the layer loop, exposed for accuracy tests against mpmath
 extern "C" void emul_sincos(int n, const double* x, double* s, double* c) {
   for (int i = 0; i < n; ++i) sincos_fast(x[i], s[i], c[i]);

@@ -322,6 +322,76 @@ def test_low_contrast_cavity_straight_line_path_against_oracle(eng):
         rep.check(max_loose_fraction=0.01)
 
 
+def test_cavity_kernel_pair_counts_and_rescale_vote(eng):
+    """The cavity kernel resolves pair counts up to 40 at compile time (one straight-line squaring chain per k, the
+    generic bit loop above) and skips its final rescale for warps whose points all have |x| < 2 (x = half the period's
+    trace).  Every compiled chain, the generic fallback and both sides of the vote must agree bit for bit with the op
+    interpreter (PST_FLAG_NO_SHAPE_FASTPATH: runtime bit loop, rescale after every power), and hold parity against the
+    oracle: pair counts 3..41 with unequal mirrors, and a high-contrast mirror (n = 3.9 / 1.0: |x| = 2.08 at the stop-band
+    centre, < 2 towards the edges, so warps mix and split) next to a low-contrast one."""
+    from tests import periodic_cases as pc
+
+    NOFAST = 1 << 11
+    th = np.linspace(0.0, 1.0, 150)  # >= 120 angles: the row-mode launch of the bench
+    wl = np.linspace(0.8, 1.25, 12)
+    for k1, k2 in ((3, 5), (7, 7), (11, 6), (16, 23), (31, 31), (40, 41), (41, 40), (13, 1), (2, 2)):
+        cols, lm, ld = pc.quarter_wave_stack(1, wl, n_hi=2.3, n_lo=1.38)
+        lm = [0] + [1, 2] * k1 + [4] + [2, 1] * k2 + [3]
+        ld = [0.0] + [ld[1], ld[2]] * k1 + [1.0 / 3.0] + [ld[2], ld[1]] * k2 + [0.0]
+        cols = np.concatenate([cols, np.full((1, len(wl)), 1.5 + 3e-4j)])
+        a = eng.eval_grid(wl, th, cols.real, cols.imag, lm, ld, POLS).numpy()
+        b = eng.eval_grid(wl, th, cols.real, cols.imag, lm, ld, POLS, flags=NOFAST).numpy()
+        for key in ("R", "T", "A"):
+            assert np.array_equal(a[key], b[key]), (k1, k2, key)
+        assert np.isfinite(a["R"]).all() and np.isfinite(a["T"]).all()
+    sel = np.array([0, 37, 149])
+    for n_hi, n_lo, pairs in ((3.9, 1.0, 12), (1.46, 1.45, 12)):
+        wl = pc.band_edge_wavelengths(n_hi, n_lo, 24, 6, lo=0.7, hi=1.4)
+        cols, lm, ld = pc.quarter_wave_stack(pairs, wl, n_hi=n_hi, n_lo=n_lo, spacer=(1.5 + 0j, 1.0 / 3.0))
+        a = eng.eval_grid(wl, th, cols.real, cols.imag, lm, ld, POLS, cos_theta=np.cos(th)).numpy()
+        b = eng.eval_grid(wl, th, cols.real, cols.imag, lm, ld, POLS, cos_theta=np.cos(th), flags=NOFAST).numpy()
+        for key in ("R", "T", "A"):
+            assert np.array_equal(a[key], b[key]), (n_hi, key)
+        rep = parity.compare_grid(f"cavity {n_hi}/{n_lo} x{pairs}", a["T"][0][:, :, sel], a["R"][0][:, :, sel], wl,
+                                  pc.per_layer(cols, lm), ld, th[sel])
+        rep.check(max_loose_fraction=0.01)
+
+
+def test_phase_bound_fallback_keeps_the_range_tests(eng):
+    """The layer loops (K1 untyped, K2) run without sincos' per-layer range test when max|q| |cos| max|d| of the warp is
+    inside the fast range.  A layer of 3e8 um (phase ~ 3e9 rad > 2^30) must send the warp back to the tested loops and
+    through the Payne-Hanek reduction: same bits as the typed path (which tests per layer), parity against the oracle,
+    and the swept-thickness variant (the block's swept value enters the bound) equal to the fixed-thickness launches."""
+    from pistachio_b200._cabi import FLAG_FORCE_DEEP_KERNEL, FLAG_NO_LAYER_CSE
+
+    wl = np.linspace(0.9, 1.1, 40)
+    th = np.array([0.0, 0.3, 0.7])
+    nw = len(wl)
+    cols = np.array([np.full(nw, 1.0 + 0j), np.full(nw, 2.1 + 0j), np.full(nw, 1.4 + 0j), np.full(nw, 1.5 + 0j)])
+    lm = [0, 1, 2, 1, 2, 1, 3]
+    for thick in (0.13, 3.0e8):
+        ld = [0.0, 0.11, thick, 0.12, 0.19, 0.10, 0.0]
+        kw = dict(cos_theta=np.cos(th))
+        typed = eng.eval_grid(wl, th, cols.real, cols.imag, lm, ld, POLS, **kw).numpy()
+        loop = eng.eval_grid(wl, th, cols.real, cols.imag, lm, ld, POLS, flags=FLAG_NO_LAYER_CSE, **kw).numpy()
+        deep = eng.eval_grid(wl, th, cols.real, cols.imag, lm, ld, POLS, flags=FLAG_FORCE_DEEP_KERNEL, **kw).numpy()
+        for key in ("R", "T", "A"):
+            assert np.array_equal(typed[key], loop[key]), (thick, key)
+        np.testing.assert_allclose(deep["R"], loop["R"], rtol=0, atol=1e-11)
+        rep = parity.compare_grid(f"thick layer {thick}", loop["T"][0], loop["R"][0], wl, [cols[m] for m in lm], ld, th)
+        rep.check(max_loose_fraction=0.01)
+    sw = np.array([0.13, 3.0e8, 0.2])
+    ld = [0.0, 0.11, 0.13, 0.12, 0.19, 0.10, 0.0]
+    swept = eng.eval_grid(wl, th, cols.real, cols.imag, lm, ld, POLS, sweep_layer=2, sweep_d=sw, flags=FLAG_NO_LAYER_CSE,
+                          cos_theta=np.cos(th)).numpy()
+    for i, dv in enumerate(sw):
+        ld2 = list(ld)
+        ld2[2] = float(dv)
+        one = eng.eval_grid(wl, th, cols.real, cols.imag, lm, ld2, POLS, flags=FLAG_NO_LAYER_CSE, cos_theta=np.cos(th)).numpy()
+        for key in ("R", "T"):
+            assert np.array_equal(swept[key][i], one[key][0]), (i, key)
+
+
 def test_period_power_against_mpmath_truth(eng):
     """200 pairs of n = 1.50/1.45 over 0.90-1.10 um against a 50-digit evaluation of the model, and a
     1000-pair high-contrast stop band where the reference overflows (no oracle): the closed-form power must be as close

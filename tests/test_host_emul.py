@@ -193,3 +193,28 @@ def test_emul_period_power_against_mpmath_truth(emul):
     err_s = max(np.abs(Rs - Rt).max(), np.abs(Ts - Tt).max())
     print(f"200 pairs 1.50/1.45 vs mpmath: closed-form power {err_p:.2e}, layer by layer {err_s:.2e}")
     assert err_p < 1e-12 and err_p < 3 * err_s + 2e-14
+
+
+def test_compile_time_pair_power_equals_the_bit_loop(emul):
+    """pair_power_small (pair counts 1..kPowerFixedMax resolved at compile time: the cavity and typed kernels' default)
+    performs the operations of the generic left-to-right bit loop in the same order: (t_k, s_k) must be equal bit for
+    bit for every compiled count, in pass bands (|x| < 1), at band edges and inside stop bands; counts above the range
+    are refused.  Both agree with the Chebyshev polynomials t_k = T_k(x), s_k = U_{k-1}(x) when s2 = 1 - x^2."""
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.uniform(-1.0, 1.0, 12), [-1.0, 1.0, 0.0, -0.999999, 1.000001], rng.uniform(1.0, 2.5, 6) * rng.choice([-1, 1], 6)])
+    out_f, out_g = (C.c_double * 3)(), (C.c_double * 3)()
+    emul.emul_pair_power.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    emul.emul_pair_power.restype = None
+    for k in range(1, 41):
+        for x in xs:
+            for s2 in (1.0 - x * x, (1.0 - x * x) * (1.0 + 3e-13)):
+                emul.emul_pair_power(float(x), float(s2), k, 1, out_f)
+                emul.emul_pair_power(float(x), float(s2), k, 0, out_g)
+                assert out_f[2] == 1.0
+                assert out_f[0] == out_g[0] and out_f[1] == out_g[1], (k, x)
+        x = 0.3
+        emul.emul_pair_power(x, 1.0 - x * x, k, 1, out_f)
+        th = np.arccos(x)
+        np.testing.assert_allclose([out_f[0], out_f[1]], [np.cos(k * th), np.sin(k * th) / np.sin(th)], rtol=0, atol=1e-13 * k)
+    emul.emul_pair_power(0.3, 0.91, 41, 1, out_f)
+    assert out_f[2] == 0.0
