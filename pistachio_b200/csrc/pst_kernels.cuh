@@ -1328,8 +1328,15 @@ __device__ __forceinline__ void sweep_loop(const GridParams& prm, const SweepCon
         m00 = {fma(cx, k.al0[pp].re, sx * k.be0[pp].re), fma(cx, k.al0[pp].im, sx * k.be0[pp].im)};
         m10 = {fma(cx, k.al1[pp].re, sx * k.be1[pp].re), fma(cx, k.al1[pp].im, sx * k.be1[pp].im)};
       } else {
-        m00 = cadd(cmul(cphi, k.al0[pp]), cmul(sphi, k.be0[pp]));
-        m10 = cadd(cmul(cphi, k.al1[pp]), cmul(sphi, k.be1[pp]));
+        // cos(phi) a + sin(phi) b as one FMA chain per component (8 FP64 instructions per entry instead of the 10 of two
+        // complex products and a sum): cos(phi) = (P1, -P2), sin(phi) = (P3, P4)
+        const double P1 = cphi.re, P2 = -cphi.im, P3 = sphi.re, P4 = sphi.im;
+        auto mix = [&](const cplx& a, const cplx& b) -> cplx {
+          return {fma(P1, a.re, fma(P2, a.im, fma(P3, b.re, -(P4 * b.im)))),
+                  fma(P1, a.im, fma(P3, b.im, fma(P4, b.re, -(P2 * a.re))))};
+        };
+        m00 = mix(k.al0[pp], k.be0[pp]);
+        m10 = mix(k.al1[pp], k.be1[pp]);
       }
       const double den = fma(m00.re, m00.re, m00.im * m00.im);
       const double num = fma(m10.re, m10.re, m10.im * m10.im);
