@@ -10,7 +10,19 @@
 //                            ordered segments, one warp row per segment builds the 2x2 product of its
 //                            segment, and the segment products are combined in order through shared
 //                            memory (associative, non-commutative scan over layers)
+//   tmm_typed_kernel     K1  layer CSE: identical (material, thickness) layers share one cached matrix; run-length op
+//                            interpreter; repeated lossless pairs as the power of their period (pst_chain.cuh)
+//   tmm_cavity_kernel    K1  periodic mirror / spacer / periodic mirror as straight-line code (the bench kernel)
+//   tmm_sweep_kernel     K3  thickness sweeps: prefix / suffix of the chain once per thread, one sincos (+ exp pair) and
+//                            two 2-term sums per thickness and polarisation, streaming stores
+//   tmm_snell_kernel         refraction mode (PST_FLAG_SNELL);  field_amplitudes_kernel: (A_j, B_j) per layer
+//   tmm_chain_f32_kernel     optional fp32 chain (pst_f32.cuh)
+//   find_peaks_kernel, polariton_branches_kernel, fit_two_lorentzians_kernel (pst_fit.cuh)
+//                            fused spectral reductions of the notebooks (scipy find_peaks semantics; joint two-Lorentzian
+//                            Levenberg-Marquardt fit)
 //   layer_matrices_kernel    [D, P, D^-1, M] per wavelength          (tm.py:190-305)
+//   propagation_kernel, wavenumbers_kernel, chain_matrices_kernel, fresnel_kernel, interface_matrix_kernel
+//                            the remaining per-method entry points of the drop-in API (tm.py:172-234, 559-568, 730-751)
 //   t_r_kernel               (T, R) from caller-supplied matrices    (tm.py:464-514)
 //
 // Model: with phi = kx d, a = n cos(theta) (s) or n / cos(theta) (p),
