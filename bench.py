@@ -553,6 +553,7 @@ def run_ours(args):
     cx.fp64_peak = eng.fp64_peak_tflops(8192)
 
     flags = (16 if args.no_layer_cse else 0) | (128 if args.no_periodic_power else 0)  # PST_FLAG_NO_LAYER_CSE / _NO_PERIODIC_POWER
+    flags |= 2048 if args.no_shape_fastpath else 0  # PST_FLAG_NO_SHAPE_FASTPATH
     flags |= 512 if args.fp32 else 0  # PST_FLAG_FP32 (optional mode; the default and every reported headline number is fp64)
 
     # ---- headline: K timed steps, CUDA events on the launching stream, L2 flushed between steps (outputs are also
@@ -896,6 +897,8 @@ def main():
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained segment")
     ap.add_argument("--no-ablation", action="store_true")
     ap.add_argument("--no-layer-cse", action="store_true", help="ablation: rebuild every layer matrix (PST_FLAG_NO_LAYER_CSE)")
+    ap.add_argument("--no-shape-fastpath", action="store_true",
+                    help="ablation: mirror/spacer/mirror programs through the typed kernel's op interpreter (PST_FLAG_NO_SHAPE_FASTPATH)")
     ap.add_argument("--fp32", action="store_true", help="optional fp32 mode (PST_FLAG_FP32): fp64 phase, fp32 chain, <= 1e-5")
     ap.add_argument("--no-periodic-power", action="store_true",
                     help="ablation: apply repeated lossless pairs layer by layer (PST_FLAG_NO_PERIODIC_POWER)")
