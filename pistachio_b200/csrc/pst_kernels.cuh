@@ -44,6 +44,16 @@ struct LayerEntry {  // 16 bytes: one LDS.128 / LDG.128 per layer
   int type;  // index into the per-thread layer-matrix cache (typed path); -1 when unused
 };
 
+// one 128-bit load per layer entry (the compiler otherwise fetches d, mat and type with three loads where they are used)
+__device__ __forceinline__ LayerEntry load_entry(const LayerEntry* p) {
+  const int4 raw = *reinterpret_cast<const int4*>(p);
+  LayerEntry e;
+  e.d = __hiloint2double(raw.y, raw.x);
+  e.mat = raw.z;
+  e.type = raw.w;
+  return e;
+}
+
 constexpr int kMaxTypes = 8;        // distinct (material, thickness) pairs the typed path caches per thread
 constexpr int kTypeRecBytes = 80;   // one cached layer matrix: 10 doubles (complex form) or 5 (real form); the
                                     // power-of-two exponents of all types follow the records as ints
@@ -419,12 +429,20 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
   if constexpr (SEG) init_identity<NPOL>(st);
   else init_exit_columns<NPOL, NC>(st, exit_row.nr, exit_row.ni, ct, prm.pol_first);
 
-  // ---- iteration over this thread's layers j_hi-1 .. j_lo: apply(entry, j) per layer, rescale() every kRenormEvery layers
+  // Rescaling interval from the grid-wide growth bound (prep_kernel; the typed kernel's rule): one layer multiplies
+  // max|v| by at most 2^lg, so 900 / lg layers after a rescale cannot leave the fp64 range -- ordinary stacks of a
+  // hundred layers rescale once, at the end, instead of every kRenormEvery layers (rescaling is an exact power of two:
+  // no result bit depends on where it happens).  Block-uniform: it sets trip counts.
+  const unsigned growth_word = __ldg(prm.lossy_word);
+  const int lg_layer = growth_log2(growth_E_of_word(growth_word), (growth_word >> 31) != 0u);
+  const int every = max(kRenormEvery, min(1024, __float2int_rz(899.5f * __frcp_rn((float)lg_layer)))) & ~(kRenormEvery - 1);
+
+  // ---- iteration over this thread's layers j_hi-1 .. j_lo: apply(entry, j) per layer, rescale() every `every` layers
   auto for_each_layer = [&](auto UNROLLED, auto&& apply, auto&& apply2, auto&& rescale) {
     if constexpr (!STREAM) {
       int j = j_hi - 1;
       while (j >= j_lo) {
-        const int j_stop = max(j - kRenormEvery, j_lo - 1);
+        const int j_stop = max(j - every, j_lo - 1);
         for (; j - 1 > j_stop; j -= 2) apply2(lay + j, j, std::integral_constant<int, 2>{});  // layers j, j - 1
         if (j > j_stop) {
           apply(lay[j], j);
@@ -464,6 +482,7 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
                    (uint32_t)bytes, &s_sbar[warp][k & 1]);
       };
       issue(0);
+      int since = 0;  // layers (rounded up to batches) applied since the last rescale
       for (int k = 0; k < n_chunks; ++k) {
         if (k + 1 < n_chunks) issue(k + 1);
         mbar_wait(&s_sbar[warp][k & 1], (uint32_t)((k >> 1) & 1));
@@ -476,15 +495,16 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
 #pragma unroll kK2Unroll
             for (int i = 0; i < kRenormEvery; i += kK2Group)  // kK2Group layers at a time: their sincos chains interleave
               apply2(top - (b0 + i), j_top - (b0 + i), std::integral_constant<int, kK2Group>{});
-            rescale();
           } else if (left > b0) {
             const int end = min(left, b0 + kRenormEvery);
             for (int i = b0; i < end; ++i) apply(top[-i], j_top - i);
-            rescale();
           }
+          since += kRenormEvery;
+          if (since >= every) { rescale(); since = 0; }  // block-uniform
         }
         __syncwarp();  // every lane is done with this buffer before chunk k + 2 overwrites it
       }
+      rescale();  // the segment product leaves normalised: the ordered combine multiplies products
     }
   };
 
@@ -597,7 +617,7 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
                      if constexpr (N == 2) {
                        // two lossless neighbours (block-uniform: the flag is the material's): their sincos chains share a
                        // basic block under one joint range test, then the two ordered steps
-                       const LayerEntry le0 = first[0], le1 = first[-1];
+                       const LayerEntry le0 = load_entry(first), le1 = load_entry(first - 1);
                        if (le0.type == 0 && le1.type == 0) {
                          double q0, n0, in0, q1, n1, in1, sx0, cx0, sx1, cx1;
                          opt_row_real(le0.mat, q0, n0, in0);
