@@ -722,6 +722,12 @@ def run_ours(args):
         except Exception as e:
             configs["c5_full"] = {"error": repr(e)[:300]}
         torch.cuda.empty_cache()
+        # configs[2] at FULL size (5.24e10 points, chunked): strong scaling, R/T/A to HBM and T + fused peak search
+        try:
+            configs["c3_full"] = c3_full_size(cx, pdist)
+        except Exception as e:
+            configs["c3_full"] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
 
     if rank != 0:
         return
@@ -882,6 +888,61 @@ def c5_full_size(cx: Ctx, pdist):
         except Exception as e:
             res[tag] = {"unavailable": repr(e)[:200]}
     return res
+
+
+def c3_full_size(cx: Ctx, pdist, chunk: int = 512):
+    """BASELINE configs[2] at FULL size: 1e5 cavity thicknesses x 4096 wavelengths x 64 angles x s/p = 5.24e10 spectral
+    points, strong scaling (the thickness axis is cut over the ranks, no communication).  The result would be 1.26 TB of
+    R, T, A, so the sweep runs in chunks of `chunk` thicknesses whose buffers are reused: once writing R, T, A to HBM
+    (with the path's properties checked on every value in the warm-up pass), once in the form the reference's
+    notebooks consume it -- T only, fused with the device peak search (pst_find_peaks, "Cavity Length Determiner")."""
+    torch, dist, eng, rank, world = cx.torch, cx.dist, cx.eng, cx.rank, cx.world
+    from pistachio_b200 import workloads as wk
+
+    n_d, pols = 100000, ("s-wave", "p-wave")
+    w = wk.c3_polariton(n_d=n_d, n_wl=4096, n_theta=64)
+    lo, hi = pdist.shard_bounds(n_d, world, rank)
+    prep = eng.prepare_workload(w)
+    d_all = prep["sweep_d"]
+    out = {k: torch.empty((chunk, 2, 4096, 64), dtype=torch.float64, device=eng.device) for k in ("R", "T", "A")}
+    nu = 1.0e4 / prep["wl"]
+    bad = torch.zeros((), dtype=torch.int64, device=eng.device)
+    peaks = torch.zeros((), dtype=torch.int64, device=eng.device)
+
+    def sub(i0, i1):
+        p = dict(prep)
+        p["sweep_d"] = d_all[i0:i1]
+        return p, {k: v[:i1 - i0] for k, v in out.items()}
+
+    def pass_rta(check=False):
+        for i0 in range(lo, hi, chunk):
+            p, o = sub(i0, min(i0 + chunk, hi))
+            eng.eval_prepared(p, pols=pols, out=o)
+            if check:
+                bad.add_(((o["A"] != (1.0 - o["R"]) - o["T"]) | (o["R"] < 0) | (o["R"] > 1) | (o["T"] < 0)).sum())
+
+    def pass_fused():
+        for i0 in range(lo, hi, chunk):
+            p, o = sub(i0, min(i0 + chunk, hi))
+            res = eng.eval_prepared(p, pols=pols, want=("T",), out={"T": o["T"]})
+            _, _, cnt, _ = eng.find_peaks(res.T, height=0.01, distance=20, max_peaks=32, axis=nu, reverse=True)
+            peaks.add_(cnt.clamp_min(0).sum())
+
+    pass_rta(check=True)  # warm-up + properties
+    ms_rta = cx.time_steps(pass_rta, 1, flush=False) * 1e3
+    pass_fused()
+    peaks.zero_()
+    ms_fused = cx.time_steps(pass_fused, 1, flush=False) * 1e3
+    if world > 1:
+        dist.all_reduce(bad)
+        dist.all_reduce(peaks)
+    pts = n_d * 2 * 4096 * 64
+    return {"workload": f"configs[2] polariton cavity-length sweep at full size: {n_d} d x 4096 wl x 64 theta x s/p = {pts:.3e} points",
+            "scaling": "strong", "n_gpus": world, "chunk_thicknesses": chunk,
+            "R_T_A_to_hbm": {"ms": ms_rta, "points_per_s": pts / (ms_rta / 1e3),
+                             "hbm_store_GBps_per_gpu": 24.0 * pts / world / (ms_rta / 1e3) / 1e9},
+            "T_plus_fused_peak_search": {"ms": ms_fused, "points_per_s": pts / (ms_fused / 1e3), "peaks_found": int(peaks.item())},
+            "property_violations": int(bad.item())}
 
 
 def main():

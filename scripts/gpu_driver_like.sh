@@ -18,6 +18,8 @@ print('sustained', d.get('sustained'))
 for k, v in (d.get('configs') or {}).items():
     if 'error' in v:
         print(k, 'ERROR', v['error']); continue
+    if k == 'c3_full':
+        print(k, 'R,T,A %.4g pts/s (%.1f ms)' % (v['R_T_A_to_hbm']['points_per_s'], v['R_T_A_to_hbm']['ms']), 'fused %.4g pts/s (%.1f ms)' % (v['T_plus_fused_peak_search']['points_per_s'], v['T_plus_fused_peak_search']['ms']), 'violations', v['property_violations']); continue
     rf = v.get('roofline') or {}
     print(k, '%.4g pts/s' % v.get('value', v.get('points_per_s_compute', 0)), 'ms', v.get('ms_per_step', v.get('compute_ms')), rf.get('bound'), rf.get('frac'))
 print('ablation', {k: v['value'] for k, v in (d.get('ablation') or {}).items() if isinstance(v, dict)})
