@@ -890,10 +890,11 @@ def c5_full_size(cx: Ctx, pdist):
     return res
 
 
-def c3_full_size(cx: Ctx, pdist, chunk: int = 512):
+def c3_full_size(cx: Ctx, pdist, chunk: int = 2048):
     """BASELINE configs[2] at FULL size: 1e5 cavity thicknesses x 4096 wavelengths x 64 angles x s/p = 5.24e10 spectral
     points, strong scaling (the thickness axis is cut over the ranks, no communication).  The result would be 1.26 TB of
-    R, T, A, so the sweep runs in chunks of `chunk` thicknesses whose buffers are reused: once writing R, T, A to HBM
+    R, T, A, so the sweep runs in chunks of `chunk` thicknesses whose buffers are reused (2048 thicknesses = 8.6 GB per
+    array: 262 144 spectra per peak-search launch keep that kernel at the HBM rate; 512 left it at half): once writing R, T, A to HBM
     (with the path's properties checked on every value in the warm-up pass), once in the form the reference's
     notebooks consume it -- T only, fused with the device peak search (pst_find_peaks, "Cavity Length Determiner")."""
     torch, dist, eng, rank, world = cx.torch, cx.dist, cx.eng, cx.rank, cx.world

@@ -1332,14 +1332,17 @@ struct SweepConsts {
   int kfix[NPOL];
 };
 
-template <int NPOL, bool LOSSLESS, bool FAST>
+// FAST: 0 = general stores (peers, multicast, plane duplication, any other subset); otherwise the mask of LOCAL arrays
+// the loop writes with streaming stores and untested cursors -- 7 = R, T, A; 3 = R, T (what tm.py returns); 2 = T only
+// (sweeps feeding the fused peak search: through the general path a T-only chunk ran 30 % SLOWER than writing all three)
+template <int NPOL, bool LOSSLESS, int FAST>
 __device__ __forceinline__ void sweep_loop(const GridParams& prm, const SweepConsts<NPOL>& k, int s_begin, int s_end,
                                            unsigned p) {
   const size_t plane = (size_t)prm.points;
   const size_t o0 = (size_t)s_begin * NPOL * plane + (size_t)p;
-  double* pR = FAST ? prm.R + o0 : nullptr;
-  double* pT = FAST ? prm.T + o0 : nullptr;
-  double* pA = FAST ? prm.A + o0 : nullptr;
+  double* pR = (FAST & 1) ? prm.R + o0 : nullptr;
+  double* pT = (FAST & 2) ? prm.T + o0 : nullptr;
+  double* pA = (FAST & 4) ? prm.A + o0 : nullptr;
   double d = __ldg(prm.sweep_d + s_begin);
   for (int sw = s_begin; sw < s_end; ++sw) {
     const double d_next = __ldg(prm.sweep_d + min(sw + 1, s_end - 1));  // next thickness in flight during this one
@@ -1375,11 +1378,10 @@ __device__ __forceinline__ void sweep_loop(const GridParams& prm, const SweepCon
       const double iden = recip_nr(den);
       const double R = num * iden;
       const double T = scale_sq(k.det_re * iden, -(k.kfix[pp] + sc));
-      if constexpr (FAST) {
-        __stcs(pR, R);
-        __stcs(pT, T);
-        __stcs(pA, (1.0 - R) - T);
-        pR += plane; pT += plane; pA += plane;
+      if constexpr (FAST != 0) {
+        if constexpr ((FAST & 1) != 0) { __stcs(pR, R); pR += plane; }
+        if constexpr ((FAST & 2) != 0) { __stcs(pT, T); pT += plane; }
+        if constexpr ((FAST & 4) != 0) { __stcs(pA, (1.0 - R) - T); pA += plane; }
       } else {
         store_point<true>(prm, ((size_t)sw * (NPOL << prm.pol_dup) + pp) * plane + (size_t)p, R, T, (1.0 - R) - T);
       }
@@ -1515,14 +1517,15 @@ tmm_sweep_kernel(const GridParams prm, int n_sweep, int sweeps_per_block) {
   for (int pp = 0; pp < NPOL; ++pp) {
     kc.al0[pp] = al0[pp]; kc.al1[pp] = al1[pp]; kc.be0[pp] = be0[pp]; kc.be1[pp] = be1[pp]; kc.kfix[pp] = kfix[pp];
   }
-  const bool fast = prm.R && prm.T && prm.A && prm.n_peers == 0 && !(prm.flags & kFlagMulticastOut) && !prm.pol_dup;
-  if (s_lossless) {
-    if (fast) sweep_loop<NPOL, true, true>(prm, kc, s_begin, s_end, p);
-    else sweep_loop<NPOL, true, false>(prm, kc, s_begin, s_end, p);
-  } else {
-    if (fast) sweep_loop<NPOL, false, true>(prm, kc, s_begin, s_end, p);
-    else sweep_loop<NPOL, false, false>(prm, kc, s_begin, s_end, p);
-  }
+  const bool local = prm.n_peers == 0 && !(prm.flags & kFlagMulticastOut) && !prm.pol_dup;
+  const int mask = local ? ((prm.R ? 1 : 0) | (prm.T ? 2 : 0) | (prm.A ? 4 : 0)) : 0;
+#define PST_SL(LOSSLESS)                                                              \
+  if (mask == 7) sweep_loop<NPOL, LOSSLESS, 7>(prm, kc, s_begin, s_end, p);           \
+  else if (mask == 3) sweep_loop<NPOL, LOSSLESS, 3>(prm, kc, s_begin, s_end, p);      \
+  else if (mask == 2) sweep_loop<NPOL, LOSSLESS, 2>(prm, kc, s_begin, s_end, p);      \
+  else sweep_loop<NPOL, LOSSLESS, 0>(prm, kc, s_begin, s_end, p);
+  if (s_lossless) { PST_SL(true) } else { PST_SL(false) }
+#undef PST_SL
 }
 
 // ----------------------------------------------------------------------- per-layer matrices (API parity)
