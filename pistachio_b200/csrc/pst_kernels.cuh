@@ -965,7 +965,11 @@ __device__ __noinline__ void cavity_lossy_mirrors(const double* rv, double dA, d
 
 // MODE: 0 lossless spacer, 1 absorbing spacer, 2 absorbing mirror layers (cold);  RESC: rescaled powering;
 // MIRRORED: the second mirror is the mirror image of the first (only looked at when the pair counts agree)
-template <int NPOL, bool ROW, int MODE, bool RESC, bool MIRRORED>
+// NOTEST: the block's three phases are bounded inside sincos' fast range for every angle (|q d| < 2^28 with |cos| <= 1;
+// decided once per block from the staged row), so the tile loop carries no range tests and -- what matters more -- no call
+// to the out-of-line Payne-Hanek path, whose calling convention made the compiler reload every constant after each of
+// the three sincos
+template <int NPOL, bool ROW, int MODE, bool RESC, bool MIRRORED, bool NOTEST = false>
 __device__ __forceinline__ void cavity_tiles(const GridParams& prm, const CavityPlan& cp, unsigned s_base, unsigned lossy_mask,
                                              bool mid_rescale, bool calm_skips_rescale) {
   const unsigned npts = (unsigned)prm.points, nth = (unsigned)prm.n_theta;
@@ -1031,7 +1035,7 @@ __device__ __forceinline__ void cavity_tiles(const GridParams& prm, const Cavity
         const double2 q = PST_V2(0);
         const double xA = layer_phase(q.x, ct, cp.d[0]), xB = layer_phase(q.y, ct, cp.d[1]);
         double sA, cA, sB, cB;
-        if (sincos_in_fast_range(xA) && sincos_in_fast_range(xB)) {
+        if (NOTEST || (sincos_in_fast_range(xA) && sincos_in_fast_range(xB))) {
           sincos_core(xA, sA, cA);
           sincos_core(xB, sB, cB);
         } else {
@@ -1060,7 +1064,8 @@ __device__ __forceinline__ void cavity_tiles(const GridParams& prm, const Cavity
       {
         const double2 qd = PST_V2(6), nc = PST_V2(8);
         double sC, cC;
-        sincos_fast(layer_phase(qd.x, ct, qd.y), sC, cC);
+        if constexpr (NOTEST) sincos_core(layer_phase(qd.x, ct, qd.y), sC, cC);
+        else sincos_fast(layer_phase(qd.x, ct, qd.y), sC, cC);
         if constexpr (MODE == 0) {
           apply_real_layer<NPOL, 1>(st, finish_real_layer<NPOL>(sC, cC, nc.x, nc.y, ct, ict, prm.pol_first));
         } else {
@@ -1160,8 +1165,17 @@ tmm_cavity_kernel(const GridParams prm, const CavityPlan cp) {
   const int E = growth_E_of_word(lossy_mask);
   const bool calm_skips = !mid_rescale && 2 * (cp.k1 + cp.k2) + cp.hb1 + cp.hb2 + 5 * lg + 2 * E + 9 <= 500;
 #define PST_CT(MODE, RESC, MIR) cavity_tiles<NPOL, ROW, MODE, RESC, MIR>(prm, cp, s_base, lossy_mask, mid_rescale, calm_skips)
+#define PST_CTN(MODE, MIR) cavity_tiles<NPOL, ROW, MODE, false, MIR, true>(prm, cp, s_base, lossy_mask, mid_rescale, calm_skips)
+  bool notest = false;
+  if constexpr (ROW) {  // block-uniform: the staged row holds q_A, q_B, q_C.re and d_C of this wavelength
+    const double bound = fmax(fmax(fabs(s_row[0] * cp.d[0]), fabs(s_row[1] * cp.d[1])), fabs(s_row[6] * s_row[7]));
+    notest = bound < 268435456.0;  // 2^28: |cos(theta)| <= 1, a factor four of slack; NaN fails
+  }
   if (lossyAB) PST_CT(2, false, false);
-  else if (!resc) {
+  else if (!resc && notest) {
+    if (!lossyC) { if (mir) PST_CTN(0, true); else PST_CTN(0, false); }
+    else { if (mir) PST_CTN(1, true); else PST_CTN(1, false); }
+  } else if (!resc) {
     if (!lossyC) { if (mir) PST_CT(0, false, true); else PST_CT(0, false, false); }
     else { if (mir) PST_CT(1, false, true); else PST_CT(1, false, false); }
   } else {
@@ -1169,6 +1183,7 @@ tmm_cavity_kernel(const GridParams prm, const CavityPlan cp) {
     else { if (mir) PST_CT(1, true, true); else PST_CT(1, true, false); }
   }
 #undef PST_CT
+#undef PST_CTN
 }
 
 // ------------------------------------------------------------------------------------ refraction mode

@@ -344,6 +344,14 @@ def test_cavity_kernel_pair_counts_and_rescale_vote(eng):
         for key in ("R", "T", "A"):
             assert np.array_equal(a[key], b[key]), (k1, k2, key)
         assert np.isfinite(a["R"]).all() and np.isfinite(a["T"]).all()
+    # a spacer of 2e8 um (phase ~ 2e9 rad): the block's phase bound fails, the tile loop with range tests runs and the spacer's
+    # sincos takes the Payne-Hanek reduction -- still the interpreter's bits
+    cols, lm, ld = pc.quarter_wave_stack(9, wl, n_hi=2.3, n_lo=1.38, spacer=(1.5 + 0j, 2.0e8))
+    a = eng.eval_grid(wl, th, cols.real, cols.imag, lm, ld, POLS).numpy()
+    b = eng.eval_grid(wl, th, cols.real, cols.imag, lm, ld, POLS, flags=NOFAST).numpy()
+    for key in ("R", "T", "A"):
+        assert np.array_equal(a[key], b[key]), ("thick spacer", key)
+    assert np.isfinite(a["R"]).all()
     sel = np.array([0, 37, 149])
     for n_hi, n_lo, pairs in ((3.9, 1.0, 12), (1.46, 1.45, 12)):
         wl = pc.band_edge_wavelengths(n_hi, n_lo, 24, 6, lo=0.7, hi=1.4)
