@@ -113,18 +113,22 @@ PST_HD CplxLayer<NPOL> finish_cplx_layer(double sx, double cx, double y, const O
   return m;
 }
 
-template <int NPOL>
+// IN_RANGE: the caller has bounded the phase inside sincos' fast range (|x| < 2^30): no range test and no call to the
+// out-of-line large-argument path -- a call inside a layer loop makes the compiler reload every constant after it
+template <int NPOL, bool IN_RANGE = false>
 PST_HD RealLayer<NPOL> build_real_layer(double qr, double nr, double inr, double d, double ct, double ict,
                                         int pol_first) {
   double sx, cx;
-  sincos_fast(layer_phase(qr, ct, d), sx, cx);
+  if constexpr (IN_RANGE) sincos_core(layer_phase(qr, ct, d), sx, cx);
+  else sincos_fast(layer_phase(qr, ct, d), sx, cx);
   return finish_real_layer<NPOL>(sx, cx, nr, inr, ct, ict, pol_first);
 }
 
-template <int NPOL>
+template <int NPOL, bool IN_RANGE = false>
 PST_HD CplxLayer<NPOL> build_cplx_layer(const OptRow& o, double d, double ct, double ict, int pol_first) {
   double sx, cx;
-  sincos_fast(layer_phase(o.qr, ct, d), sx, cx);
+  if constexpr (IN_RANGE) sincos_core(layer_phase(o.qr, ct, d), sx, cx);
+  else sincos_fast(layer_phase(o.qr, ct, d), sx, cx);
   return finish_cplx_layer<NPOL>(sx, cx, layer_phase(o.qi, ct, d), o, ct, ict, pol_first);
 }
 

@@ -549,7 +549,8 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
           std::true_type{},
           [&](const LayerEntry& le, int j) {
             double nr, inr, sx, cx;
-            sincos_fast(phase_of(le, j, nr, inr), sx, cx);
+            if constexpr (decltype(NOTEST)::value) sincos_core(phase_of(le, j, nr, inr), sx, cx);
+            else sincos_fast(phase_of(le, j, nr, inr), sx, cx);
             step(sx, cx, nr, inr);
           },
           [&](const LayerEntry* first, int j_first, auto N_) {
@@ -599,18 +600,19 @@ tmm_chain_kernel(const GridParams prm) {          // BASELINE configs[3] (16 384
     }
   }
   if (!done) {
+    auto run = [&](auto NOTEST) {
+    constexpr bool IN_RANGE = decltype(NOTEST)::value;  // the warp's phase bound covers every layer: no call in the loop
     auto apply_any = [&](const LayerEntry& le, int j) {
           const double d = (!STAGE_LAYERS && j == prm.sweep_layer) ? d_sweep : le.d;
           const int lossy = le.type;  // untyped launches get the flagged layer list (prep_kernel)
           if (lossy == 0) {
             double qr, nr, inr;
             opt_row_real(le.mat, qr, nr, inr);
-            apply_real_layer<NPOL, NC>(st, build_real_layer<NPOL>(qr, nr, inr, d, ct, ict, prm.pol_first));
+            apply_real_layer<NPOL, NC>(st, build_real_layer<NPOL, IN_RANGE>(qr, nr, inr, d, ct, ict, prm.pol_first));
           } else {
-            apply_cplx_layer<NPOL, NC>(st, build_cplx_layer<NPOL>(opt_row(le.mat), d, ct, ict, prm.pol_first));
+            apply_cplx_layer<NPOL, NC>(st, build_cplx_layer<NPOL, IN_RANGE>(opt_row(le.mat), d, ct, ict, prm.pol_first));
           }
         };
-    auto run = [&](auto NOTEST) {
     for_each_layer(std::false_type{}, apply_any,
                    [&](const LayerEntry* first, int j_first, auto N_) {
                      constexpr int N = decltype(N_)::value;
