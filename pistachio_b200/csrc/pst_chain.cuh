@@ -114,7 +114,7 @@ PST_HD CplxLayer<NPOL> finish_cplx_layer(double sx, double cx, double y, const O
 }
 
 // IN_RANGE: the caller has bounded the phase inside sincos' fast range (|x| < 2^30): no range test and no call to the
-// out-of-line large-argument path -- a call inside a layer loop makes the compiler reload every constant after it
+// out-of-line large-argument path (a possible call inside a layer loop costs a convergence barrier per layer)
 template <int NPOL, bool IN_RANGE = false>
 PST_HD RealLayer<NPOL> build_real_layer(double qr, double nr, double inr, double d, double ct, double ict,
                                         int pol_first) {

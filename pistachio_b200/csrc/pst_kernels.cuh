@@ -968,9 +968,9 @@ __device__ __noinline__ void cavity_lossy_mirrors(const double* rv, double dA, d
 // MODE: 0 lossless spacer, 1 absorbing spacer, 2 absorbing mirror layers (cold);  RESC: rescaled powering;
 // MIRRORED: the second mirror is the mirror image of the first (only looked at when the pair counts agree)
 // NOTEST: the block's three phases are bounded inside sincos' fast range for every angle (|q d| < 2^28 with |cos| <= 1;
-// decided once per block from the staged row), so the tile loop carries no range tests and -- what matters more -- no call
-// to the out-of-line Payne-Hanek path, whose calling convention made the compiler reload every constant after each of
-// the three sincos
+// decided once per block from the staged row), so the tile loop carries no range tests and no call to the out-of-line
+// Payne-Hanek path: a possible call costs a convergence barrier (BSSY/BSYNC) around each sincos and pins the compiler's
+// schedule there (measured: 506 -> 495 instructions per point, 0.1927 -> 0.1869 ms)
 template <int NPOL, bool ROW, int MODE, bool RESC, bool MIRRORED, bool NOTEST = false>
 __device__ __forceinline__ void cavity_tiles(const GridParams& prm, const CavityPlan& cp, unsigned s_base, unsigned lossy_mask,
                                              bool mid_rescale, bool calm_skips_rescale) {
