@@ -162,7 +162,9 @@ typedef struct pst_grid_args {
   const double* wl;        /* [dev] n_wl */
   const double* theta;     /* [dev] n_theta, radians */
   const double* cos_theta; /* [dev] n_theta or NULL.  When given it is used instead of cos(theta[i]) so a host
-                              that already evaluated np.cos (as tm.py:209,270 do) gets the same bits */
+                              that already evaluated np.cos (as tm.py:209,270 do) gets the same bits.  Cosines of real
+                              angles: |cos_theta[i]| <= 1 (the kernels bound the layer phases by |q d| on that basis
+                              when they choose loops without large-argument handling; there is a factor 4 of slack) */
   const double* mat_n;     /* [dev] [n_mat][n_wl] real index on the grid */
   const double* mat_k;     /* [dev] [n_mat][n_wl] extinction coefficient (k > 0 absorbs) */
   const int* layer_mat;    /* [host] n_layers: column of mat_n/mat_k used by each layer */
